@@ -1,0 +1,34 @@
+"""B200-native reduction-operator assembly path of FEniCSx_ii (Π, Πᵀ, ΠᵀMΠ, MΠ).
+
+Exports the reference's names for the hot path (reference ``__init__.py:1-32``); everything
+outside the path (UFL rewriting, form assembly, solver) stays with the reference / dolfinx.
+"""
+
+from .assembly import (
+    assign_LG_map,
+    average_coefficient,
+    restrict_columns,
+    restrict_rows,
+    restrict_rows_and_columns,
+)
+from .interpolation import create_interpolation_matrix
+from .quadrature import Quadrature
+from .restriction_operators import Circle, Disk, MappedRestriction, PointwiseTrace, ReductionOperator
+from .sparse import DeviceCSR, MatrixCSR
+
+__all__ = [
+    "Circle",
+    "DeviceCSR",
+    "Disk",
+    "MappedRestriction",
+    "MatrixCSR",
+    "PointwiseTrace",
+    "Quadrature",
+    "ReductionOperator",
+    "assign_LG_map",
+    "average_coefficient",
+    "create_interpolation_matrix",
+    "restrict_columns",
+    "restrict_rows",
+    "restrict_rows_and_columns",
+]

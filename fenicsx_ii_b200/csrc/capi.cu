@@ -1,0 +1,371 @@
+// extern "C" boundary (include/fxii.h).  No exceptions cross it: every entry point catches,
+// records a thread-local message and returns a negative status.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace fxii {
+void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* cell_nodes, int64_t n_cells,
+                double padding, cudaStream_t s);
+void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr* out, fxii_pi_stats* stats,
+                 bool keep_points);
+void csr_transpose(const fxii_csr* a, cudaStream_t s, fxii_csr* out);
+void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row_end, cudaStream_t s, fxii_csr* out,
+            int64_t* ip_out);
+void csr_scale_rows(fxii_csr* a, const double* d_host, cudaStream_t s);
+void csr_spmv(const fxii_csr* a, const double* u_host, double* y_host, cudaStream_t s);
+}  // namespace fxii
+
+static thread_local std::string g_last_error;
+
+template <typename F>
+static int guarded(F&& f) {
+  try {
+    f();
+    return FXII_OK;
+  } catch (const fxii::Error& e) {
+    g_last_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return FXII_E_INVALID;
+  } catch (...) {
+    g_last_error = "unknown error";
+    return FXII_E_INVALID;
+  }
+}
+
+#define S(stream) reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" {
+
+int fxii_version(void) { return 100; }
+
+const char* fxii_last_error(void) { return g_last_error.c_str(); }
+
+int fxii_device_count(int* n) {
+  return guarded([&] { FXII_CUDA(cudaGetDeviceCount(n)); });
+}
+
+int fxii_set_device(int device) {
+  return guarded([&] { FXII_CUDA(cudaSetDevice(device)); });
+}
+
+int fxii_sm_count(int* n) {
+  return guarded([&] {
+    int dev = 0;
+    FXII_CUDA(cudaGetDevice(&dev));
+    FXII_CUDA(cudaDeviceGetAttribute(n, cudaDevAttrMultiProcessorCount, dev));
+  });
+}
+
+int fxii_mesh_create(const double* x, int64_t n_nodes, const int32_t* cell_nodes, int64_t n_cells, double padding,
+                     void* stream, fxii_mesh** out) {
+  return guarded([&] {
+    FXII_CHECK(x && cell_nodes && out, "null argument");
+    auto* m = new fxii_mesh();
+    try {
+      fxii::mesh_build(m, x, n_nodes, cell_nodes, n_cells, padding, S(stream));
+    } catch (...) {
+      delete m;
+      throw;
+    }
+    *out = m;
+  });
+}
+
+int fxii_mesh_info(const fxii_mesh* m, int64_t* n_cells, int64_t* n_nodes, int64_t* device_bytes, int32_t* max_depth) {
+  return guarded([&] {
+    FXII_CHECK(m, "null mesh");
+    if (n_cells) *n_cells = m->n_cells;
+    if (n_nodes) *n_nodes = m->n_nodes;
+    if (device_bytes) *device_bytes = m->x.bytes() + m->cell_nodes.bytes() + m->cellgeo.bytes() + m->nodes.bytes();
+    if (max_depth) *max_depth = m->max_depth;
+  });
+}
+
+int fxii_mesh_destroy(fxii_mesh* m) {
+  return guarded([&] { delete m; });
+}
+
+int fxii_space_create(fxii_mesh* mesh, const int32_t* dofmap, int32_t nd, int32_t degree, int64_t n_dofs, void* stream,
+                      fxii_space** out) {
+  return guarded([&] {
+    FXII_CHECK(mesh && dofmap && out, "null argument");
+    if (!((degree == 1 && nd == 4) || (degree == 2 && nd == 10)))
+      throw fxii::Error(FXII_E_UNSUPPORTED, "only Lagrange P1 (nd=4) and P2 (nd=10) on affine tetrahedra are supported");
+    auto* s = new fxii_space();
+    s->mesh = mesh;
+    s->nd = nd;
+    s->degree = degree;
+    s->n_dofs = n_dofs;
+    try {
+      s->dofmap.upload(dofmap, (int64_t)nd * mesh->n_cells, S(stream));
+      FXII_CUDA(cudaStreamSynchronize(S(stream)));
+    } catch (...) {
+      delete s;
+      throw;
+    }
+    *out = s;
+  });
+}
+
+int fxii_space_destroy(fxii_space* s) {
+  return guarded([&] { delete s; });
+}
+
+int fxii_rows_create(const double* gx, int64_t n_gnodes, const int32_t* gcells, int64_t n_gcells, const int32_t* cells_k,
+                     int64_t n_cells_k, const double* xref, int32_t nip, const int32_t* row_dofs, int64_t n_rows_total,
+                     int32_t kind, int32_t nq, const double* table, const double* w, const double* radius,
+                     int32_t radius_per_row, void* stream, fxii_rows** out) {
+  return guarded([&] {
+    FXII_CHECK(out && nip >= 1 && n_cells_k >= 0 && n_rows_total >= 0, "bad argument");
+    FXII_CHECK(kind == FXII_OP_TRACE || kind == FXII_OP_CIRCLE || kind == FXII_OP_DISK, "bad operator kind");
+    FXII_CHECK(n_cells_k == 0 || (gx && gcells && cells_k && xref && row_dofs), "null argument");
+    if (kind == FXII_OP_TRACE) nq = 1;
+    else FXII_CHECK(nq >= 1 && table && w && radius, "circle/disk operators need table, w and radius");
+    for (int64_t i = 0; i < n_cells_k; ++i)
+      FXII_CHECK(cells_k[i] >= 0 && cells_k[i] < n_gcells, "cells_k out of range");
+    for (int64_t i = 0; i < 2 * n_gcells; ++i) FXII_CHECK(gcells[i] >= 0 && gcells[i] < n_gnodes, "gamma cell node out of range");
+    auto* r = new fxii_rows();
+    cudaStream_t s = S(stream);
+    try {
+      fxii::init_pool_once();
+      r->kind = kind;
+      r->nq = nq;
+      r->nip = nip;
+      r->n_point_rows = n_cells_k * nip;
+      r->n_rows_total = n_rows_total;
+      r->radius_per_row = radius_per_row;
+      r->gx.upload(gx, 3 * n_gnodes, s);
+      r->gcells.upload(gcells, 2 * n_gcells, s);
+      r->cells_k.upload(cells_k, n_cells_k, s);
+      r->xref.upload(xref, nip, s);
+      r->row_dofs.upload(row_dofs, n_cells_k * nip, s);
+      if (kind != FXII_OP_TRACE) {
+        r->table.upload(table, 3 * (int64_t)nq, s);
+        r->w.upload(w, nq, s);
+        r->radius.upload(radius, radius_per_row ? n_cells_k * nip : 1, s);
+      }
+      FXII_CUDA(cudaStreamSynchronize(s));
+    } catch (...) {
+      delete r;
+      throw;
+    }
+    *out = r;
+  });
+}
+
+int fxii_rows_create_points(const double* points, const double* weights, const double* scales, int64_t n_point_rows,
+                            int32_t nq, const int32_t* row_dofs, int64_t n_rows_total, void* stream, fxii_rows** out) {
+  return guarded([&] {
+    FXII_CHECK(out && nq >= 1 && n_point_rows >= 0, "bad argument");
+    FXII_CHECK(n_point_rows == 0 || (points && weights && scales && row_dofs), "null argument");
+    auto* r = new fxii_rows();
+    cudaStream_t s = S(stream);
+    try {
+      fxii::init_pool_once();
+      r->kind = FXII_OP_POINTS;
+      r->nq = nq;
+      r->nip = 1;
+      r->n_point_rows = n_point_rows;
+      r->n_rows_total = n_rows_total;
+      r->pts_in.upload(points, 3 * n_point_rows * nq, s);
+      r->w_in.upload(weights, n_point_rows * nq, s);
+      r->s_in.upload(scales, n_point_rows, s);
+      r->row_dofs.upload(row_dofs, n_point_rows, s);
+      FXII_CUDA(cudaStreamSynchronize(s));
+    } catch (...) {
+      delete r;
+      throw;
+    }
+    *out = r;
+  });
+}
+
+int fxii_rows_destroy(fxii_rows* r) {
+  return guarded([&] { delete r; });
+}
+
+int fxii_rows_keep_points(fxii_rows* r, int32_t flag) {
+  return guarded([&] {
+    FXII_CHECK(r, "null rows");
+    r->keep_points = flag != 0;
+  });
+}
+
+int fxii_pi_assemble(const fxii_space* space, fxii_rows* rows, void* stream, fxii_csr** out, fxii_pi_stats* stats) {
+  fxii_csr* c = nullptr;
+  int rc = guarded([&] {
+    FXII_CHECK(space && rows && out, "null argument");
+    c = new fxii_csr();
+    fxii::pi_assemble(space, rows, S(stream), c, stats, rows->keep_points);
+  });
+  if (rc == FXII_OK || rc == FXII_E_NOT_FOUND) {
+    // on NOT_FOUND the matrix is still returned (entries of unfound points are zero) so that a
+    // caller can inspect the diagnostics; the status tells it apart
+    *out = c;
+  } else {
+    delete c;
+    if (out) *out = nullptr;
+  }
+  return rc;
+}
+
+int fxii_rows_download_diag(const fxii_rows* rows, int32_t* cell, uint8_t* n_colliding, double* points, void* stream) {
+  return guarded([&] {
+    FXII_CHECK(rows, "null rows");
+    cudaStream_t s = S(stream);
+    const int64_t Np = rows->n_point_rows * rows->nq;
+    FXII_CHECK(rows->cell.n == Np, "no assembly has run on this rows handle");
+    if (cell && Np) FXII_CUDA(cudaMemcpyAsync(cell, rows->cell.p, sizeof(int32_t) * (size_t)Np, cudaMemcpyDeviceToHost, s));
+    if (n_colliding && Np) FXII_CUDA(cudaMemcpyAsync(n_colliding, rows->ncoll.p, (size_t)Np, cudaMemcpyDeviceToHost, s));
+    if (points) {
+      FXII_CHECK(rows->points.n == 3 * Np, "points were not kept (fxii_rows_keep_points)");
+      if (Np) FXII_CUDA(cudaMemcpyAsync(points, rows->points.p, sizeof(double) * 3 * (size_t)Np, cudaMemcpyDeviceToHost, s));
+    }
+    FXII_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int fxii_rows_download_coo(const fxii_rows* rows, int32_t* cols, double* vals, void* stream) {
+  return guarded([&] {
+    FXII_CHECK(rows, "null rows");
+    cudaStream_t s = S(stream);
+    const int64_t E = rows->n_point_rows * rows->nq * rows->nd;
+    FXII_CHECK(rows->coo_cols.n == E && rows->nd > 0, "no assembly has run on this rows handle");
+    if (cols && E) FXII_CUDA(cudaMemcpyAsync(cols, rows->coo_cols.p, sizeof(int32_t) * (size_t)E, cudaMemcpyDeviceToHost, s));
+    if (vals && E) FXII_CUDA(cudaMemcpyAsync(vals, rows->coo_vals.p, sizeof(double) * (size_t)E, cudaMemcpyDeviceToHost, s));
+    FXII_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+static fxii_csr* csr_from(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                          const double* values, cudaMemcpyKind kind, cudaStream_t s) {
+  FXII_CHECK(n_rows >= 0 && n_cols >= 0 && nnz >= 0 && indptr, "bad CSR arguments");
+  fxii::init_pool_once();
+  auto* c = new fxii_csr();
+  try {
+    c->n_rows = n_rows;
+    c->n_cols = n_cols;
+    c->nnz = nnz;
+    c->indptr.alloc(n_rows + 1, s);
+    c->indices.alloc(nnz, s);
+    c->values.alloc(nnz, s);
+    FXII_CUDA(cudaMemcpyAsync(c->indptr.p, indptr, sizeof(int64_t) * (size_t)(n_rows + 1), kind, s));
+    if (nnz) {
+      FXII_CUDA(cudaMemcpyAsync(c->indices.p, indices, sizeof(int32_t) * (size_t)nnz, kind, s));
+      FXII_CUDA(cudaMemcpyAsync(c->values.p, values, sizeof(double) * (size_t)nnz, kind, s));
+    }
+    FXII_CUDA(cudaStreamSynchronize(s));
+  } catch (...) {
+    delete c;
+    throw;
+  }
+  return c;
+}
+
+int fxii_csr_upload(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                    const double* values, void* stream, fxii_csr** out) {
+  return guarded([&] {
+    FXII_CHECK(out, "null out");
+    *out = csr_from(n_rows, n_cols, nnz, indptr, indices, values, cudaMemcpyHostToDevice, S(stream));
+  });
+}
+
+int fxii_csr_from_device(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* indptr_dev,
+                         const int32_t* indices_dev, const double* values_dev, void* stream, fxii_csr** out) {
+  return guarded([&] {
+    FXII_CHECK(out, "null out");
+    *out = csr_from(n_rows, n_cols, nnz, indptr_dev, indices_dev, values_dev, cudaMemcpyDeviceToDevice, S(stream));
+  });
+}
+
+int fxii_csr_info(const fxii_csr* a, int64_t* n_rows, int64_t* n_cols, int64_t* nnz) {
+  return guarded([&] {
+    FXII_CHECK(a, "null csr");
+    if (n_rows) *n_rows = a->n_rows;
+    if (n_cols) *n_cols = a->n_cols;
+    if (nnz) *nnz = a->nnz;
+  });
+}
+
+int fxii_csr_device_ptrs(const fxii_csr* a, void** indptr_dev, void** indices_dev, void** values_dev) {
+  return guarded([&] {
+    FXII_CHECK(a, "null csr");
+    if (indptr_dev) *indptr_dev = a->indptr.p;
+    if (indices_dev) *indices_dev = a->indices.p;
+    if (values_dev) *values_dev = a->values.p;
+  });
+}
+
+int fxii_csr_download(const fxii_csr* a, int64_t* indptr, int32_t* indices, double* values, void* stream) {
+  return guarded([&] {
+    FXII_CHECK(a, "null csr");
+    cudaStream_t s = S(stream);
+    if (indptr) FXII_CUDA(cudaMemcpyAsync(indptr, a->indptr.p, sizeof(int64_t) * (size_t)(a->n_rows + 1), cudaMemcpyDeviceToHost, s));
+    if (indices && a->nnz) FXII_CUDA(cudaMemcpyAsync(indices, a->indices.p, sizeof(int32_t) * (size_t)a->nnz, cudaMemcpyDeviceToHost, s));
+    if (values && a->nnz) FXII_CUDA(cudaMemcpyAsync(values, a->values.p, sizeof(double) * (size_t)a->nnz, cudaMemcpyDeviceToHost, s));
+    FXII_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int fxii_csr_destroy(fxii_csr* a) {
+  return guarded([&] { delete a; });
+}
+
+int fxii_csr_transpose(const fxii_csr* a, void* stream, fxii_csr** out) {
+  return guarded([&] {
+    FXII_CHECK(a && out, "null argument");
+    auto* c = new fxii_csr();
+    try {
+      fxii::csr_transpose(a, S(stream), c);
+      FXII_CUDA(cudaStreamSynchronize(S(stream)));
+    } catch (...) {
+      delete c;
+      throw;
+    }
+    *out = c;
+  });
+}
+
+int fxii_spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row_end, void* stream, fxii_csr** out,
+                int64_t* ip) {
+  return guarded([&] {
+    FXII_CHECK(a && b && out, "null argument");
+    auto* c = new fxii_csr();
+    try {
+      fxii::spgemm(a, b, row_begin, row_end, S(stream), c, ip);
+      FXII_CUDA(cudaStreamSynchronize(S(stream)));
+    } catch (...) {
+      delete c;
+      throw;
+    }
+    *out = c;
+  });
+}
+
+int fxii_csr_scale_rows(fxii_csr* a, const double* d, void* stream) {
+  return guarded([&] {
+    FXII_CHECK(a && d, "null argument");
+    fxii::csr_scale_rows(a, d, S(stream));
+  });
+}
+
+int fxii_csr_spmv(const fxii_csr* a, const double* u, double* y, void* stream) {
+  return guarded([&] {
+    FXII_CHECK(a && u && y, "null argument");
+    fxii::csr_spmv(a, u, y, S(stream));
+  });
+}
+
+int fxii_csr_spmv_t(const fxii_csr* a, const double* u, double* y, void* stream) {
+  return guarded([&] {
+    FXII_CHECK(a && u && y, "null argument");
+    fxii_csr t;
+    fxii::csr_transpose(a, S(stream), &t);
+    fxii::csr_spmv(&t, u, y, S(stream));
+  });
+}
+
+}  // extern "C"

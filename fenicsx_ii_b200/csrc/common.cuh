@@ -1,0 +1,172 @@
+// Shared helpers for the fxii CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/fxii.h"
+
+namespace fxii {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define FXII_CUDA(expr)                                                                     \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      throw ::fxii::Error(FXII_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + \
+                                           " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+
+#define FXII_CHECK(cond, msg)                                       \
+  do {                                                              \
+    if (!(cond)) throw ::fxii::Error(FXII_E_INVALID, std::string(msg)); \
+  } while (0)
+
+inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// grid for a grid-stride kernel: whole waves of the SM count, capped by the work available
+inline int grid_for(int64_t work_items, int block, int blocks_per_sm) {
+  int64_t need = (work_items + block - 1) / block;
+  int64_t cap = (int64_t)num_sms() * blocks_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// stream-ordered device buffer
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  int64_t n = 0;
+  cudaStream_t st = nullptr;  // stream the buffer was allocated on; frees are ordered on it
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), st(o.st) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; st = o.st; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  void alloc(int64_t count, cudaStream_t s) {
+    release();
+    n = count;
+    st = s;
+    if (count > 0) FXII_CUDA(cudaMallocAsync((void**)&p, sizeof(T) * (size_t)count, s));
+  }
+  void upload(const T* host, int64_t count, cudaStream_t s) {
+    alloc(count, s);
+    if (count > 0) FXII_CUDA(cudaMemcpyAsync(p, host, sizeof(T) * (size_t)count, cudaMemcpyHostToDevice, s));
+  }
+  void release() {
+    if (p) cudaFreeAsync(p, st);
+    p = nullptr;
+    n = 0;
+  }
+  int64_t bytes() const { return (int64_t)sizeof(T) * n; }
+  ~DevBuf() { release(); }
+};
+
+void init_pool_once();
+
+// ---- handle layouts -------------------------------------------------------------------------
+struct alignas(16) BvhNode {  // 64 B: both child boxes live in the parent
+  float lo_l[3], hi_l[3];
+  float lo_r[3], hi_r[3];
+  int32_t left, right;  // >= 0: internal node index; < 0: leaf, cell = ~child
+  int32_t parent, pad;
+};
+static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
+
+// ---- device helpers shared by the row kernels -----------------------------------------------------
+#ifdef __CUDACC__
+// bitonic sort of cap (power of two) 64-bit keys in shared memory by `nthreads` cooperating threads
+template <bool BLOCK>
+__device__ __forceinline__ void group_sync() {
+  if (BLOCK) __syncthreads();
+  else __syncwarp();
+}
+
+template <bool BLOCK>
+__device__ void bitonic_sort_u64(uint64_t* keys, uint32_t cap, int tid, int nthreads) {
+  for (uint32_t k = 2; k <= cap; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t t = tid; t < cap / 2; t += nthreads) {
+        const uint32_t i = 2 * t - (t & (j - 1));  // index with bit j cleared
+        const uint32_t ixj = i | j;
+        const bool up = (i & k) == 0;
+        const uint64_t a = keys[i], b = keys[ixj];
+        if ((a > b) == up) {
+          keys[i] = b;
+          keys[ixj] = a;
+        }
+      }
+      group_sync<BLOCK>();
+    }
+  }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace fxii
+
+struct fxii_mesh {
+  int64_t n_cells = 0, n_nodes = 0;
+  double padding = 0;
+  fxii::DevBuf<double> x;            // [n_nodes,3]
+  fxii::DevBuf<int32_t> cell_nodes;  // [n_cells,4]
+  fxii::DevBuf<double> cellgeo;      // [n_cells,12]: v0 (3) + K=J^{-1} row-major (9), 96 B per cell
+  fxii::DevBuf<fxii::BvhNode> nodes; // [max(n_cells-1,1)]
+  int32_t root = 0;
+  int32_t max_depth = 0;
+};
+
+struct fxii_space {
+  const fxii_mesh* mesh = nullptr;
+  int32_t nd = 0, degree = 0;
+  int64_t n_dofs = 0;
+  fxii::DevBuf<int32_t> dofmap;  // [n_cells, nd]
+};
+
+struct fxii_rows {
+  int32_t kind = 0, nq = 1, nip = 1;
+  int64_t n_point_rows = 0;  // Nr
+  int64_t n_rows_total = 0;  // rows of Π
+  int32_t radius_per_row = 0;
+  bool keep_points = false;  // also write the generated 3D points (diagnostics only)
+  // Γ inputs
+  fxii::DevBuf<double> gx;
+  fxii::DevBuf<int32_t> gcells, cells_k, row_dofs;
+  fxii::DevBuf<double> xref, table, w, radius;
+  // generic-operator inputs (kind == POINTS)
+  fxii::DevBuf<double> pts_in, w_in, s_in;
+  // per-build products kept for diagnostics / parity tests
+  fxii::DevBuf<double> frames;   // [Nr,16] row frames
+  fxii::DevBuf<double> points;   // [Np,3]
+  fxii::DevBuf<int32_t> cell;    // [Np]
+  fxii::DevBuf<uint8_t> ncoll;   // [Np]
+  fxii::DevBuf<int32_t> coo_cols;  // [E]
+  fxii::DevBuf<double> coo_vals;   // [E]
+  int32_t nd = 0;
+};
+
+struct fxii_csr {
+  int64_t n_rows = 0, n_cols = 0, nnz = 0;
+  fxii::DevBuf<int64_t> indptr;
+  fxii::DevBuf<int32_t> indices;
+  fxii::DevBuf<double> values;
+};

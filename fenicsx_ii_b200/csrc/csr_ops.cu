@@ -1,0 +1,441 @@
+// CSR products of the block assembly: explicit transpose, row-wise hash SpGEMM, row scaling, SpMV.
+//
+// Reference calls replaced (file:line under /root/reference/src/fenicsx_ii/):
+//   csr_transpose   PETSc Mat.transpose     matrix_assembler.py:184,236; demos/coupled_poisson.py:120-121
+//   spgemm          PETSc Mat.matMult       matrix_assembler.py:185,210,237,245; demos/coupled_poisson.py:111,167,177
+//   csr_scale_rows  M_Γ·Π for the diagonal quadrature-element mass (demos/coupled_poisson.py:164-167)
+//   csr_spmv        K.mult                  assembly.py:67;  csr_spmv_t: vector_assembler.py:177
+//
+// PETSc semantics kept: the SYMBOLIC product pattern survives (cancellation zeros and Π's explicit
+// zeros stay), columns are sorted, and c_ij accumulates a_ik*b_kj over k in A's column order, so
+// results are bitwise reproducible run to run.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace fxii {
+
+// ---- transpose ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+expand_rows_kernel(const int64_t* __restrict__ indptr, int64_t n_rows, int32_t* __restrict__ row_of) {
+  // one warp per row
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n_rows; r += nwarps) {
+    const int64_t a = indptr[r], b = indptr[r + 1];
+    for (int64_t k = a + lane; k < b; k += 32) row_of[k] = (int32_t)r;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+col_hist_kernel(const int32_t* __restrict__ indices, int64_t nnz, unsigned long long* __restrict__ count) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&count[indices[k]], 1ULL);
+}
+
+__global__ void __launch_bounds__(256)
+gather_transposed_kernel(const int32_t* __restrict__ perm, const int32_t* __restrict__ row_of,
+                         const double* __restrict__ values, int64_t nnz, int32_t* __restrict__ t_indices,
+                         double* __restrict__ t_values) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t src = perm[k];
+    t_indices[k] = row_of[src];
+    t_values[k] = values[src];
+  }
+}
+
+__global__ void __launch_bounds__(256) iota32_kernel(int32_t* __restrict__ a, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] = (int32_t)i;
+}
+
+static void exclusive_scan_i64(const long long* in, long long* out, int64_t n, cudaStream_t s) {
+  size_t tb = 0;
+  FXII_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, s));
+  DevBuf<uint8_t> tmp;
+  tmp.alloc((int64_t)tb, s);
+  FXII_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, in, out, n, s));
+}
+
+// Stable sort of the entries by column (radix sort is stable), so every row of Aᵀ lists the
+// source rows in ascending order — the order MatTranspose produces.
+void csr_transpose(const fxii_csr* a, cudaStream_t s, fxii_csr* out) {
+  FXII_CHECK(a->nnz < ((int64_t)1 << 31), "transpose: nnz must fit int32 (shard the matrix)");
+  out->n_rows = a->n_cols;
+  out->n_cols = a->n_rows;
+  out->nnz = a->nnz;
+  const int64_t nnz = a->nnz;
+  DevBuf<unsigned long long> count;
+  count.alloc(a->n_cols + 1, s);
+  FXII_CUDA(cudaMemsetAsync(count.p, 0, sizeof(unsigned long long) * (size_t)(a->n_cols + 1), s));
+  out->indptr.alloc(a->n_cols + 1, s);
+  out->indices.alloc(nnz, s);
+  out->values.alloc(nnz, s);
+  if (nnz > 0) {
+    col_hist_kernel<<<grid_for(nnz, 256, 8), 256, 0, s>>>(a->indices.p, nnz, count.p);
+    FXII_CUDA(cudaGetLastError());
+  }
+  exclusive_scan_i64((const long long*)count.p, (long long*)out->indptr.p, a->n_cols + 1, s);
+  if (nnz == 0) return;
+  DevBuf<int32_t> row_of, iota, perm, keys_sorted;
+  row_of.alloc(nnz, s);
+  iota.alloc(nnz, s);
+  perm.alloc(nnz, s);
+  keys_sorted.alloc(nnz, s);
+  expand_rows_kernel<<<grid_for(a->n_rows * 32, 256, 8), 256, 0, s>>>(a->indptr.p, a->n_rows, row_of.p);
+  iota32_kernel<<<grid_for(nnz, 256, 8), 256, 0, s>>>(iota.p, nnz);
+  int end_bit = 1;
+  while (end_bit < 31 && ((int64_t)1 << end_bit) < a->n_cols) ++end_bit;
+  size_t tb = 0;
+  FXII_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, a->indices.p, keys_sorted.p, iota.p, perm.p, nnz, 0, end_bit, s));
+  DevBuf<uint8_t> tmp;
+  tmp.alloc((int64_t)tb, s);
+  FXII_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, a->indices.p, keys_sorted.p, iota.p, perm.p, nnz, 0, end_bit, s));
+  gather_transposed_kernel<<<grid_for(nnz, 256, 8), 256, 0, s>>>(perm.p, row_of.p, a->values.p, nnz, out->indices.p,
+                                                                 out->values.p);
+  FXII_CUDA(cudaGetLastError());
+}
+
+// ---- SpGEMM -------------------------------------------------------------------------------------
+// upper bound of nnz(C_i): number of intermediate products of row i
+__global__ void __launch_bounds__(256)
+spgemm_ub_kernel(const int64_t* __restrict__ a_ptr, const int32_t* __restrict__ a_idx, const int64_t* __restrict__ b_ptr,
+                 int64_t row_begin, int64_t n_rows, int64_t* __restrict__ ub) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n_rows; i += nwarps) {
+    const int64_t a0 = a_ptr[row_begin + i], a1 = a_ptr[row_begin + i + 1];
+    long long sum = 0;
+    for (int64_t k = a0 + lane; k < a1; k += 32) {
+      const int c = a_idx[k];
+      sum += b_ptr[c + 1] - b_ptr[c];
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) ub[i] = sum;
+  }
+}
+
+constexpr int32_t kEmpty = -1;
+
+__device__ __forceinline__ uint32_t hash_col(uint32_t c) { return c * 2654435761u; }
+
+// insert key into an open-addressing table of `cap` (power of two) slots; returns the slot
+__device__ __forceinline__ uint32_t hash_insert(int32_t* keys, uint32_t cap, int32_t key) {
+  uint32_t h = hash_col((uint32_t)key) & (cap - 1);
+  while (true) {
+    const int32_t prev = atomicCAS(&keys[h], kEmpty, key);
+    if (prev == kEmpty || prev == key) return h;
+    h = (h + 1) & (cap - 1);
+  }
+}
+
+// One GROUP (warp or block) per output row.  Pass NUMERIC=false counts the distinct columns;
+// NUMERIC=true accumulates values — sequentially over k (A's column order), in parallel over the
+// entries of B's row k, whose columns are distinct, so no two lanes touch the same slot between two
+// group barriers and the sum order is fixed — then compacts the occupied slots into (col, slot)
+// keys, bitonic-sorts them and writes the row in ascending column order.
+// Table storage: shared memory (g_keys == nullptr) or a per-row slice of global memory.
+// Layout per group for capacity cap: vals f64[cap] | sort u64[cap/2] | keys i32[cap]  (NUMERIC)
+//                                    keys i32[cap]                                     (count)
+template <bool BLOCK, bool NUMERIC>
+__global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int32_t* __restrict__ a_idx,
+                                   const double* __restrict__ a_val, const int64_t* __restrict__ b_ptr,
+                                   const int32_t* __restrict__ b_idx, const double* __restrict__ b_val,
+                                   int64_t row_begin, const int32_t* __restrict__ row_list, int64_t n_list, uint32_t cap,
+                                   int32_t* __restrict__ g_keys, double* __restrict__ g_vals,
+                                   uint64_t* __restrict__ g_sort, const int64_t* __restrict__ g_off,
+                                   int64_t* __restrict__ row_nnz, const int64_t* __restrict__ c_ptr,
+                                   int32_t* __restrict__ c_idx, double* __restrict__ c_val) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const int nthreads = BLOCK ? blockDim.x : 32;
+  const int tid = BLOCK ? threadIdx.x : (threadIdx.x & 31);
+  const int groups_per_block = BLOCK ? 1 : blockDim.x / 32;
+  const int gid = BLOCK ? 0 : threadIdx.x / 32;
+  __shared__ int s_cnt[32];
+  for (int64_t li = (int64_t)blockIdx.x * groups_per_block + gid; li < n_list; li += (int64_t)gridDim.x * groups_per_block) {
+    const int64_t i = row_list[li];  // row index relative to row_begin
+    int32_t* keys;
+    double* vals = nullptr;
+    uint64_t* sortbuf = nullptr;
+    uint32_t tcap = cap;
+    if (g_keys) {
+      const int64_t o0 = g_off[li], o1 = g_off[li + 1];
+      tcap = (uint32_t)(o1 - o0);
+      keys = g_keys + o0;
+      if (NUMERIC) {
+        vals = g_vals + o0;
+        sortbuf = g_sort + o0 / 2;
+      }
+    } else {
+      unsigned char* base = s_raw + (size_t)gid * cap * (NUMERIC ? 16 : 4);
+      if (NUMERIC) {
+        vals = reinterpret_cast<double*>(base);
+        sortbuf = reinterpret_cast<uint64_t*>(base + (size_t)cap * 8);
+        keys = reinterpret_cast<int32_t*>(base + (size_t)cap * 12);
+      } else {
+        keys = reinterpret_cast<int32_t*>(base);
+      }
+    }
+    for (uint32_t t = tid; t < tcap; t += nthreads) {
+      keys[t] = kEmpty;
+      if (NUMERIC) vals[t] = 0.0;
+    }
+    group_sync<BLOCK>();
+    const int64_t a0 = a_ptr[row_begin + i], a1 = a_ptr[row_begin + i + 1];
+    for (int64_t ka = a0; ka < a1; ++ka) {
+      const int k = a_idx[ka];
+      const double av = NUMERIC ? a_val[ka] : 0.0;
+      const int64_t b0 = b_ptr[k], b1 = b_ptr[k + 1];
+      for (int64_t kb = b0 + tid; kb < b1; kb += nthreads) {
+        const uint32_t slot = hash_insert(keys, tcap, b_idx[kb]);
+        if (NUMERIC) vals[slot] += av * b_val[kb];
+      }
+      if (NUMERIC) group_sync<BLOCK>();
+    }
+    group_sync<BLOCK>();
+    if (!NUMERIC) {
+      int local = 0;
+      for (uint32_t t = tid; t < tcap; t += nthreads) local += keys[t] != kEmpty;
+      for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+      if (BLOCK) {
+        if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = local;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          int tot = 0;
+          for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_cnt[w];
+          row_nnz[i] = tot;
+        }
+        __syncthreads();
+      } else if (tid == 0) {
+        row_nnz[i] = local;
+      }
+      group_sync<BLOCK>();
+    } else {
+      const int64_t out0 = c_ptr[i];
+      const uint32_t nnz = (uint32_t)(c_ptr[i + 1] - out0);
+      uint32_t scap = 2;
+      while (scap < nnz) scap <<= 1;
+      for (uint32_t t = tid; t < scap; t += nthreads) sortbuf[t] = ~0ULL;
+      group_sync<BLOCK>();
+      // compact occupied slots; order is irrelevant (sorted next), so a shared counter suffices
+      if (tid == 0) s_cnt[gid] = 0;
+      group_sync<BLOCK>();
+      for (uint32_t t0 = 0; t0 < tcap; t0 += nthreads) {
+        const uint32_t t = t0 + tid;
+        const int32_t key = t < tcap ? keys[t] : kEmpty;
+        const bool occ = key != kEmpty;
+        const unsigned ball = __ballot_sync(0xffffffffu, occ);
+        int wbase = 0;
+        if ((threadIdx.x & 31) == 0 && ball) wbase = atomicAdd(&s_cnt[gid], __popc(ball));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (occ) sortbuf[wbase + __popc(ball & ((1u << (threadIdx.x & 31)) - 1))] = ((uint64_t)(uint32_t)key << 32) | t;
+      }
+      group_sync<BLOCK>();
+      bitonic_sort_u64<BLOCK>(sortbuf, scap, tid, nthreads);
+      for (uint32_t t = tid; t < nnz; t += nthreads) {
+        const uint64_t e = sortbuf[t];
+        c_idx[out0 + t] = (int32_t)(e >> 32);
+        c_val[out0 + t] = vals[(uint32_t)(e & 0xffffffffu)];
+      }
+      group_sync<BLOCK>();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+classify_rows_kernel(const int64_t* __restrict__ ub, int64_t n_rows, int64_t t0, int64_t t1, int64_t t2,
+                     int32_t* __restrict__ bin_of) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t u = ub[i];
+    bin_of[i] = u == 0 ? -1 : (u <= t0 ? 0 : (u <= t1 ? 1 : (u <= t2 ? 2 : 3)));
+  }
+}
+
+struct IsBin {
+  const int32_t* bin_of;
+  int b;
+  __device__ bool operator()(const int32_t& i) const { return bin_of[i] == b; }
+};
+
+__global__ void __launch_bounds__(256)
+global_table_sizes_kernel(const int32_t* __restrict__ row_list, int64_t n_list, const int64_t* __restrict__ ub,
+                          int64_t* __restrict__ sizes) {
+  for (int64_t li = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; li <= n_list; li += (int64_t)gridDim.x * blockDim.x) {
+    if (li == n_list) {
+      sizes[li] = 0;
+      continue;
+    }
+    uint64_t u = (uint64_t)ub[row_list[li]] * 2;
+    uint64_t cap = 1024;
+    while (cap < u) cap <<= 1;
+    sizes[li] = (int64_t)cap;
+  }
+}
+
+// bins by intermediate-product bound: 0: warp/row, shared table 512; 1: warp/row, 2048;
+// 2: block/row, 8192; 3: block/row, global-memory table of 2*ub slots
+void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row_end, cudaStream_t s, fxii_csr* out,
+            int64_t* ip_out) {
+  FXII_CHECK(a->n_cols == b->n_rows, "spgemm: inner dimensions differ");
+  if (row_end < 0) row_end = a->n_rows;
+  FXII_CHECK(row_begin >= 0 && row_begin <= row_end && row_end <= a->n_rows, "spgemm: bad row window");
+  const int64_t m = row_end - row_begin;
+  out->n_rows = m;
+  out->n_cols = b->n_cols;
+  DevBuf<int64_t> ub, row_nnz;
+  ub.alloc(m + 1, s);
+  row_nnz.alloc(m + 1, s);
+  FXII_CUDA(cudaMemsetAsync(ub.p, 0, sizeof(int64_t) * (size_t)(m + 1), s));
+  FXII_CUDA(cudaMemsetAsync(row_nnz.p, 0, sizeof(int64_t) * (size_t)(m + 1), s));
+  out->indptr.alloc(m + 1, s);
+  if (m == 0) {
+    FXII_CUDA(cudaMemsetAsync(out->indptr.p, 0, sizeof(int64_t), s));
+    out->nnz = 0;
+    if (ip_out) *ip_out = 0;
+    return;
+  }
+  spgemm_ub_kernel<<<grid_for(m * 32, 256, 8), 256, 0, s>>>(a->indptr.p, a->indices.p, b->indptr.p, row_begin, m, ub.p);
+  FXII_CUDA(cudaGetLastError());
+  // total intermediate products
+  DevBuf<int64_t> ip_dev;
+  ip_dev.alloc(1, s);
+  {
+    size_t tb = 0;
+    FXII_CUDA(cub::DeviceReduce::Sum(nullptr, tb, ub.p, ip_dev.p, m, s));
+    DevBuf<uint8_t> tmp;
+    tmp.alloc((int64_t)tb, s);
+    FXII_CUDA(cub::DeviceReduce::Sum(tmp.p, tb, ub.p, ip_dev.p, m, s));
+  }
+  const int64_t T0 = 256, T1 = 1024, T2 = 4096;
+  const uint32_t caps[3] = {512, 2048, 8192};
+  DevBuf<int32_t> bin_of, iota, lists[4];
+  bin_of.alloc(m, s);
+  iota.alloc(m, s);
+  classify_rows_kernel<<<grid_for(m, 256, 8), 256, 0, s>>>(ub.p, m, T0, T1, T2, bin_of.p);
+  iota32_kernel<<<grid_for(m, 256, 8), 256, 0, s>>>(iota.p, m);
+  DevBuf<int64_t> n_sel;
+  n_sel.alloc(4, s);
+  int64_t h_n[4] = {0, 0, 0, 0};
+  for (int bin = 0; bin < 4; ++bin) {
+    lists[bin].alloc(m, s);
+    size_t tb = 0;
+    IsBin pred{bin_of.p, bin};
+    FXII_CUDA(cub::DeviceSelect::If(nullptr, tb, iota.p, lists[bin].p, n_sel.p + bin, m, pred, s));
+    DevBuf<uint8_t> tmp;
+    tmp.alloc((int64_t)tb, s);
+    FXII_CUDA(cub::DeviceSelect::If(tmp.p, tb, iota.p, lists[bin].p, n_sel.p + bin, m, pred, s));
+  }
+  int64_t h_ip = 0;
+  FXII_CUDA(cudaMemcpyAsync(h_n, n_sel.p, sizeof(h_n), cudaMemcpyDeviceToHost, s));
+  FXII_CUDA(cudaMemcpyAsync(&h_ip, ip_dev.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  FXII_CUDA(cudaStreamSynchronize(s));
+  if (ip_out) *ip_out = h_ip;
+
+  // global tables for bin 3
+  DevBuf<int64_t> g_sizes, g_off;
+  DevBuf<int32_t> g_keys;
+  DevBuf<double> g_vals;
+  DevBuf<uint64_t> g_sort;
+  if (h_n[3] > 0) {
+    g_sizes.alloc(h_n[3] + 1, s);
+    g_off.alloc(h_n[3] + 1, s);
+    global_table_sizes_kernel<<<grid_for(h_n[3] + 1, 256, 8), 256, 0, s>>>(lists[3].p, h_n[3], ub.p, g_sizes.p);
+    exclusive_scan_i64((const long long*)g_sizes.p, (long long*)g_off.p, h_n[3] + 1, s);
+    int64_t total = 0;
+    FXII_CUDA(cudaMemcpyAsync(&total, g_off.p + h_n[3], sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    FXII_CUDA(cudaStreamSynchronize(s));
+    g_keys.alloc(total, s);
+    g_vals.alloc(total, s);
+    g_sort.alloc(total / 2 + 1, s);
+  }
+
+  auto launch = [&](bool numeric) {
+    for (int bin = 0; bin < 4; ++bin) {
+      const int64_t nl = h_n[bin];
+      if (nl == 0) continue;
+      const bool block = bin >= 2;
+      const bool global = bin == 3;
+      const uint32_t cap = global ? 0 : caps[bin];
+      const int threads = block ? 256 : (bin == 0 ? 256 : 128);
+      const int groups = block ? 1 : threads / 32;
+      const size_t smem = global ? 0 : (size_t)cap * (numeric ? 16 : 4) * groups;
+      const int grid = (int)std::min<int64_t>((nl + groups - 1) / groups, (int64_t)num_sms() * 16);
+#define FXII_SPGEMM_LAUNCH(BLK, NUM)                                                                                  \
+  do {                                                                                                                \
+    if (smem > 48 * 1024)                                                                                             \
+      FXII_CUDA(cudaFuncSetAttribute(spgemm_rows_kernel<BLK, NUM>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                     (int)smem));                                                                     \
+    spgemm_rows_kernel<BLK, NUM><<<grid, threads, smem, s>>>(                                                         \
+        a->indptr.p, a->indices.p, a->values.p, b->indptr.p, b->indices.p, b->values.p, row_begin, lists[bin].p, nl,  \
+        cap, global ? g_keys.p : nullptr, global ? g_vals.p : nullptr, global ? g_sort.p : nullptr,                \
+        global ? g_off.p : nullptr, row_nnz.p,                                                                        \
+        out->indptr.p, out->indices.p, out->values.p);                                                                \
+    FXII_CUDA(cudaGetLastError());                                                                                    \
+  } while (0)
+      if (block && numeric) FXII_SPGEMM_LAUNCH(true, true);
+      else if (block && !numeric) FXII_SPGEMM_LAUNCH(true, false);
+      else if (!block && numeric) FXII_SPGEMM_LAUNCH(false, true);
+      else FXII_SPGEMM_LAUNCH(false, false);
+#undef FXII_SPGEMM_LAUNCH
+    }
+  };
+  launch(false);
+  exclusive_scan_i64((const long long*)row_nnz.p, (long long*)out->indptr.p, m + 1, s);
+  int64_t nnz = 0;
+  FXII_CUDA(cudaMemcpyAsync(&nnz, out->indptr.p + m, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  FXII_CUDA(cudaStreamSynchronize(s));
+  out->nnz = nnz;
+  out->indices.alloc(nnz, s);
+  out->values.alloc(nnz, s);
+  if (nnz > 0) launch(true);
+}
+
+// ---- row scaling, SpMV --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+scale_rows_kernel(const int64_t* __restrict__ indptr, int64_t n_rows, const double* __restrict__ d, double* __restrict__ values) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n_rows; r += nwarps) {
+    const double f = d[r];
+    for (int64_t k = indptr[r] + lane; k < indptr[r + 1]; k += 32) values[k] = f * values[k];
+  }
+}
+
+void csr_scale_rows(fxii_csr* a, const double* d_host, cudaStream_t s) {
+  DevBuf<double> d;
+  d.upload(d_host, a->n_rows, s);
+  if (a->n_rows > 0) scale_rows_kernel<<<grid_for(a->n_rows * 32, 256, 8), 256, 0, s>>>(a->indptr.p, a->n_rows, d.p, a->values.p);
+  FXII_CUDA(cudaGetLastError());
+  FXII_CUDA(cudaStreamSynchronize(s));
+}
+
+// one warp per row; lanes stride the row, partial sums combined by a fixed shuffle tree
+__global__ void __launch_bounds__(256)
+spmv_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const double* __restrict__ values,
+            int64_t n_rows, const double* __restrict__ u, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n_rows; r += nwarps) {
+    double sum = 0.0;
+    for (int64_t k = indptr[r] + lane; k < indptr[r + 1]; k += 32) sum += values[k] * __ldg(&u[indices[k]]);
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) y[r] = sum;
+  }
+}
+
+void csr_spmv(const fxii_csr* a, const double* u_host, double* y_host, cudaStream_t s) {
+  DevBuf<double> u, y;
+  u.upload(u_host, a->n_cols, s);
+  y.alloc(a->n_rows, s);
+  if (a->n_rows > 0) {
+    spmv_kernel<<<grid_for(a->n_rows * 32, 256, 8), 256, 0, s>>>(a->indptr.p, a->indices.p, a->values.p, a->n_rows, u.p, y.p);
+    FXII_CUDA(cudaGetLastError());
+    FXII_CUDA(cudaMemcpyAsync(y_host, y.p, sizeof(double) * (size_t)a->n_rows, cudaMemcpyDeviceToHost, s));
+  }
+  FXII_CUDA(cudaStreamSynchronize(s));
+}
+
+}  // namespace fxii

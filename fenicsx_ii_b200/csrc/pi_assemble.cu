@@ -1,0 +1,764 @@
+// Π assembly: row frames -> fused (point generation + LBVH location + pull-back + tabulation)
+// -> segment-structured COO -> CSR.
+//
+// Reference stages replaced (file:line under /root/reference/src/fenicsx_ii/):
+//   row_frames_kernel      utils.py:11-33 (push-forward, tangents), quadrature.py:35-69 (Rodrigues),
+//                          restriction_operators.py:189-205 / 301-315 (radius, weights, scales)
+//   pi_locate_tabulate     restriction_operators.py:191-199 (averaging points),
+//                          interpolation.py:66-68 (determine_point_ownership),
+//                          interpolation_utils.py:36-38 (pull_back), :59-74 (basis tabulation),
+//                          interpolation.py:234-238 (value = (phi*w)/scale)
+//   rows_count / rows_fill interpolation.py:140-163 (SparsityPattern insert + finalize),
+//                          :205-250 (first-visit-wins masking, ADD_VALUES in l order, assemble)
+//
+// This translation unit is compiled with -fmad=false so the fp64 geometry follows the same
+// operation order as the CPU oracle (no FMA contraction).
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace fxii {
+
+constexpr int kStack = 96;          // LBVH depth bound: 63-bit Morton key + 32-bit index tie-break
+constexpr double kCollisionD2 = 10.0 * 2.220446049250313e-16;  // dolfinx: d^2 < 10*eps
+
+// frame layout (16 doubles = 128 B per point row):
+//  [0..2] x0, [3] R, [4..12] Rot row-major, [13] weight multiplier, [14] scale, [15] unused
+constexpr int kFrame = 16;
+
+__global__ void __launch_bounds__(128)
+row_frames_kernel(const double* __restrict__ gx, const int32_t* __restrict__ gcells, const int32_t* __restrict__ cells_k,
+                  const double* __restrict__ xref, int nip, const double* __restrict__ radius, int radius_per_row,
+                  int kind, int64_t n_point_rows, double* __restrict__ frames) {
+  const double PI = 3.141592653589793;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_point_rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = r / nip;
+    const int j = (int)(r - i * nip);
+    const int c = cells_k[i];
+    const int g0 = gcells[2 * (int64_t)c], g1 = gcells[2 * (int64_t)c + 1];
+    double v0[3], v1[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      v0[d] = gx[3 * (int64_t)g0 + d];
+      v1[d] = gx[3 * (int64_t)g1 + d];
+    }
+    const double X = xref[j];
+    double* f = frames + kFrame * r;
+    const double omx = 1.0 - X;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) f[d] = v0[d] * omx + v1[d] * X;  // utils.py:18-20
+    if (kind == FXII_OP_TRACE) {
+      f[3] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) f[4 + k] = 0.0;
+      f[13] = 1.0;
+      f[14] = 1.0;
+      f[15] = 0.0;
+      continue;
+    }
+    // tangent (utils.py:31-32) then the normalisation of rotation_matrix (quadrature.py:43)
+    double t[3] = {v0[0] - v1[0], v0[1] - v1[1], v0[2] - v1[2]};
+    double nrm = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) t[d] = t[d] / nrm;
+    nrm = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+    double n[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) n[d] = t[d] / nrm;
+    // axis = ez x n ; ez when the cross product vanishes (np.isclose(.,0): <= 1e-8)
+    double a[3] = {-n[1], n[0], 0.0};
+    double an = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    if (an <= 1.0e-8) {
+      a[0] = 0.0;
+      a[1] = 0.0;
+      a[2] = 1.0;
+    }
+    an = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) a[d] = a[d] / an;
+    const double ct = n[2];
+    const double st = sqrt(1.0 - ct * ct);
+    const double omc = 1.0 - ct;
+    const double sm[9] = {0.0, -a[2], a[1], a[2], 0.0, -a[0], -a[1], a[0], 0.0};
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const double diag = (p == q) ? ct : 0.0;
+        f[4 + 3 * p + q] = (diag + sm[3 * p + q] * st) + (a[p] * a[q]) * omc;
+      }
+    const double R = radius_per_row ? radius[r] : radius[0];
+    f[3] = R;
+    if (kind == FXII_OP_CIRCLE) {
+      const double scale = 2.0 * R * PI;  // restriction_operators.py:203
+      f[13] = scale;
+      f[14] = scale;
+    } else {  // DISK
+      f[13] = R * R;         // :312
+      f[14] = PI * (R * R);  // :311
+    }
+    f[15] = 0.0;
+  }
+}
+
+// ---- geometry helpers --------------------------------------------------------------------------
+__device__ __forceinline__ double dot3(const double* a, const double* b) {
+  return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2];
+}
+
+// squared distance point-triangle (Ericson, Real-Time Collision Detection 5.1.5); mirrors
+// oracle/pi_oracle.py:_closest_point_triangle_d2
+__device__ double tri_dist2(const double* p, const double* a, const double* b, const double* c) {
+  double ab[3], ac[3], ap[3], bp[3], cp[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    ab[d] = b[d] - a[d];
+    ac[d] = c[d] - a[d];
+    ap[d] = p[d] - a[d];
+    bp[d] = p[d] - b[d];
+    cp[d] = p[d] - c[d];
+  }
+  const double d1 = dot3(ab, ap), d2 = dot3(ac, ap);
+  const double d3 = dot3(ab, bp), d4 = dot3(ac, bp);
+  const double d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+  const double vc = d1 * d4 - d3 * d2;
+  const double vb = d5 * d2 - d1 * d6;
+  const double va = d3 * d6 - d5 * d4;
+  double q[3];
+  if (d1 <= 0 && d2 <= 0) {
+    q[0] = a[0]; q[1] = a[1]; q[2] = a[2];
+  } else if (d3 >= 0 && d4 <= d3) {
+    q[0] = b[0]; q[1] = b[1]; q[2] = b[2];
+  } else if (vc <= 0 && d1 >= 0 && d3 <= 0) {
+    const double v = d1 / (d1 - d3);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) q[d] = a[d] + v * ab[d];
+  } else if (d6 >= 0 && d5 <= d6) {
+    q[0] = c[0]; q[1] = c[1]; q[2] = c[2];
+  } else if (vb <= 0 && d2 >= 0 && d6 <= 0) {
+    const double w = d2 / (d2 - d6);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) q[d] = a[d] + w * ac[d];
+  } else if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
+    const double w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+#pragma unroll
+    for (int d = 0; d < 3; ++d) q[d] = b[d] + w * (c[d] - b[d]);
+  } else {
+    const double denom = 1.0 / (va + vb + vc);
+    const double v = vb * denom, w = vc * denom;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) q[d] = (a[d] + ab[d] * v) + ac[d] * w;
+  }
+  double e[3] = {p[0] - q[0], p[1] - q[1], p[2] - q[2]};
+  return dot3(e, e);
+}
+
+struct CellGeo {
+  double v0[3];
+  double K[9];
+};
+
+__device__ __forceinline__ void load_cellgeo(const double* __restrict__ cellgeo, int cell, CellGeo& g) {
+  const double2* src = reinterpret_cast<const double2*>(cellgeo + 12 * (int64_t)cell);
+  double2 a0 = __ldg(src), a1 = __ldg(src + 1), a2 = __ldg(src + 2), a3 = __ldg(src + 3), a4 = __ldg(src + 4),
+          a5 = __ldg(src + 5);
+  g.v0[0] = a0.x; g.v0[1] = a0.y; g.v0[2] = a1.x;
+  g.K[0] = a1.y; g.K[1] = a2.x; g.K[2] = a2.y;
+  g.K[3] = a3.x; g.K[4] = a3.y; g.K[5] = a4.x;
+  g.K[6] = a4.y; g.K[7] = a5.x; g.K[8] = a5.y;
+}
+
+// X = K (x - v0): interpolation_utils.py:36-38 for affine cells
+__device__ __forceinline__ void pull_back(const CellGeo& g, const double* p, double* X) {
+  const double d0 = p[0] - g.v0[0], d1 = p[1] - g.v0[1], d2 = p[2] - g.v0[2];
+  X[0] = (g.K[0] * d0 + g.K[1] * d1) + g.K[2] * d2;
+  X[1] = (g.K[3] * d0 + g.K[4] * d1) + g.K[5] * d2;
+  X[2] = (g.K[6] * d0 + g.K[7] * d1) + g.K[8] * d2;
+}
+
+// Slow path of the leaf test (some barycentric coordinate negative): exact fp64 padded-box test
+// (dolfinx point_in_bbox, slack 1e-14*extent) and exact point-tetrahedron distance.
+// Returns false when the cell is not a candidate; otherwise d2.
+__device__ bool cell_distance2(const double* __restrict__ x, const int4* __restrict__ cell_nodes, int cell,
+                               const double* p, double padding, double& d2) {
+  const int4 nd = __ldg(&cell_nodes[cell]);
+  const int id[4] = {nd.x, nd.y, nd.z, nd.w};
+  double v[4][3];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) v[k][d] = __ldg(&x[3 * (int64_t)id[k] + d]);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double lo = fmin(fmin(v[0][d], v[1][d]), fmin(v[2][d], v[3][d])) - padding;
+    const double hi = fmax(fmax(v[0][d], v[1][d]), fmax(v[2][d], v[3][d])) + padding;
+    const double eps = 1e-14 * (hi - lo);
+    if (!(p[d] >= lo - eps && p[d] <= hi + eps)) return false;
+  }
+  double best = tri_dist2(p, v[1], v[2], v[3]);
+  best = fmin(best, tri_dist2(p, v[0], v[2], v[3]));
+  best = fmin(best, tri_dist2(p, v[0], v[1], v[3]));
+  best = fmin(best, tri_dist2(p, v[0], v[1], v[2]));
+  d2 = best;
+  return true;
+}
+
+struct LocateResult {
+  int cell;      // lowest colliding cell index, or nearest-cell fallback, or -1
+  int ncoll;     // size of the colliding set
+  bool fallback;
+};
+
+// Full traversal (no early exit): every leaf whose fp32 box contains the point is tested and the
+// LOWEST colliding cell index wins, independent of tree shape (north_star tie-break).
+__device__ LocateResult locate_point(const BvhNode* __restrict__ nodes, const double* __restrict__ cellgeo,
+                                     const double* __restrict__ x, const int4* __restrict__ cell_nodes,
+                                     double padding, const double* p) {
+  const float plo[3] = {__double2float_rd(p[0]), __double2float_rd(p[1]), __double2float_rd(p[2])};
+  const float phi[3] = {__double2float_ru(p[0]), __double2float_ru(p[1]), __double2float_ru(p[2])};
+  int stack[kStack];
+  int sp = 0;
+  int node = 0;
+  int best = 0x7fffffff, ncoll = 0;
+  int fb_cell = -1;
+  double fb_d2 = 1e300;
+  while (true) {
+    const float4* nf = reinterpret_cast<const float4*>(nodes + node);
+    const float4 q0 = __ldg(nf), q1 = __ldg(nf + 1), q2 = __ldg(nf + 2);
+    const int4 ch = __ldg(reinterpret_cast<const int4*>(nf + 3));
+    // q0 = lo_l.xyz hi_l.x ; q1 = hi_l.yz lo_r.xy ; q2 = lo_r.z hi_r.xyz
+    const bool hit_l = q0.x <= phi[0] && q0.y <= phi[1] && q0.z <= phi[2] && q0.w >= plo[0] && q1.x >= plo[1] && q1.y >= plo[2];
+    const bool hit_r = q1.z <= phi[0] && q1.w <= phi[1] && q2.x <= phi[2] && q2.y >= plo[0] && q2.z >= plo[1] && q2.w >= plo[2];
+    int next = -1;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+      const bool hit = side == 0 ? hit_l : hit_r;
+      const int child = side == 0 ? ch.x : ch.y;
+      if (!hit) continue;
+      if (child >= 0) {
+        if (next < 0) next = child;
+        else if (sp < kStack) stack[sp++] = child;
+      } else {
+        const int cell = ~child;
+        CellGeo g;
+        load_cellgeo(cellgeo, cell, g);
+        double X[3];
+        pull_back(g, p, X);
+        const double l0 = ((1.0 - X[0]) - X[1]) - X[2];
+        if (l0 >= 0 && X[0] >= 0 && X[1] >= 0 && X[2] >= 0) {
+          best = min(best, cell);
+          ++ncoll;
+        } else {
+          double d2;
+          if (cell_distance2(x, cell_nodes, cell, p, padding, d2)) {
+            if (d2 < kCollisionD2) {
+              best = min(best, cell);
+              ++ncoll;
+            } else if (d2 < fb_d2 || (d2 == fb_d2 && cell < fb_cell)) {
+              fb_d2 = d2;
+              fb_cell = cell;
+            }
+          }
+        }
+      }
+    }
+    if (next >= 0) {
+      node = next;
+    } else if (sp > 0) {
+      node = stack[--sp];
+    } else {
+      break;
+    }
+  }
+  LocateResult r;
+  r.ncoll = ncoll;
+  r.fallback = false;
+  if (best != 0x7fffffff) {
+    r.cell = best;
+  } else if (fb_cell >= 0 && fb_d2 <= padding * padding) {
+    r.cell = fb_cell;
+    r.fallback = true;
+  } else {
+    r.cell = -1;
+  }
+  return r;
+}
+
+struct PiCounters {
+  unsigned long long not_found, ties, fallback;
+};
+
+// One thread per 3D point p = r*nq + l (interpolation.py:57).  ND = dofs per V cell.
+template <int ND>
+__global__ void __launch_bounds__(128)
+pi_locate_tabulate_kernel(const BvhNode* __restrict__ nodes, const double* __restrict__ cellgeo,
+                          const double* __restrict__ x, const int4* __restrict__ cell_nodes, double padding,
+                          const int32_t* __restrict__ dofmap, const double* __restrict__ frames,
+                          const double* __restrict__ table, const double* __restrict__ wq,
+                          const double* __restrict__ pts_in, const double* __restrict__ w_in, const double* __restrict__ s_in,
+                          int kind, int nq, int64_t n_points, int32_t* __restrict__ out_cell,
+                          uint8_t* __restrict__ out_ncoll, double* __restrict__ out_points,
+                          int32_t* __restrict__ coo_cols, double* __restrict__ coo_vals, PiCounters* counters) {
+  extern __shared__ double s_tab[];  // [nq*4]: xp (3) + w
+  if (kind == FXII_OP_CIRCLE || kind == FXII_OP_DISK) {
+    for (int k = threadIdx.x; k < nq; k += blockDim.x) {
+      s_tab[4 * k + 0] = table[3 * k + 0];
+      s_tab[4 * k + 1] = table[3 * k + 1];
+      s_tab[4 * k + 2] = table[3 * k + 2];
+      s_tab[4 * k + 3] = wq[k];
+    }
+    __syncthreads();
+  }
+  for (int64_t pidx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pidx < n_points;
+       pidx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = pidx / nq;
+    const int l = (int)(pidx - r * nq);
+    double p[3], W, S;
+    if (kind == FXII_OP_POINTS) {
+      p[0] = pts_in[3 * pidx];
+      p[1] = pts_in[3 * pidx + 1];
+      p[2] = pts_in[3 * pidx + 2];
+      W = w_in[pidx];
+      S = s_in[r];
+    } else {
+      const double* f = frames + kFrame * r;
+      if (kind == FXII_OP_TRACE) {
+        p[0] = f[0]; p[1] = f[1]; p[2] = f[2];
+        W = 1.0;
+        S = 1.0;
+      } else {
+        const double xp0 = s_tab[4 * l], xp1 = s_tab[4 * l + 1], xp2 = s_tab[4 * l + 2];
+        const double R = f[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const double applied = (f[4 + 3 * d] * xp0 + f[5 + 3 * d] * xp1) + f[6 + 3 * d] * xp2;
+          p[d] = f[d] + applied * R;  // restriction_operators.py:191-199
+        }
+        W = s_tab[4 * l + 3] * f[13];
+        S = f[14];
+      }
+    }
+    const LocateResult res = locate_point(nodes, cellgeo, x, cell_nodes, padding, p);
+    out_cell[pidx] = res.cell;
+    out_ncoll[pidx] = (uint8_t)min(res.ncoll, 255);
+    if (out_points) {
+      out_points[3 * pidx] = p[0];
+      out_points[3 * pidx + 1] = p[1];
+      out_points[3 * pidx + 2] = p[2];
+    }
+    if (res.ncoll > 1) atomicAdd(&counters->ties, 1ULL);
+    if (res.fallback) atomicAdd(&counters->fallback, 1ULL);
+    int32_t cols[ND];
+    double vals[ND];
+    if (res.cell < 0) {
+      atomicAdd(&counters->not_found, 1ULL);
+#pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        cols[d] = 0;
+        vals[d] = 0.0;
+      }
+    } else {
+      CellGeo g;
+      load_cellgeo(cellgeo, res.cell, g);
+      double X[3];
+      pull_back(g, p, X);
+      double lam[4] = {((1.0 - X[0]) - X[1]) - X[2], X[0], X[1], X[2]};
+      double phi[ND];
+      if (ND == 4) {
+#pragma unroll
+        for (int d = 0; d < 4; ++d) phi[d] = lam[d];
+      } else {  // P2, basix order: vertices, then edges (2,3),(1,3),(1,2),(0,3),(0,2),(0,1)
+#pragma unroll
+        for (int d = 0; d < 4; ++d) phi[d] = lam[d] * (2.0 * lam[d] - 1.0);
+        phi[4 % ND] = 4.0 * lam[2] * lam[3];
+        phi[5 % ND] = 4.0 * lam[1] * lam[3];
+        phi[6 % ND] = 4.0 * lam[1] * lam[2];
+        phi[7 % ND] = 4.0 * lam[0] * lam[3];
+        phi[8 % ND] = 4.0 * lam[0] * lam[2];
+        phi[9 % ND] = 4.0 * lam[0] * lam[1];
+      }
+      const int32_t* dm = dofmap + (int64_t)ND * res.cell;
+      if (ND == 4) {
+        const int4 d4 = __ldg(reinterpret_cast<const int4*>(dm));
+        cols[0] = d4.x; cols[1] = d4.y; cols[2] = d4.z; cols[3 % ND] = d4.w;
+      } else {
+#pragma unroll
+        for (int d = 0; d < ND; d += 2) {
+          const int2 d2 = __ldg(reinterpret_cast<const int2*>(dm + d));
+          cols[d] = d2.x;
+          cols[(d + 1) % ND] = d2.y;
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < ND; ++d) vals[d] = (phi[d] * W) / S;  // interpolation.py:234-238
+    }
+    int32_t* oc = coo_cols + (int64_t)ND * pidx;
+    double* ov = coo_vals + (int64_t)ND * pidx;
+    if (ND == 4) {
+      *reinterpret_cast<int4*>(oc) = make_int4(cols[0], cols[1], cols[2], cols[3 % ND]);
+    } else {
+#pragma unroll
+      for (int d = 0; d < ND; d += 2) *reinterpret_cast<int2*>(oc + d) = make_int2(cols[d], cols[(d + 1) % ND]);
+    }
+#pragma unroll
+    for (int d = 0; d < ND; d += 2) *reinterpret_cast<double2*>(ov + d) = make_double2(vals[d], vals[(d + 1) % ND]);
+  }
+}
+
+// =================================================================================================
+// COO -> CSR.  The COO is segment structured: point row r owns the SEG = nq*nd consecutive
+// entries [r*SEG, (r+1)*SEG).  Matrix row rho collects the segments of all point rows with
+// row_dofs[r] == rho, in ascending r; only the FIRST of them contributes values
+// (first-visit-wins, interpolation.py:208-217,242), later ones contribute explicit zeros to the
+// pattern.  Each row is sorted by column in shared memory with (col, position) keys — a stable
+// sort — and duplicates are summed left to right, i.e. in l order (ADD_VALUES).
+// =================================================================================================
+
+__device__ __forceinline__ uint32_t next_pow2(uint32_t v) {
+  return v <= 1 ? 1u : 1u << (32 - __clz(v - 1));
+}
+
+// Shared body: loads the keys of matrix row `rho`, sorts, returns the number of entries.
+// smem: keys[cap]
+template <bool BLOCK>
+__device__ uint32_t load_sort_row(const int64_t* __restrict__ seg_ptr, const int32_t* __restrict__ seg_rows,
+                                  const int32_t* __restrict__ coo_cols, int seg, int64_t rho, uint64_t* keys,
+                                  uint32_t cap, int tid, int nthreads) {
+  const int64_t s0 = seg_ptr[rho], s1 = seg_ptr[rho + 1];
+  const uint32_t n = (uint32_t)((s1 - s0) * seg);
+  for (uint32_t e = tid; e < cap; e += nthreads) {
+    uint64_t key = ~0ULL;
+    if (e < n) {
+      const uint32_t si = e / seg;
+      const uint32_t off = e - si * seg;
+      const int64_t r = seg_rows[s0 + si];
+      const uint32_t col = (uint32_t)coo_cols[r * seg + off];
+      key = ((uint64_t)col << 32) | e;
+    }
+    keys[e] = key;
+  }
+  group_sync<BLOCK>();
+  bitonic_sort_u64<BLOCK>(keys, cap, tid, nthreads);
+  return n;
+}
+
+// pass 1: nnz per matrix row.  BLOCK=false: one warp per row; BLOCK=true: one block per row.
+template <bool BLOCK>
+__global__ void rows_count_kernel(const int64_t* __restrict__ seg_ptr, const int32_t* __restrict__ seg_rows,
+                                  const int32_t* __restrict__ coo_cols, int seg, int64_t n_rows, uint32_t cap,
+                                  int64_t* __restrict__ row_nnz) {
+  extern __shared__ uint64_t s_keys[];
+  const int nthreads = BLOCK ? blockDim.x : 32;
+  const int tid = BLOCK ? threadIdx.x : (threadIdx.x & 31);
+  const int groups_per_block = BLOCK ? 1 : blockDim.x / 32;
+  const int gid = BLOCK ? 0 : threadIdx.x / 32;
+  uint64_t* keys = s_keys + (size_t)gid * cap;
+  __shared__ int s_count;
+  for (int64_t rho = (int64_t)blockIdx.x * groups_per_block + gid; rho < n_rows;
+       rho += (int64_t)gridDim.x * groups_per_block) {
+    const uint32_t n = load_sort_row<BLOCK>(seg_ptr, seg_rows, coo_cols, seg, rho, keys, cap, tid, nthreads);
+    int local = 0;
+    for (uint32_t e = tid; e < n; e += nthreads) {
+      const uint32_t col = (uint32_t)(keys[e] >> 32);
+      local += (e == 0 || (uint32_t)(keys[e - 1] >> 32) != col) ? 1 : 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if (BLOCK) {
+      if (threadIdx.x == 0) s_count = 0;
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0 && local) atomicAdd(&s_count, local);
+      __syncthreads();
+      if (threadIdx.x == 0) row_nnz[rho] = s_count;
+      __syncthreads();
+    } else {
+      if (tid == 0) row_nnz[rho] = local;
+      __syncwarp();
+    }
+  }
+}
+
+// pass 2: sorted unique columns and summed values.
+template <bool BLOCK>
+__global__ void rows_fill_kernel(const int64_t* __restrict__ seg_ptr, const int32_t* __restrict__ seg_rows,
+                                 const int32_t* __restrict__ coo_cols, const double* __restrict__ coo_vals, int seg,
+                                 int64_t n_rows, uint32_t cap, const int64_t* __restrict__ indptr,
+                                 int32_t* __restrict__ indices, double* __restrict__ values) {
+  extern __shared__ uint64_t s_keys[];
+  const int nthreads = BLOCK ? blockDim.x : 32;
+  const int tid = BLOCK ? threadIdx.x : (threadIdx.x & 31);
+  const int groups_per_block = BLOCK ? 1 : blockDim.x / 32;
+  const int gid = BLOCK ? 0 : threadIdx.x / 32;
+  uint64_t* keys = s_keys + (size_t)gid * cap;
+  __shared__ int s_warp_heads[32];
+  for (int64_t rho = (int64_t)blockIdx.x * groups_per_block + gid; rho < n_rows;
+       rho += (int64_t)gridDim.x * groups_per_block) {
+    const uint32_t n = load_sort_row<BLOCK>(seg_ptr, seg_rows, coo_cols, seg, rho, keys, cap, tid, nthreads);
+    const int64_t s0 = seg_ptr[rho];
+    const int64_t out0 = indptr[rho];
+    // heads are processed in chunks of nthreads sorted positions; running head count kept uniform
+    int base = 0;
+    for (uint32_t e0 = 0; e0 < n; e0 += nthreads) {
+      const uint32_t e = e0 + tid;
+      bool head = false;
+      uint32_t col = 0;
+      if (e < n) {
+        col = (uint32_t)(keys[e] >> 32);
+        head = (e == 0) || ((uint32_t)(keys[e - 1] >> 32) != col);
+      }
+      const unsigned ball = __ballot_sync(0xffffffffu, head);
+      int pos = __popc(ball & ((1u << (threadIdx.x & 31)) - 1));
+      int chunk_total;
+      if (BLOCK) {
+        const int wid = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0) s_warp_heads[wid] = __popc(ball);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+          const int c = s_warp_heads[w];
+          if (w < wid) before += c;
+          total += c;
+        }
+        pos += before;
+        chunk_total = total;
+        __syncthreads();
+      } else {
+        chunk_total = __popc(ball);
+      }
+      if (head) {
+        double sum = 0.0;
+        for (uint32_t k = e; k < n && (uint32_t)(keys[k] >> 32) == col; ++k) {
+          const uint32_t src = (uint32_t)(keys[k] & 0xffffffffu);
+          const uint32_t si = src / seg;
+          const uint32_t off = src - si * seg;
+          // only the first (lowest r) segment of a row carries values: first-visit-wins
+          const double v = si == 0 ? coo_vals[(int64_t)seg_rows[s0] * seg + off] : 0.0;
+          sum += v;
+        }
+        indices[out0 + base + pos] = (int32_t)col;
+        values[out0 + base + pos] = sum;
+      }
+      base += chunk_total;
+    }
+    group_sync<BLOCK>();
+  }
+}
+
+// seg_count[rho] += 1 for every point row
+__global__ void __launch_bounds__(256)
+seg_hist_kernel(const int32_t* __restrict__ row_dofs, int64_t n_point_rows, int64_t n_rows_total,
+                unsigned long long* __restrict__ seg_count, int* __restrict__ bad) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_point_rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const int rho = row_dofs[r];
+    if (rho < 0 || rho >= n_rows_total) {
+      *bad = 1;
+      continue;
+    }
+    atomicAdd(&seg_count[rho], 1ULL);
+  }
+}
+
+__global__ void __launch_bounds__(256) iota_kernel(int32_t* __restrict__ a, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] = (int32_t)i;
+}
+
+__global__ void __launch_bounds__(256)
+max_u64_kernel(const unsigned long long* __restrict__ a, int64_t n, unsigned long long* __restrict__ out) {
+  unsigned long long m = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = max(m, a[i]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+static float elapsed_ms(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms;
+}
+
+// Segment-structured COO -> CSR.  coo_cols/coo_vals: [n_point_rows*seg].
+void coo_segments_to_csr(const int32_t* row_dofs, int64_t n_point_rows, int64_t n_rows_total, int seg,
+                         const int32_t* coo_cols, const double* coo_vals, int64_t n_cols, cudaStream_t s,
+                         fxii_csr* out) {
+  out->n_rows = n_rows_total;
+  out->n_cols = n_cols;
+  DevBuf<unsigned long long> seg_count;  // [n_rows_total + 1], last slot stays 0
+  seg_count.alloc(n_rows_total + 1, s);
+  FXII_CUDA(cudaMemsetAsync(seg_count.p, 0, sizeof(unsigned long long) * (size_t)(n_rows_total + 1), s));
+  DevBuf<int> bad;
+  bad.alloc(2, s);
+  FXII_CUDA(cudaMemsetAsync(bad.p, 0, 2 * sizeof(int), s));
+  DevBuf<int64_t> seg_ptr;
+  seg_ptr.alloc(n_rows_total + 1, s);
+  DevBuf<int32_t> seg_rows, iota, keys_sorted;
+  seg_rows.alloc(n_point_rows, s);
+  DevBuf<unsigned long long> max_seg;
+  max_seg.alloc(1, s);
+  FXII_CUDA(cudaMemsetAsync(max_seg.p, 0, sizeof(unsigned long long), s));
+  if (n_point_rows > 0) {
+    seg_hist_kernel<<<grid_for(n_point_rows, 256, 8), 256, 0, s>>>(row_dofs, n_point_rows, n_rows_total, seg_count.p, bad.p);
+    max_u64_kernel<<<grid_for(n_rows_total, 256, 8), 256, 0, s>>>(seg_count.p, n_rows_total, max_seg.p);
+  }
+  {
+    size_t tb = 0;
+    FXII_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, (const long long*)seg_count.p, (long long*)seg_ptr.p,
+                                            (int64_t)(n_rows_total + 1), s));
+    DevBuf<uint8_t> tmp;
+    tmp.alloc((int64_t)tb, s);
+    FXII_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, (const long long*)seg_count.p, (long long*)seg_ptr.p,
+                                            (int64_t)(n_rows_total + 1), s));
+  }
+  if (n_point_rows > 0) {
+    // stable sort of point rows by matrix row: ascending r inside each row
+    iota.alloc(n_point_rows, s);
+    keys_sorted.alloc(n_point_rows, s);
+    iota_kernel<<<grid_for(n_point_rows, 256, 8), 256, 0, s>>>(iota.p, n_point_rows);
+    int end_bit = 1;
+    while (end_bit < 31 && ((int64_t)1 << end_bit) < n_rows_total) ++end_bit;
+    size_t tb = 0;
+    FXII_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, row_dofs, keys_sorted.p, iota.p, seg_rows.p, n_point_rows, 0,
+                                              end_bit, s));
+    DevBuf<uint8_t> tmp;
+    tmp.alloc((int64_t)tb, s);
+    FXII_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, row_dofs, keys_sorted.p, iota.p, seg_rows.p, n_point_rows, 0,
+                                              end_bit, s));
+  }
+  unsigned long long h_max_seg = 0;
+  int h_bad[2] = {0, 0};
+  FXII_CUDA(cudaMemcpyAsync(&h_max_seg, max_seg.p, sizeof(h_max_seg), cudaMemcpyDeviceToHost, s));
+  FXII_CUDA(cudaMemcpyAsync(h_bad, bad.p, sizeof(h_bad), cudaMemcpyDeviceToHost, s));
+  FXII_CUDA(cudaStreamSynchronize(s));
+  FXII_CHECK(h_bad[0] == 0, "row_dofs out of range [0, n_rows_total)");
+  const uint64_t max_entries = h_max_seg * (uint64_t)seg;
+  FXII_CHECK(max_entries <= 16384, "a matrix row collects more than 16384 COO entries (unsupported)");
+  uint32_t cap = 1;
+  while (cap < max_entries) cap <<= 1;
+  if (cap < 2) cap = 2;
+
+  DevBuf<int64_t> row_nnz;
+  row_nnz.alloc(n_rows_total + 1, s);
+  FXII_CUDA(cudaMemsetAsync(row_nnz.p, 0, sizeof(int64_t) * (size_t)(n_rows_total + 1), s));
+  out->indptr.alloc(n_rows_total + 1, s);
+  const bool block_mode = cap > 64;
+  int threads, grid;
+  size_t smem;
+  if (block_mode) {
+    threads = cap >= 512 ? 256 : 128;
+    smem = (size_t)cap * sizeof(uint64_t);
+    grid = (int)std::min<int64_t>(n_rows_total, (int64_t)num_sms() * 8);
+    if (smem > 48 * 1024) {
+      FXII_CUDA(cudaFuncSetAttribute(rows_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FXII_CUDA(cudaFuncSetAttribute(rows_fill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+  } else {
+    threads = 256;
+    smem = (size_t)cap * sizeof(uint64_t) * (threads / 32);
+    grid = (int)std::min<int64_t>((n_rows_total + 7) / 8, (int64_t)num_sms() * 8);
+  }
+  if (grid < 1) grid = 1;
+  if (n_rows_total > 0) {
+    if (block_mode)
+      rows_count_kernel<true><<<grid, threads, smem, s>>>(seg_ptr.p, seg_rows.p, coo_cols, seg, n_rows_total, cap, row_nnz.p);
+    else
+      rows_count_kernel<false><<<grid, threads, smem, s>>>(seg_ptr.p, seg_rows.p, coo_cols, seg, n_rows_total, cap, row_nnz.p);
+    FXII_CUDA(cudaGetLastError());
+  }
+  {
+    size_t tb = 0;
+    FXII_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, (const long long*)row_nnz.p, (long long*)out->indptr.p,
+                                            (int64_t)(n_rows_total + 1), s));
+    DevBuf<uint8_t> tmp;
+    tmp.alloc((int64_t)tb, s);
+    FXII_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, (const long long*)row_nnz.p, (long long*)out->indptr.p,
+                                            (int64_t)(n_rows_total + 1), s));
+  }
+  int64_t nnz = 0;
+  FXII_CUDA(cudaMemcpyAsync(&nnz, out->indptr.p + n_rows_total, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  FXII_CUDA(cudaStreamSynchronize(s));
+  out->nnz = nnz;
+  out->indices.alloc(nnz, s);
+  out->values.alloc(nnz, s);
+  if (n_rows_total > 0 && nnz > 0) {
+    if (block_mode)
+      rows_fill_kernel<true><<<grid, threads, smem, s>>>(seg_ptr.p, seg_rows.p, coo_cols, coo_vals, seg, n_rows_total, cap,
+                                                         out->indptr.p, out->indices.p, out->values.p);
+    else
+      rows_fill_kernel<false><<<grid, threads, smem, s>>>(seg_ptr.p, seg_rows.p, coo_cols, coo_vals, seg, n_rows_total, cap,
+                                                          out->indptr.p, out->indices.p, out->values.p);
+    FXII_CUDA(cudaGetLastError());
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr* out, fxii_pi_stats* stats,
+                 bool keep_points) {
+  const fxii_mesh* m = sp->mesh;
+  const int nd = sp->nd;
+  const int nq = rows->nq;
+  const int64_t Nr = rows->n_point_rows;
+  const int64_t Np = Nr * nq;
+  const int64_t E = Np * nd;
+  rows->nd = nd;
+  cudaEvent_t ev[4];
+  for (auto& e : ev) FXII_CUDA(cudaEventCreate(&e));
+  FXII_CUDA(cudaEventRecord(ev[0], s));
+  if (rows->kind != FXII_OP_POINTS) {
+    rows->frames.alloc(kFrame * Nr, s);
+    if (Nr > 0) {
+      row_frames_kernel<<<grid_for(Nr, 128, 16), 128, 0, s>>>(rows->gx.p, rows->gcells.p, rows->cells_k.p, rows->xref.p,
+                                                              rows->nip, rows->radius.p, rows->radius_per_row, rows->kind,
+                                                              Nr, rows->frames.p);
+      FXII_CUDA(cudaGetLastError());
+    }
+  }
+  FXII_CUDA(cudaEventRecord(ev[1], s));
+  rows->cell.alloc(Np, s);
+  rows->ncoll.alloc(Np, s);
+  if (keep_points) rows->points.alloc(3 * Np, s);
+  else rows->points.release();
+  rows->coo_cols.alloc(E, s);
+  rows->coo_vals.alloc(E, s);
+  DevBuf<PiCounters> counters;
+  counters.alloc(1, s);
+  FXII_CUDA(cudaMemsetAsync(counters.p, 0, sizeof(PiCounters), s));
+  if (Np > 0) {
+    const int threads = 128;
+    const int grid = grid_for(Np, threads, 12);
+    const size_t smem = (rows->kind == FXII_OP_CIRCLE || rows->kind == FXII_OP_DISK) ? sizeof(double) * 4 * (size_t)nq : 0;
+    FXII_CHECK(smem <= 48 * 1024, "operator table too large for shared memory (nq > 1536)");
+    const int4* cn = reinterpret_cast<const int4*>(m->cell_nodes.p);
+    if (nd == 4)
+      pi_locate_tabulate_kernel<4><<<grid, threads, smem, s>>>(
+          m->nodes.p, m->cellgeo.p, m->x.p, cn, m->padding, sp->dofmap.p, rows->frames.p, rows->table.p, rows->w.p,
+          rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, nq, Np, rows->cell.p, rows->ncoll.p, rows->points.p,
+          rows->coo_cols.p, rows->coo_vals.p, counters.p);
+    else
+      pi_locate_tabulate_kernel<10><<<grid, threads, smem, s>>>(
+          m->nodes.p, m->cellgeo.p, m->x.p, cn, m->padding, sp->dofmap.p, rows->frames.p, rows->table.p, rows->w.p,
+          rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, nq, Np, rows->cell.p, rows->ncoll.p, rows->points.p,
+          rows->coo_cols.p, rows->coo_vals.p, counters.p);
+    FXII_CUDA(cudaGetLastError());
+  }
+  FXII_CUDA(cudaEventRecord(ev[2], s));
+  coo_segments_to_csr(rows->row_dofs.p, Nr, rows->n_rows_total, nq * nd, rows->coo_cols.p, rows->coo_vals.p, sp->n_dofs, s,
+                      out);
+  FXII_CUDA(cudaEventRecord(ev[3], s));
+  PiCounters h;
+  FXII_CUDA(cudaMemcpyAsync(&h, counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  FXII_CUDA(cudaStreamSynchronize(s));
+  if (stats) {
+    stats->n_points = Np;
+    stats->n_entries = E;
+    stats->n_not_found = (int64_t)h.not_found;
+    stats->n_ties = (int64_t)h.ties;
+    stats->n_fallback = (int64_t)h.fallback;
+    stats->ms_frames = elapsed_ms(ev[0], ev[1]);
+    stats->ms_locate = elapsed_ms(ev[1], ev[2]);
+    stats->ms_csr = elapsed_ms(ev[2], ev[3]);
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (h.not_found > 0)
+    throw Error(FXII_E_NOT_FOUND, std::to_string(h.not_found) + " of " + std::to_string(Np) +
+                                      " points lie in no cell of the 3D mesh (interpolation.py:78)");
+}
+
+}  // namespace fxii

@@ -1,0 +1,281 @@
+"""``create_interpolation_matrix`` — the hot entry point (reference: interpolation.py:15-251),
+same signature and return triple, built on the CUDA path behind include/fxii.h.
+
+Stage map (reference line -> here):
+  :43-53   interpolation points, cells_K, red_op.compute_quadrature  -> DeviceRows (points are
+           generated on the device for PointwiseTrace / Circle / Disk; generic operators run
+           compute_quadrature on the host and upload the points)
+  :66-68   determine_point_ownership                                 -> LBVH location kernel
+  :116     evaluate_basis_function (pull_back + tabulation)          -> fused in the same kernel
+  :140-163 SparsityPattern                                           -> COO -> CSR kernels
+  :205-250 value insertion, first-visit-wins, assemble               -> COO -> CSR kernels
+The MPI plumbing (:82-137) is the identity on a serial communicator and is not reproduced;
+distributed 3D meshes raise NotImplementedError (no CPU fallback by design).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .sparse import DeviceCSR, MatrixCSR
+
+__all__ = ["DeviceMesh", "DeviceRows", "DeviceSpace", "PiStats", "create_interpolation_matrix", "device_space"]
+
+
+class PiStats(dict):
+    """Counters and per-stage device times of the last assembly (fxii_pi_stats)."""
+
+
+class DeviceMesh:
+    """Ω on the device: packed cell geometry + LBVH.  Built once per (mesh, tol) and cached on the
+    mesh object — the reference rebuilds dolfinx's tree on every call (interpolation.py:66-68)."""
+
+    def __init__(self, x: np.ndarray, cells: np.ndarray, padding: float, stream: int | None = None):
+        _lib.require_cuda()
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        cells = np.ascontiguousarray(cells, dtype=np.int32)
+        if x.ndim != 2 or x.shape[1] != 3:
+            raise ValueError("mesh.geometry.x must have shape (n, 3)")
+        if cells.ndim != 2 or cells.shape[1] != 4:
+            raise NotImplementedError("only affine tetrahedra (4 geometry nodes per cell) are supported")
+        if cells.size and (cells.min() < 0 or cells.max() >= x.shape[0]):
+            raise ValueError("cell node index out of range")
+        self.n_cells, self.n_nodes, self.padding = cells.shape[0], x.shape[0], float(padding)
+        out = C.c_void_p()
+        s = _lib.current_stream() if stream is None else stream
+        _lib.check(_lib.load().fxii_mesh_create(_lib.ptr(x), x.shape[0], _lib.ptr(cells), cells.shape[0], float(padding), s,
+                                                C.byref(out)))
+        self._h = out
+
+    def info(self) -> dict:
+        a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+        _lib.check(_lib.load().fxii_mesh_info(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return dict(n_cells=a.value, n_nodes=b.value, device_bytes=c.value, max_depth=d.value)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.load().fxii_mesh_destroy(h)
+            except Exception:
+                pass
+
+
+class DeviceSpace:
+    """V on the device: the cell dofmap next to its mesh."""
+
+    def __init__(self, mesh: DeviceMesh, dofmap: np.ndarray, degree: int, n_dofs: int, stream: int | None = None):
+        dofmap = np.ascontiguousarray(dofmap, dtype=np.int32)
+        if dofmap.shape[0] != mesh.n_cells:
+            raise ValueError("dofmap rows must equal the number of cells")
+        if dofmap.size and (dofmap.min() < 0 or dofmap.max() >= n_dofs):
+            raise ValueError("dof index out of range")
+        self.mesh, self.nd, self.degree, self.n_dofs = mesh, dofmap.shape[1], int(degree), int(n_dofs)
+        out = C.c_void_p()
+        s = _lib.current_stream() if stream is None else stream
+        _lib.check(_lib.load().fxii_space_create(mesh._h, _lib.ptr(dofmap), dofmap.shape[1], int(degree), int(n_dofs), s,
+                                                 C.byref(out)))
+        self._h = out
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.load().fxii_space_destroy(h)
+            except Exception:
+                pass
+
+
+class DeviceRows:
+    """The Γ side of one Π build on the device (fxii_rows)."""
+
+    def __init__(self, handle: C.c_void_p, n_point_rows: int, nq: int, n_rows_total: int):
+        self._h = handle
+        self.n_point_rows, self.nq, self.n_rows_total = n_point_rows, nq, n_rows_total
+        self.nd = None
+
+    @classmethod
+    def from_gamma(cls, gx, gcells, cells_k, xref, row_dofs, n_rows_total, desc: dict, stream=None) -> "DeviceRows":
+        gx = np.ascontiguousarray(gx, dtype=np.float64)
+        gcells = np.ascontiguousarray(gcells, dtype=np.int32)
+        cells_k = np.ascontiguousarray(cells_k, dtype=np.int32)
+        xref = np.ascontiguousarray(np.asarray(xref, dtype=np.float64).reshape(-1))
+        row_dofs = np.ascontiguousarray(np.asarray(row_dofs, dtype=np.int32).reshape(-1))
+        nip = xref.shape[0]
+        assert row_dofs.shape[0] == cells_k.shape[0] * nip
+        kind, nq = desc["kind"], int(desc["nq"])
+        table = w = radius = None
+        per_row = 0
+        if kind != _lib.OP_TRACE:
+            table = np.ascontiguousarray(desc["table"], dtype=np.float64)
+            w = np.ascontiguousarray(desc["w"], dtype=np.float64)
+            if "cell_radius" in desc:
+                radius = np.ascontiguousarray(np.repeat(desc["cell_radius"][cells_k], nip), dtype=np.float64)
+                per_row = 1
+            else:
+                radius = np.ascontiguousarray(desc["radius"], dtype=np.float64)
+                per_row = 1 if desc.get("radius_per_row") else 0
+                if per_row:
+                    assert radius.shape[0] == cells_k.shape[0] * nip
+        out = C.c_void_p()
+        s = _lib.current_stream() if stream is None else stream
+        _lib.check(_lib.load().fxii_rows_create(
+            _lib.ptr(gx), gx.shape[0], _lib.ptr(gcells), gcells.shape[0], _lib.ptr(cells_k), cells_k.shape[0],
+            _lib.ptr(xref), nip, _lib.ptr(row_dofs), int(n_rows_total), kind, nq, _lib.ptr(table), _lib.ptr(w),
+            _lib.ptr(radius), per_row, s, C.byref(out)))
+        return cls(out, cells_k.shape[0] * nip, nq, int(n_rows_total))
+
+    @classmethod
+    def from_points(cls, points, weights, scales, row_dofs, n_rows_total, stream=None) -> "DeviceRows":
+        scales = np.ascontiguousarray(scales, dtype=np.float64).reshape(-1)
+        nr = scales.shape[0]
+        weights = np.ascontiguousarray(weights, dtype=np.float64).reshape(nr, -1)
+        nq = weights.shape[1] if nr else 1
+        pts = np.asarray(points, dtype=np.float64).reshape(nr * nq, -1)
+        p3 = np.zeros((nr * nq, 3))
+        p3[:, : pts.shape[1]] = pts  # pad to 3D (interpolation.py:56-62)
+        row_dofs = np.ascontiguousarray(np.asarray(row_dofs, dtype=np.int32).reshape(-1))
+        assert row_dofs.shape[0] == nr
+        out = C.c_void_p()
+        s = _lib.current_stream() if stream is None else stream
+        _lib.check(_lib.load().fxii_rows_create_points(_lib.ptr(p3), _lib.ptr(weights), _lib.ptr(scales), nr, nq,
+                                                       _lib.ptr(row_dofs), int(n_rows_total), s, C.byref(out)))
+        return cls(out, nr, nq, int(n_rows_total))
+
+    def keep_points(self, flag: bool = True):
+        _lib.check(_lib.load().fxii_rows_keep_points(self._h, 1 if flag else 0))
+
+    def assemble(self, space: DeviceSpace, stream=None, allow_not_found: bool = False):
+        """Run the Π assembly; returns (DeviceCSR, PiStats)."""
+        out = C.c_void_p()
+        st = _lib.PiStats()
+        s = _lib.current_stream() if stream is None else stream
+        rc = _lib.load().fxii_pi_assemble(space._h, self._h, s, C.byref(out), C.byref(st))
+        self.nd = space.nd
+        stats = PiStats({k: getattr(st, k) for k, _ in _lib.PiStats._fields_})
+        if rc == _lib.FXII_E_NOT_FOUND and allow_not_found and out.value:
+            return DeviceCSR(out.value), stats
+        if rc != _lib.FXII_OK and out.value:
+            _lib.load().fxii_csr_destroy(out)
+        _lib.check(rc)
+        return DeviceCSR(out.value), stats
+
+    def diagnostics(self, points: bool = False):
+        """(owning cell i32[Np], colliding-set size u8[Np][, points f64[Np,3]])."""
+        Np = self.n_point_rows * self.nq
+        cell = np.empty(Np, dtype=np.int32)
+        ncoll = np.empty(Np, dtype=np.uint8)
+        pts = np.empty((Np, 3), dtype=np.float64) if points else None
+        _lib.check(_lib.load().fxii_rows_download_diag(self._h, _lib.ptr(cell), _lib.ptr(ncoll), _lib.ptr(pts),
+                                                       _lib.current_stream()))
+        return (cell, ncoll, pts) if points else (cell, ncoll)
+
+    def coo(self):
+        """(cols i32[E], vals f64[E]) exactly as the locate kernel wrote them."""
+        E = self.n_point_rows * self.nq * self.nd
+        cols = np.empty(E, dtype=np.int32)
+        vals = np.empty(E, dtype=np.float64)
+        _lib.check(_lib.load().fxii_rows_download_coo(self._h, _lib.ptr(cols), _lib.ptr(vals), _lib.current_stream()))
+        return cols, vals
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.load().fxii_rows_destroy(h)
+            except Exception:
+                pass
+
+
+# ---- extraction of the arrays from (dolfinx-like) objects ---------------------------------------
+def _element_degree(V) -> int:
+    el = V.element
+    if hasattr(el, "degree"):
+        return int(el.degree)
+    return int(el.basix_element.degree)  # dolfinx
+
+
+def _comm_size(mesh) -> int:
+    comm = getattr(mesh, "comm", None)
+    return 1 if comm is None else int(getattr(comm, "size", 1))
+
+
+def device_space(V, tol: float = 1.0e-8) -> DeviceSpace:
+    """Device handles of V, cached on the Python objects (mesh: per tol; space: per V)."""
+    mesh = V.mesh
+    if _comm_size(mesh) > 1:
+        raise NotImplementedError("distributed 3D meshes are not supported on the device path (no CPU fallback)")
+    if getattr(V.dofmap, "bs", 1) != 1:
+        raise NotImplementedError("blocked function spaces (bs > 1) are not supported yet")
+    cache = mesh.__dict__.setdefault("_fxii_meshes", {})
+    dmesh = cache.get(float(tol))
+    if dmesh is None:
+        x = np.asarray(mesh.geometry.x)
+        dmesh = cache[float(tol)] = DeviceMesh(x, np.asarray(mesh.geometry.dofmap), tol)
+    spaces = V.__dict__.setdefault("_fxii_spaces", {})
+    dspace = spaces.get(float(tol))
+    if dspace is None:
+        n_dofs = V.dofmap.index_map.size_local + V.dofmap.index_map.num_ghosts
+        dspace = spaces[float(tol)] = DeviceSpace(dmesh, np.asarray(V.dofmap.list), _element_degree(V), n_dofs)
+    return dspace
+
+
+def device_rows(K, red_op, cells_K=None) -> DeviceRows:
+    """interpolation.py:41-64: interpolation points of K, cells_K, the operator's quadrature."""
+    mesh_to = K.mesh
+    ref_points = np.asarray(K.element.interpolation_points, dtype=np.float64)
+    if cells_K is None:
+        n = mesh_to.topology.index_map(mesh_to.topology.dim).size_local
+        cells_K = np.arange(n, dtype=np.int32)
+    cells_K = np.ascontiguousarray(cells_K, dtype=np.int32)
+    assert K.element.interpolation_ident
+    assert not K.element.needs_dof_transformations
+    if getattr(K.dofmap, "bs", 1) != 1:
+        raise NotImplementedError("blocked K spaces (bs > 1) are not supported yet")
+    k_list = np.asarray(K.dofmap.list)
+    row_dofs = k_list[cells_K].reshape(-1)
+    n_rows_total = (K.dofmap.index_map.size_local + K.dofmap.index_map.num_ghosts) * K.dofmap.index_map_bs
+    if k_list.shape[1] != ref_points.shape[0]:
+        raise ValueError("K must have one dof per interpolation point")
+    on_device = hasattr(red_op, "device_descriptor") and red_op._mesh is mesh_to and mesh_to.topology.dim == 1 \
+        and np.asarray(mesh_to.geometry.dofmap).shape[1] == 2
+    if on_device:
+        from .restriction_operators import get_physical_points
+
+        desc = red_op.device_descriptor(lambda: get_physical_points(mesh_to, cells_K, ref_points))
+        return DeviceRows.from_gamma(np.asarray(mesh_to.geometry.x), np.asarray(mesh_to.geometry.dofmap), cells_K,
+                                     ref_points, row_dofs, n_rows_total, desc)
+    q = red_op.compute_quadrature(cells_K, ref_points)
+    return DeviceRows.from_points(q.points, q.weights, q.scales, row_dofs, n_rows_total)
+
+
+def create_interpolation_matrix(V, K, red_op, tol: float = 1.0e-8, use_petsc: bool = False, cells_K=None,
+                                complex_dtype: bool = False):
+    """Create an interpolation matrix from `V` to `K` with a specific reduction operator applied to
+    the interpolation points of `K`.
+
+    Args:
+        V: The function space to interpolate from (Lagrange P1/P2 on affine tetrahedra).
+        K: The function space to interpolate to (on the 1D mesh).
+        red_op: Reduction operator for each interpolation point on `K`.
+        tol: Tolerance (box padding) for determining point ownership.
+        use_petsc: Return a PETSc AIJ matrix (requires petsc4py) instead of a ``MatrixCSR``.
+        cells_K: Optional subset of the cells of K to process.
+        complex_dtype: Not supported on the device path.
+
+    Returns:
+        ``(A, imap_K, imap_V)``: the matrix and the (serial: unchanged) index maps of K and V.
+    """
+    if complex_dtype:
+        raise NotImplementedError("complex matrices are not supported on the device path")
+    dspace = device_space(V, tol)
+    rows = device_rows(K, red_op, cells_K)
+    csr, stats = rows.assemble(dspace)
+    A = MatrixCSR(csr, stats=stats, rows=rows)
+    imap_K, imap_V = K.dofmap.index_map, V.dofmap.index_map
+    if use_petsc:
+        return A.to_petsc(), imap_K, imap_V
+    return A, imap_K, imap_V

@@ -1,0 +1,209 @@
+"""Device-resident CSR matrix handle and the block products on it.
+
+``DeviceCSR`` wraps an ``fxii_csr*``.  Products replace the PETSc calls of the reference's
+``apply_matrix_replacer`` (matrix_assembler.py:175-258): ``transpose()`` = ``Mat.transpose``,
+``matmult()`` = ``Mat.matMult``, ``mult()`` = ``Mat.mult``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+class DeviceCSR:
+    def __init__(self, handle: int):
+        self._h = C.c_void_p(handle)
+        n_rows, n_cols, nnz = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(_lib.load().fxii_csr_info(self._h, C.byref(n_rows), C.byref(n_cols), C.byref(nnz)))
+        self.shape = (n_rows.value, n_cols.value)
+        self.nnz = nnz.value
+
+    # -- construction ----------------------------------------------------------------------------
+    @classmethod
+    def from_host(cls, indptr, indices, data, shape, stream: int | None = None) -> "DeviceCSR":
+        _lib.require_cuda()
+        indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(indices, dtype=np.int32)
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        assert indptr.shape[0] == shape[0] + 1 and indices.shape[0] == data.shape[0] == indptr[-1]
+        out = C.c_void_p()
+        s = _lib.current_stream() if stream is None else stream
+        _lib.check(_lib.load().fxii_csr_upload(shape[0], shape[1], int(indptr[-1]), _lib.ptr(indptr), _lib.ptr(indices),
+                                               _lib.ptr(data), s, C.byref(out)))
+        return cls(out.value)
+
+    @classmethod
+    def from_scipy(cls, mat) -> "DeviceCSR":
+        mat = mat.tocsr()
+        mat.sort_indices()
+        return cls.from_host(mat.indptr, mat.indices, mat.data, mat.shape)
+
+    @classmethod
+    def from_device_arrays(cls, indptr_t, indices_t, values_t, shape) -> "DeviceCSR":
+        """Copy torch CUDA tensors (int64 / int32 / float64) into a new matrix, e.g. after the
+        NCCL all-gather of row shards."""
+        out = C.c_void_p()
+        nnz = int(indices_t.numel())
+        _lib.check(_lib.load().fxii_csr_from_device(shape[0], shape[1], nnz, indptr_t.data_ptr(), indices_t.data_ptr(),
+                                                    values_t.data_ptr(), _lib.current_stream(), C.byref(out)))
+        return cls(out.value)
+
+    # -- access ----------------------------------------------------------------------------------
+    def to_host(self):
+        """(indptr int64, indices int32, data float64) numpy arrays."""
+        indptr = np.empty(self.shape[0] + 1, dtype=np.int64)
+        indices = np.empty(self.nnz, dtype=np.int32)
+        data = np.empty(self.nnz, dtype=np.float64)
+        _lib.check(_lib.load().fxii_csr_download(self._h, _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(data),
+                                                 _lib.current_stream()))
+        return indptr, indices, data
+
+    def to_host_into(self, indptr, indices, data):
+        """Download into caller-provided (e.g. pinned) buffers."""
+        _lib.check(_lib.load().fxii_csr_download(self._h, indptr.ctypes.data, indices.ctypes.data, data.ctypes.data,
+                                                 _lib.current_stream()))
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+
+        indptr, indices, data = self.to_host()
+        return sp.csr_matrix((data, indices, indptr), shape=self.shape)
+
+    def device_tensors(self):
+        """Zero-copy torch views (indptr, indices, values) of the device arrays; valid while this
+        object lives."""
+        import torch
+
+        p0, p1, p2 = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _lib.check(_lib.load().fxii_csr_device_ptrs(self._h, C.byref(p0), C.byref(p1), C.byref(p2)))
+        dev = torch.cuda.current_device()
+
+        def view(ptr, n, typestr, dtype):
+            if n == 0 or not ptr:
+                return torch.empty(0, dtype=dtype, device=f"cuda:{dev}")
+
+            class _Arr:
+                __cuda_array_interface__ = dict(shape=(n,), typestr=typestr, data=(ptr, False), version=3, strides=None)
+
+            holder = _Arr()
+            t = torch.as_tensor(holder, device=f"cuda:{dev}")
+            t._fxii_owner = self  # keep the matrix alive
+            return t
+
+        return (
+            view(p0.value, self.shape[0] + 1, "<i8", torch.int64),
+            view(p1.value, self.nnz, "<i4", torch.int32),
+            view(p2.value, self.nnz, "<f8", torch.float64),
+        )
+
+    # -- products --------------------------------------------------------------------------------
+    def transpose(self) -> "DeviceCSR":
+        out = C.c_void_p()
+        _lib.check(_lib.load().fxii_csr_transpose(self._h, _lib.current_stream(), C.byref(out)))
+        return DeviceCSR(out.value)
+
+    def matmult(self, other: "DeviceCSR", row_begin: int = 0, row_end: int = -1, return_ip: bool = False):
+        out = C.c_void_p()
+        ip = C.c_int64()
+        _lib.check(_lib.load().fxii_spgemm(self._h, other._h, row_begin, row_end, _lib.current_stream(), C.byref(out),
+                                           C.byref(ip)))
+        c = DeviceCSR(out.value)
+        return (c, ip.value) if return_ip else c
+
+    def scale_rows(self, d) -> "DeviceCSR":
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        assert d.shape == (self.shape[0],)
+        _lib.check(_lib.load().fxii_csr_scale_rows(self._h, _lib.ptr(d), _lib.current_stream()))
+        return self
+
+    def mult(self, u) -> np.ndarray:
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        assert u.shape == (self.shape[1],)
+        y = np.empty(self.shape[0], dtype=np.float64)
+        _lib.check(_lib.load().fxii_csr_spmv(self._h, _lib.ptr(u), _lib.ptr(y), _lib.current_stream()))
+        return y
+
+    def mult_transpose(self, u) -> np.ndarray:
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        assert u.shape == (self.shape[0],)
+        y = np.empty(self.shape[1], dtype=np.float64)
+        _lib.check(_lib.load().fxii_csr_spmv_t(self._h, _lib.ptr(u), _lib.ptr(y), _lib.current_stream()))
+        return y
+
+    def copy(self) -> "DeviceCSR":
+        a, b, c = self.device_tensors()
+        return DeviceCSR.from_device_arrays(a, b, c, self.shape)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.load().fxii_csr_destroy(h)
+            except Exception:
+                pass
+
+
+class MatrixCSR:
+    """What ``create_interpolation_matrix(..., use_petsc=False)`` returns: the surface of
+    ``dolfinx.la.MatrixCSR`` the callers use (``indptr``, ``indices``, ``data``, ``to_scipy``,
+    ``to_dense``) over a device-resident matrix.  Host arrays are downloaded on first access."""
+
+    def __init__(self, device: DeviceCSR, stats=None, rows=None):
+        self.device = device
+        self.stats = stats
+        self.rows = rows  # DeviceRows of the build (per-point diagnostics), may be None
+        self._host = None
+
+    def _arrays(self):
+        if self._host is None:
+            self._host = self.device.to_host()
+        return self._host
+
+    @property
+    def shape(self):
+        return self.device.shape
+
+    @property
+    def indptr(self):
+        return self._arrays()[0]
+
+    @property
+    def indices(self):
+        return self._arrays()[1]
+
+    @property
+    def data(self):
+        return self._arrays()[2]
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+
+        a, b, c = self._arrays()
+        return sp.csr_matrix((c, b, a), shape=self.shape)
+
+    def to_dense(self):
+        return self.to_scipy().toarray()
+
+    def mult(self, u):
+        return self.device.mult(u)
+
+    def scatter_reverse(self):  # serial: nothing to accumulate
+        return None
+
+    def to_petsc(self):
+        """PETSc AIJ with the CSR handed over in one call (instead of per-entry setValuesLocal,
+        interpolation.py:182-188,243-248)."""
+        try:
+            from petsc4py import PETSc
+        except ImportError as e:
+            raise RuntimeError("use_petsc=True needs petsc4py, which is not installed") from e
+        a, b, c = self._arrays()
+        if self.device.nnz >= 2**31 and PETSc.IntType().itemsize == 4:
+            raise RuntimeError("matrix needs 64-bit PETSc indices")
+        A = PETSc.Mat().createAIJ(size=self.shape, csr=(a.astype(PETSc.IntType), b.astype(PETSc.IntType), c))
+        A.assemble()
+        return A

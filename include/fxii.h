@@ -1,0 +1,148 @@
+/* fxii.h — C ABI of the B200-native reduction-operator assembly path.
+ *
+ * Drop-in boundary for the hot path of scientificcomputing/fenicsx_ii
+ * (citations are file:line under /root/reference/src/fenicsx_ii/):
+ *
+ *   create_interpolation_matrix          interpolation.py:15-251
+ *   ReductionOperator.compute_quadrature restriction_operators.py:17-47 (PointwiseTrace :60-68,
+ *                                        Circle :143-205, Disk :256-315)
+ *   Mat.transpose / Mat.matMult products matrix_assembler.py:175-258
+ *   K.mult (Π·u)                         assembly.py:61-67
+ *
+ * The reference has no FFI of its own (pure Python over dolfinx/PETSc); these entry points are
+ * what a ctypes / nanobind stub on the reference side binds.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative FXII_E_* code on failure;
+ *    fxii_last_error() returns a thread-local message.  No exceptions cross the boundary.
+ *  - all input arrays are HOST pointers unless the name ends in _dev; inputs are copied, never
+ *    retained.  Handles own their device memory until *_destroy.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *    stream-ordered; functions that must return a size to the host synchronise the stream.
+ *  - CSR: indptr int64[n_rows+1], indices int32[nnz] ascending and unique per row,
+ *    values double[nnz]; explicit zeros are preserved.
+ *  - the library acts on the CURRENT CUDA device of the calling thread.
+ */
+#ifndef FXII_H
+#define FXII_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FXII_OK 0
+#define FXII_E_INVALID (-1)   /* bad argument */
+#define FXII_E_CUDA (-2)      /* CUDA runtime error */
+#define FXII_E_NOT_FOUND (-3) /* some points lie in no cell (mirrors the assert at interpolation.py:78) */
+#define FXII_E_UNSUPPORTED (-4)
+
+/* operator kinds (restriction_operators.py) */
+#define FXII_OP_TRACE 0  /* PointwiseTrace :50-75 */
+#define FXII_OP_CIRCLE 1 /* Circle :78-205 */
+#define FXII_OP_DISK 2   /* Disk :208-315 */
+#define FXII_OP_POINTS 3 /* generic operator: caller ran compute_quadrature on the host */
+
+typedef struct fxii_mesh fxii_mesh;   /* Ω: packed affine cell geometry + LBVH (replaces the tree
+                                         dolfinx builds inside determine_point_ownership,
+                                         interpolation.py:66-68) */
+typedef struct fxii_space fxii_space; /* V: cell dofmap on a mesh (V.dofmap.list) */
+typedef struct fxii_rows fxii_rows;   /* the Γ side of one Π build: cells_K, reference points,
+                                         K dof per row, operator tables, radii */
+typedef struct fxii_csr fxii_csr;     /* device CSR matrix */
+
+int fxii_version(void);
+const char* fxii_last_error(void);
+int fxii_device_count(int* n);
+int fxii_set_device(int device);
+int fxii_sm_count(int* n);
+
+/* ---- Ω mesh (affine tetrahedra) ---------------------------------------------------------- */
+/* x: [n_nodes,3] f64, cell_nodes: [n_cells,4] i32 (mesh.geometry.x / mesh.geometry.dofmap).
+ * padding: AABB padding of determine_point_ownership (tol of interpolation.py:19). */
+int fxii_mesh_create(const double* x, int64_t n_nodes, const int32_t* cell_nodes, int64_t n_cells,
+                     double padding, void* stream, fxii_mesh** out);
+int fxii_mesh_info(const fxii_mesh* m, int64_t* n_cells, int64_t* n_nodes, int64_t* device_bytes,
+                   int32_t* max_depth);
+int fxii_mesh_destroy(fxii_mesh* m);
+
+/* ---- V space ----------------------------------------------------------------------------- */
+/* dofmap: [n_cells, nd] i32 with nd = 4 (degree 1) or 10 (degree 2), basix dof order. */
+int fxii_space_create(fxii_mesh* mesh, const int32_t* dofmap, int32_t nd, int32_t degree,
+                      int64_t n_dofs, void* stream, fxii_space** out);
+int fxii_space_destroy(fxii_space* s);
+
+/* ---- Γ rows ------------------------------------------------------------------------------ */
+/* gx [n_gnodes,3], gcells [n_gcells,2]: Γ geometry.  cells_k [n_cells_k]: Γ cells processed
+ * (cells_K of interpolation.py:47-51).  xref [nip]: reference interpolation points of K (:43).
+ * row_dofs [n_cells_k*nip]: K.dofmap.list[cells_K] flattened.  table [nq,3], w [nq]: operator
+ * tables (NULL for TRACE).  radius: [n_cells_k*nip] when radius_per_row != 0, else [1]. */
+int fxii_rows_create(const double* gx, int64_t n_gnodes, const int32_t* gcells, int64_t n_gcells,
+                     const int32_t* cells_k, int64_t n_cells_k, const double* xref, int32_t nip,
+                     const int32_t* row_dofs, int64_t n_rows_total, int32_t kind, int32_t nq,
+                     const double* table, const double* w, const double* radius,
+                     int32_t radius_per_row, void* stream, fxii_rows** out);
+/* generic operator: points [n_point_rows,nq,3], weights [n_point_rows,nq], scales [n_point_rows]
+ * as returned by ReductionOperator.compute_quadrature (quadrature.py:11-20). */
+int fxii_rows_create_points(const double* points, const double* weights, const double* scales,
+                            int64_t n_point_rows, int32_t nq, const int32_t* row_dofs,
+                            int64_t n_rows_total, void* stream, fxii_rows** out);
+int fxii_rows_destroy(fxii_rows* r);
+/* diagnostics: also materialise the generated 3D points [Np,3] (off by default: the points are
+ * otherwise never written to HBM) */
+int fxii_rows_keep_points(fxii_rows* r, int32_t flag);
+
+/* ---- Π assembly -------------------------------------------------------------------------- */
+typedef struct {
+  int64_t n_points;     /* Np = n_point_rows*nq */
+  int64_t n_entries;    /* E = Np*nd COO entries */
+  int64_t n_not_found;  /* points owned by no cell */
+  int64_t n_ties;       /* points colliding with more than one cell */
+  int64_t n_fallback;   /* points assigned by the nearest-cell fallback */
+  float ms_frames, ms_locate, ms_csr; /* device time of the three stages (CUDA events) */
+} fxii_pi_stats;
+
+/* Builds Π (n_rows_total x n_dofs).  Leaves per-point diagnostics on `rows`
+ * (fxii_rows_download_diag).  Returns FXII_E_NOT_FOUND when n_not_found > 0. */
+int fxii_pi_assemble(const fxii_space* space, fxii_rows* rows, void* stream, fxii_csr** out,
+                     fxii_pi_stats* stats);
+/* owning cell i32[Np], colliding-set size u8[Np] (saturating), points f64[Np,3] (any may be NULL) */
+int fxii_rows_download_diag(const fxii_rows* rows, int32_t* cell, uint8_t* n_colliding,
+                            double* points, void* stream);
+/* COO as written by the locate kernel: cols i32[E], vals f64[E]; entry e = p*nd + d belongs to
+ * point p = e/nd, point row r = p/nq, matrix row row_dofs[r]. */
+int fxii_rows_download_coo(const fxii_rows* rows, int32_t* cols, double* vals, void* stream);
+
+/* ---- CSR objects and products ------------------------------------------------------------ */
+int fxii_csr_upload(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* indptr,
+                    const int32_t* indices, const double* values, void* stream, fxii_csr** out);
+/* adopt copies of DEVICE arrays (e.g. after an NCCL all-gather) */
+int fxii_csr_from_device(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* indptr_dev,
+                         const int32_t* indices_dev, const double* values_dev, void* stream,
+                         fxii_csr** out);
+int fxii_csr_info(const fxii_csr* a, int64_t* n_rows, int64_t* n_cols, int64_t* nnz);
+int fxii_csr_device_ptrs(const fxii_csr* a, void** indptr_dev, void** indices_dev, void** values_dev);
+int fxii_csr_download(const fxii_csr* a, int64_t* indptr, int32_t* indices, double* values,
+                      void* stream);
+int fxii_csr_destroy(fxii_csr* a);
+
+/* Mat.transpose (matrix_assembler.py:184,236): rows of the result keep the source row order */
+int fxii_csr_transpose(const fxii_csr* a, void* stream, fxii_csr** out);
+/* Mat.matMult (matrix_assembler.py:185,210,237,245): symbolic pattern kept, columns sorted,
+ * c_ij accumulated over k in A's column order.  ip (may be NULL) = intermediate products.
+ * Optional row window [row_begin,row_end) of A (the V-dof row shard of SURVEY §8e);
+ * pass 0, -1 for all rows. */
+int fxii_spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row_end,
+                void* stream, fxii_csr** out, int64_t* ip);
+/* rows scaled by a diagonal: (diag(d)·A); d host [n_rows] — M_Γ·Π for a quadrature-element mass */
+int fxii_csr_scale_rows(fxii_csr* a, const double* d, void* stream);
+/* y = A·u (assembly.py:67); u host [n_cols], y host [n_rows] */
+int fxii_csr_spmv(const fxii_csr* a, const double* u, double* y, void* stream);
+/* y = Aᵀ·u (vector_assembler.py:177); u host [n_rows], y host [n_cols] */
+int fxii_csr_spmv_t(const fxii_csr* a, const double* u, double* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FXII_H */

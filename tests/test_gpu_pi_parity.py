@@ -1,0 +1,132 @@
+"""GPU parity of Π against the CPU oracle, through the public API / C ABI.
+
+Bar (north_star): cell ownership, sparsity pattern and CSR indices bit-exact; values within
+1e-12 of the row scale."""
+
+import numpy as np
+import pytest
+
+from fenicsx_ii_b200 import create_interpolation_matrix
+from fenicsx_ii_b200 import synthetic as sy
+from fenicsx_ii_b200.mesh import functionspace
+from tests.helpers import assert_csr_parity, make_operator, oracle_pi, small_cfg
+
+pytestmark = pytest.mark.gpu
+
+
+def run_case(V, K, gamma, op_name, radius=None, degree=None, cells_K=None, cell_radius=None):
+    rad = cell_radius if cell_radius is not None else radius
+    op = make_operator(op_name, gamma, rad, degree)
+    A, imap_K, imap_V = create_interpolation_matrix(V, K, op, cells_K=cells_K)
+    ref = oracle_pi(V, K, gamma, op_name, radius, degree, cells_K=cells_K, return_coo=True, cell_radius=cell_radius)
+    cell, ncoll = A.rows.diagnostics()
+    np.testing.assert_array_equal(cell, ref["cell"])
+    np.testing.assert_array_equal(ncoll.astype(np.int64), np.minimum(ref["n_colliding"], 255))
+    cols, vals = A.rows.coo()
+    np.testing.assert_array_equal(cols, ref["cols"])
+    assert_csr_parity((A.indptr, A.indices, A.data), ref)
+    assert A.shape == (K.num_dofs, V.num_dofs)
+    assert imap_K is K.dofmap.index_map and imap_V is V.dofmap.index_map
+    return A, ref
+
+
+@pytest.mark.parametrize("op_name,radius,degree", [("trace", None, None), ("circle", 0.2, 5), ("circle", 0.05, 5),
+                                                   ("disk", 0.1, 3), ("disk", 0.07, 7)])
+def test_config1_straight_line_ties(cuda, op_name, radius, degree):
+    """Config 1 geometry (scaled down): the line x=y=0.5 lies on mesh edges, so every centre collides
+    with several tetrahedra; the lowest cell index must win on both sides."""
+    mesh, V = small_cfg(8, 8, 16)
+    gamma = sy.straight_line(17)
+    K = functionspace(gamma, ("Quadrature", 10))
+    A, ref = run_case(V, K, gamma, op_name, radius, degree)
+    assert (ref["n_colliding"] > 1).any()
+    np.testing.assert_allclose(np.asarray(A.to_scipy().sum(axis=1)).ravel(), 1.0, atol=1e-13)
+
+
+@pytest.mark.parametrize("kspace", [("Quadrature", 10), ("DG", 1), ("DG", 2), ("Lagrange", 1), ("Lagrange", 2)])
+@pytest.mark.parametrize("op_name,radius,degree", [("trace", None, None), ("circle", 0.03, 7)])
+def test_network_generic_position(cuda, kspace, op_name, radius, degree):
+    """Config 2 shape: polyline network in generic position; continuous K exercises first-visit-wins."""
+    mesh, V = small_cfg(12, 12, 12)
+    gamma = sy.polyline_network(400, 1 / 12, n_lines=5)
+    K = functionspace(gamma, kspace)
+    A, ref = run_case(V, K, gamma, op_name, radius, degree)
+
+
+@pytest.mark.parametrize("op_name,degree", [("circle", 15), ("circle", 126), ("disk", 7)])
+def test_p2_vessel_tree_per_segment_radius(cuda, op_name, degree):
+    """Config 3/4 shape: P2, vessel tree with per-segment radii, 64-point circle / 49-point disk."""
+    mesh, V = small_cfg(10, 10, 10, degree=2)
+    h = 1 / 10
+    gamma, seg_r = sy.vessel_tree(300, h / 2, r_min=0.2 * h, r_max=1.5 * h, branch_len=40)
+    K = functionspace(gamma, ("Quadrature", 10))
+    run_case(V, K, gamma, op_name, None, degree, cell_radius=seg_r)
+
+
+def test_cells_subset_and_callable_radius(cuda):
+    mesh, V = small_cfg(8, 8, 8)
+    gamma = sy.polyline_network(120, 1 / 8, n_lines=3, lo=0.25, hi=0.75)
+    K = functionspace(gamma, ("DG", 1))
+    cells_K = np.arange(5, 97, 3, dtype=np.int32)
+    rad = lambda x: 0.02 + 0.1 * x[2] ** 2  # noqa: E731
+    A, ref = run_case(V, K, gamma, "circle", rad, 9, cells_K=cells_K)
+    # rows of cells outside cells_K are empty
+    touched = np.zeros(K.num_dofs, dtype=bool)
+    touched[K.dofmap.list[cells_K].ravel()] = True
+    assert (np.diff(A.indptr)[~touched] == 0).all()
+
+
+def test_empty_cells(cuda):
+    mesh, V = small_cfg(4, 4, 4)
+    gamma = sy.straight_line(5)
+    K = functionspace(gamma, ("Quadrature", 4))
+    from fenicsx_ii_b200 import PointwiseTrace
+
+    A, _, _ = create_interpolation_matrix(V, K, PointwiseTrace(gamma), cells_K=np.zeros(0, dtype=np.int32))
+    assert A.device.nnz == 0 and A.shape == (K.num_dofs, V.num_dofs)
+
+
+def test_point_outside_raises(cuda):
+    from fenicsx_ii_b200 import PointwiseTrace
+    from fenicsx_ii_b200._lib import PointsNotFound
+
+    mesh, V = small_cfg(4, 4, 4)
+    nodes = np.array([[0.5, 0.5, 0.5], [0.5, 0.5, 1.5]])
+    gamma = sy.line_mesh(nodes)
+    K = functionspace(gamma, ("DG", 1))
+    with pytest.raises(PointsNotFound):
+        create_interpolation_matrix(V, K, PointwiseTrace(gamma))
+
+
+def test_mapped_restriction_host_points(cuda):
+    """Generic operators go through compute_quadrature on the host (FXII_OP_POINTS path)."""
+    from fenicsx_ii_b200 import MappedRestriction
+
+    mesh, V = small_cfg(6, 6, 6)
+    gamma = sy.polyline_network(60, 1 / 6, n_lines=2, lo=0.3, hi=0.6)
+    K = functionspace(gamma, ("DG", 1))
+    shift = lambda x: x + np.array([[0.05], [0.02], [-0.03]])  # noqa: E731
+    op = MappedRestriction(gamma, shift)
+    A, _, _ = create_interpolation_matrix(V, K, op)
+    q = op.compute_quadrature(np.arange(60, dtype=np.int32), K.element.interpolation_points)
+    from oracle import pi_oracle as orc
+
+    ref = orc.assemble_pi(mesh.geometry.x, mesh.geometry.dofmap, V.dofmap.list, 1, gamma.geometry.x, gamma.geometry.dofmap,
+                          K.dofmap.list, K.element.interpolation_points, "points", n_rows=K.num_dofs,
+                          points=q.points, weights=q.weights, scales=q.scales)
+    assert_csr_parity((A.indptr, A.indices, A.data), ref)
+    u = 2.0 * mesh.geometry.x[:, 0] - mesh.geometry.x[:, 2] + 0.3
+    np.testing.assert_allclose(A.mult(u), 2.0 * q.points[:, 0] - q.points[:, 2] + 0.3, rtol=1e-12, atol=1e-13)
+
+
+def test_run_to_run_bitwise_reproducible(cuda):
+    mesh, V = small_cfg(8, 8, 8, degree=2)
+    gamma, seg_r = sy.vessel_tree(200, 1 / 16, branch_len=50)
+    K = functionspace(gamma, ("Lagrange", 1))
+    from fenicsx_ii_b200 import Disk
+
+    op = Disk(gamma, seg_r, degree=5)
+    A1, _, _ = create_interpolation_matrix(V, K, op)
+    A2, _, _ = create_interpolation_matrix(V, K, op)
+    np.testing.assert_array_equal(A1.indices, A2.indices)
+    assert A1.data.tobytes() == A2.data.tobytes()
