@@ -44,6 +44,8 @@ class PiStats(C.Structure):
         ("ms_frames", C.c_float),
         ("ms_locate", C.c_float),
         ("ms_csr", C.c_float),
+        ("ms_csr_count", C.c_float),
+        ("ms_csr_fill", C.c_float),
     ]
 
 
@@ -59,6 +61,7 @@ SIGNATURES = {
     "fxii_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "fxii_set_device": (C.c_int, [C.c_int]),
     "fxii_sm_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "fxii_launch_count": (C.c_int64, []),
     "fxii_mesh_create": (C.c_int, [_vp, _i64, _vp, _i64, _dbl, _vp, C.POINTER(_vp)]),
     "fxii_mesh_info": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i32)]),
     "fxii_mesh_destroy": (C.c_int, [_vp]),

@@ -17,6 +17,9 @@ void csr_spmv(const fxii_csr* a, const double* u_host, double* y_host, cudaStrea
 }  // namespace fxii
 
 static thread_local std::string g_last_error;
+namespace fxii {
+int64_t g_launches = 0;
+}
 
 template <typename F>
 static int guarded(F&& f) {
@@ -50,6 +53,8 @@ int fxii_device_count(int* n) {
 int fxii_set_device(int device) {
   return guarded([&] { FXII_CUDA(cudaSetDevice(device)); });
 }
+
+int64_t fxii_launch_count(void) { return fxii::g_launches; }
 
 int fxii_sm_count(int* n) {
   return guarded([&] {

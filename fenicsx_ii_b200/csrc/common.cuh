@@ -82,6 +82,8 @@ struct DevBuf {
 };
 
 void init_pool_once();
+extern int64_t g_launches;  // kernels launched by this library (fxii_launch_count)
+#define FXII_LAUNCHED(n) (::fxii::g_launches += (n))
 
 // ---- handle layouts -------------------------------------------------------------------------
 struct alignas(16) BvhNode {  // 64 B: both child boxes live in the parent

@@ -72,7 +72,7 @@ void csr_transpose(const fxii_csr* a, cudaStream_t s, fxii_csr* out) {
   out->indices.alloc(nnz, s);
   out->values.alloc(nnz, s);
   if (nnz > 0) {
-    col_hist_kernel<<<grid_for(nnz, 256, 8), 256, 0, s>>>(a->indices.p, nnz, count.p);
+    { col_hist_kernel<<<grid_for(nnz, 256, 8), 256, 0, s>>>(a->indices.p, nnz, count.p); FXII_LAUNCHED(1); }
     FXII_CUDA(cudaGetLastError());
   }
   exclusive_scan_i64((const long long*)count.p, (long long*)out->indptr.p, a->n_cols + 1, s);
@@ -82,8 +82,8 @@ void csr_transpose(const fxii_csr* a, cudaStream_t s, fxii_csr* out) {
   iota.alloc(nnz, s);
   perm.alloc(nnz, s);
   keys_sorted.alloc(nnz, s);
-  expand_rows_kernel<<<grid_for(a->n_rows * 32, 256, 8), 256, 0, s>>>(a->indptr.p, a->n_rows, row_of.p);
-  iota32_kernel<<<grid_for(nnz, 256, 8), 256, 0, s>>>(iota.p, nnz);
+  { expand_rows_kernel<<<grid_for(a->n_rows * 32, 256, 8), 256, 0, s>>>(a->indptr.p, a->n_rows, row_of.p); FXII_LAUNCHED(1); }
+  { iota32_kernel<<<grid_for(nnz, 256, 8), 256, 0, s>>>(iota.p, nnz); FXII_LAUNCHED(1); }
   int end_bit = 1;
   while (end_bit < 31 && ((int64_t)1 << end_bit) < a->n_cols) ++end_bit;
   size_t tb = 0;
@@ -91,8 +91,8 @@ void csr_transpose(const fxii_csr* a, cudaStream_t s, fxii_csr* out) {
   DevBuf<uint8_t> tmp;
   tmp.alloc((int64_t)tb, s);
   FXII_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, a->indices.p, keys_sorted.p, iota.p, perm.p, nnz, 0, end_bit, s));
-  gather_transposed_kernel<<<grid_for(nnz, 256, 8), 256, 0, s>>>(perm.p, row_of.p, a->values.p, nnz, out->indices.p,
-                                                                 out->values.p);
+  { gather_transposed_kernel<<<grid_for(nnz, 256, 8), 256, 0, s>>>(perm.p, row_of.p, a->values.p, nnz, out->indices.p,
+                                                                 out->values.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
 }
 
@@ -295,7 +295,7 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
     if (ip_out) *ip_out = 0;
     return;
   }
-  spgemm_ub_kernel<<<grid_for(m * 32, 256, 8), 256, 0, s>>>(a->indptr.p, a->indices.p, b->indptr.p, row_begin, m, ub.p);
+  { spgemm_ub_kernel<<<grid_for(m * 32, 256, 8), 256, 0, s>>>(a->indptr.p, a->indices.p, b->indptr.p, row_begin, m, ub.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
   // total intermediate products
   DevBuf<int64_t> ip_dev;
@@ -312,8 +312,8 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
   DevBuf<int32_t> bin_of, iota, lists[4];
   bin_of.alloc(m, s);
   iota.alloc(m, s);
-  classify_rows_kernel<<<grid_for(m, 256, 8), 256, 0, s>>>(ub.p, m, T0, T1, T2, bin_of.p);
-  iota32_kernel<<<grid_for(m, 256, 8), 256, 0, s>>>(iota.p, m);
+  { classify_rows_kernel<<<grid_for(m, 256, 8), 256, 0, s>>>(ub.p, m, T0, T1, T2, bin_of.p); FXII_LAUNCHED(1); }
+  { iota32_kernel<<<grid_for(m, 256, 8), 256, 0, s>>>(iota.p, m); FXII_LAUNCHED(1); }
   DevBuf<int64_t> n_sel;
   n_sel.alloc(4, s);
   int64_t h_n[4] = {0, 0, 0, 0};
@@ -340,7 +340,7 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
   if (h_n[3] > 0) {
     g_sizes.alloc(h_n[3] + 1, s);
     g_off.alloc(h_n[3] + 1, s);
-    global_table_sizes_kernel<<<grid_for(h_n[3] + 1, 256, 8), 256, 0, s>>>(lists[3].p, h_n[3], ub.p, g_sizes.p);
+    { global_table_sizes_kernel<<<grid_for(h_n[3] + 1, 256, 8), 256, 0, s>>>(lists[3].p, h_n[3], ub.p, g_sizes.p); FXII_LAUNCHED(1); }
     exclusive_scan_i64((const long long*)g_sizes.p, (long long*)g_off.p, h_n[3] + 1, s);
     int64_t total = 0;
     FXII_CUDA(cudaMemcpyAsync(&total, g_off.p + h_n[3], sizeof(int64_t), cudaMemcpyDeviceToHost, s));
@@ -366,12 +366,13 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
     if (smem > 48 * 1024)                                                                                             \
       FXII_CUDA(cudaFuncSetAttribute(spgemm_rows_kernel<BLK, NUM>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                      (int)smem));                                                                     \
-    spgemm_rows_kernel<BLK, NUM><<<grid, threads, smem, s>>>(                                                         \
+    { spgemm_rows_kernel<BLK, NUM><<<grid, threads, smem, s>>>(                                                         \
         a->indptr.p, a->indices.p, a->values.p, b->indptr.p, b->indices.p, b->values.p, row_begin, lists[bin].p, nl,  \
         cap, global ? g_keys.p : nullptr, global ? g_vals.p : nullptr, global ? g_sort.p : nullptr,                \
         global ? g_off.p : nullptr, row_nnz.p,                                                                        \
         out->indptr.p, out->indices.p, out->values.p);                                                                \
     FXII_CUDA(cudaGetLastError());                                                                                    \
+    FXII_LAUNCHED(1); }                                                                                                 \
   } while (0)
       if (block && numeric) FXII_SPGEMM_LAUNCH(true, true);
       else if (block && !numeric) FXII_SPGEMM_LAUNCH(true, false);
@@ -406,7 +407,7 @@ scale_rows_kernel(const int64_t* __restrict__ indptr, int64_t n_rows, const doub
 void csr_scale_rows(fxii_csr* a, const double* d_host, cudaStream_t s) {
   DevBuf<double> d;
   d.upload(d_host, a->n_rows, s);
-  if (a->n_rows > 0) scale_rows_kernel<<<grid_for(a->n_rows * 32, 256, 8), 256, 0, s>>>(a->indptr.p, a->n_rows, d.p, a->values.p);
+  if (a->n_rows > 0) { scale_rows_kernel<<<grid_for(a->n_rows * 32, 256, 8), 256, 0, s>>>(a->indptr.p, a->n_rows, d.p, a->values.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
   FXII_CUDA(cudaStreamSynchronize(s));
 }
@@ -431,7 +432,7 @@ void csr_spmv(const fxii_csr* a, const double* u_host, double* y_host, cudaStrea
   u.upload(u_host, a->n_cols, s);
   y.alloc(a->n_rows, s);
   if (a->n_rows > 0) {
-    spmv_kernel<<<grid_for(a->n_rows * 32, 256, 8), 256, 0, s>>>(a->indptr.p, a->indices.p, a->values.p, a->n_rows, u.p, y.p);
+    { spmv_kernel<<<grid_for(a->n_rows * 32, 256, 8), 256, 0, s>>>(a->indptr.p, a->indices.p, a->values.p, a->n_rows, u.p, y.p); FXII_LAUNCHED(1); }
     FXII_CUDA(cudaGetLastError());
     FXII_CUDA(cudaMemcpyAsync(y_host, y.p, sizeof(double) * (size_t)a->n_rows, cudaMemcpyDeviceToHost, s));
   }

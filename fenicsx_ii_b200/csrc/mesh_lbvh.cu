@@ -301,7 +301,7 @@ void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* c
     init[3 + d] = 0ULL;
   }
   FXII_CUDA(cudaMemcpyAsync(bounds.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
-  scene_bounds_kernel<<<grid_for(n_nodes, 256, 8), 256, 0, s>>>(m->x.p, n_nodes, bounds.p);
+  { scene_bounds_kernel<<<grid_for(n_nodes, 256, 8), 256, 0, s>>>(m->x.p, n_nodes, bounds.p); FXII_LAUNCHED(1); }
 
   DevBuf<uint64_t> keys, keys_sorted;
   DevBuf<int32_t> ids, ids_sorted, leaf_parent, flags;
@@ -311,8 +311,8 @@ void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* c
   ids_sorted.alloc(n, s);
   leaf_parent.alloc(n, s);
   flags.alloc(n_internal, s);
-  cell_geom_morton_kernel<<<grid_for(n_cells, 256, 8), 256, 0, s>>>(
-      m->x.p, reinterpret_cast<const int4*>(m->cell_nodes.p), n_cells, bounds.p, m->cellgeo.p, keys.p, ids.p);
+  { cell_geom_morton_kernel<<<grid_for(n_cells, 256, 8), 256, 0, s>>>(
+      m->x.p, reinterpret_cast<const int4*>(m->cell_nodes.p), n_cells, bounds.p, m->cellgeo.p, keys.p, ids.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
 
   size_t tmp_bytes = 0;
@@ -340,15 +340,15 @@ void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* c
     return;
   }
   FXII_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int32_t) * (size_t)n_internal, s));
-  karras_internal_kernel<<<grid_for(n - 1, 256, 8), 256, 0, s>>>(keys_sorted.p, ids_sorted.p, n, m->nodes.p, leaf_parent.p);
+  { karras_internal_kernel<<<grid_for(n - 1, 256, 8), 256, 0, s>>>(keys_sorted.p, ids_sorted.p, n, m->nodes.p, leaf_parent.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
-  refit_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(m->x.p, reinterpret_cast<const int4*>(m->cell_nodes.p), ids_sorted.p,
-                                                   leaf_parent.p, n, padding, m->nodes.p, flags.p);
+  { refit_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(m->x.p, reinterpret_cast<const int4*>(m->cell_nodes.p), ids_sorted.p,
+                                                   leaf_parent.p, n, padding, m->nodes.p, flags.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
   DevBuf<int32_t> depth;
   depth.alloc(1, s);
   FXII_CUDA(cudaMemsetAsync(depth.p, 0, sizeof(int32_t), s));
-  depth_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(m->nodes.p, leaf_parent.p, n, depth.p);
+  { depth_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(m->nodes.p, leaf_parent.p, n, depth.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
   int32_t h = 0;
   FXII_CUDA(cudaMemcpyAsync(&h, depth.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));

@@ -578,7 +578,9 @@ static float elapsed_ms(cudaEvent_t a, cudaEvent_t b) {
 // Segment-structured COO -> CSR.  coo_cols/coo_vals: [n_point_rows*seg].
 void coo_segments_to_csr(const int32_t* row_dofs, int64_t n_point_rows, int64_t n_rows_total, int seg,
                          const int32_t* coo_cols, const double* coo_vals, int64_t n_cols, cudaStream_t s,
-                         fxii_csr* out) {
+                         fxii_csr* out, float* ms_count, float* ms_fill) {
+  cudaEvent_t ke[4];
+  for (auto& e : ke) FXII_CUDA(cudaEventCreate(&e));
   out->n_rows = n_rows_total;
   out->n_cols = n_cols;
   DevBuf<unsigned long long> seg_count;  // [n_rows_total + 1], last slot stays 0
@@ -595,8 +597,8 @@ void coo_segments_to_csr(const int32_t* row_dofs, int64_t n_point_rows, int64_t 
   max_seg.alloc(1, s);
   FXII_CUDA(cudaMemsetAsync(max_seg.p, 0, sizeof(unsigned long long), s));
   if (n_point_rows > 0) {
-    seg_hist_kernel<<<grid_for(n_point_rows, 256, 8), 256, 0, s>>>(row_dofs, n_point_rows, n_rows_total, seg_count.p, bad.p);
-    max_u64_kernel<<<grid_for(n_rows_total, 256, 8), 256, 0, s>>>(seg_count.p, n_rows_total, max_seg.p);
+    { seg_hist_kernel<<<grid_for(n_point_rows, 256, 8), 256, 0, s>>>(row_dofs, n_point_rows, n_rows_total, seg_count.p, bad.p); FXII_LAUNCHED(1); }
+    { max_u64_kernel<<<grid_for(n_rows_total, 256, 8), 256, 0, s>>>(seg_count.p, n_rows_total, max_seg.p); FXII_LAUNCHED(1); }
   }
   {
     size_t tb = 0;
@@ -611,7 +613,7 @@ void coo_segments_to_csr(const int32_t* row_dofs, int64_t n_point_rows, int64_t 
     // stable sort of point rows by matrix row: ascending r inside each row
     iota.alloc(n_point_rows, s);
     keys_sorted.alloc(n_point_rows, s);
-    iota_kernel<<<grid_for(n_point_rows, 256, 8), 256, 0, s>>>(iota.p, n_point_rows);
+    { iota_kernel<<<grid_for(n_point_rows, 256, 8), 256, 0, s>>>(iota.p, n_point_rows); FXII_LAUNCHED(1); }
     int end_bit = 1;
     while (end_bit < 31 && ((int64_t)1 << end_bit) < n_rows_total) ++end_bit;
     size_t tb = 0;
@@ -655,13 +657,15 @@ void coo_segments_to_csr(const int32_t* row_dofs, int64_t n_point_rows, int64_t 
     grid = (int)std::min<int64_t>((n_rows_total + 7) / 8, (int64_t)num_sms() * 8);
   }
   if (grid < 1) grid = 1;
+  FXII_CUDA(cudaEventRecord(ke[0], s));
   if (n_rows_total > 0) {
     if (block_mode)
-      rows_count_kernel<true><<<grid, threads, smem, s>>>(seg_ptr.p, seg_rows.p, coo_cols, seg, n_rows_total, cap, row_nnz.p);
+      { rows_count_kernel<true><<<grid, threads, smem, s>>>(seg_ptr.p, seg_rows.p, coo_cols, seg, n_rows_total, cap, row_nnz.p); FXII_LAUNCHED(1); }
     else
-      rows_count_kernel<false><<<grid, threads, smem, s>>>(seg_ptr.p, seg_rows.p, coo_cols, seg, n_rows_total, cap, row_nnz.p);
+      { rows_count_kernel<false><<<grid, threads, smem, s>>>(seg_ptr.p, seg_rows.p, coo_cols, seg, n_rows_total, cap, row_nnz.p); FXII_LAUNCHED(1); }
     FXII_CUDA(cudaGetLastError());
   }
+  FXII_CUDA(cudaEventRecord(ke[1], s));
   {
     size_t tb = 0;
     FXII_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, (const long long*)row_nnz.p, (long long*)out->indptr.p,
@@ -677,15 +681,21 @@ void coo_segments_to_csr(const int32_t* row_dofs, int64_t n_point_rows, int64_t 
   out->nnz = nnz;
   out->indices.alloc(nnz, s);
   out->values.alloc(nnz, s);
+  FXII_CUDA(cudaEventRecord(ke[2], s));
   if (n_rows_total > 0 && nnz > 0) {
     if (block_mode)
-      rows_fill_kernel<true><<<grid, threads, smem, s>>>(seg_ptr.p, seg_rows.p, coo_cols, coo_vals, seg, n_rows_total, cap,
-                                                         out->indptr.p, out->indices.p, out->values.p);
+      { rows_fill_kernel<true><<<grid, threads, smem, s>>>(seg_ptr.p, seg_rows.p, coo_cols, coo_vals, seg, n_rows_total, cap,
+                                                         out->indptr.p, out->indices.p, out->values.p); FXII_LAUNCHED(1); }
     else
-      rows_fill_kernel<false><<<grid, threads, smem, s>>>(seg_ptr.p, seg_rows.p, coo_cols, coo_vals, seg, n_rows_total, cap,
-                                                          out->indptr.p, out->indices.p, out->values.p);
+      { rows_fill_kernel<false><<<grid, threads, smem, s>>>(seg_ptr.p, seg_rows.p, coo_cols, coo_vals, seg, n_rows_total, cap,
+                                                          out->indptr.p, out->indices.p, out->values.p); FXII_LAUNCHED(1); }
     FXII_CUDA(cudaGetLastError());
   }
+  FXII_CUDA(cudaEventRecord(ke[3], s));
+  FXII_CUDA(cudaEventSynchronize(ke[3]));
+  if (ms_count) *ms_count = elapsed_ms(ke[0], ke[1]);
+  if (ms_fill) *ms_fill = elapsed_ms(ke[2], ke[3]);
+  for (auto& e : ke) cudaEventDestroy(e);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -704,9 +714,9 @@ void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr
   if (rows->kind != FXII_OP_POINTS) {
     rows->frames.alloc(kFrame * Nr, s);
     if (Nr > 0) {
-      row_frames_kernel<<<grid_for(Nr, 128, 16), 128, 0, s>>>(rows->gx.p, rows->gcells.p, rows->cells_k.p, rows->xref.p,
+      { row_frames_kernel<<<grid_for(Nr, 128, 16), 128, 0, s>>>(rows->gx.p, rows->gcells.p, rows->cells_k.p, rows->xref.p,
                                                               rows->nip, rows->radius.p, rows->radius_per_row, rows->kind,
-                                                              Nr, rows->frames.p);
+                                                              Nr, rows->frames.p); FXII_LAUNCHED(1); }
       FXII_CUDA(cudaGetLastError());
     }
   }
@@ -727,20 +737,21 @@ void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr
     FXII_CHECK(smem <= 48 * 1024, "operator table too large for shared memory (nq > 1536)");
     const int4* cn = reinterpret_cast<const int4*>(m->cell_nodes.p);
     if (nd == 4)
-      pi_locate_tabulate_kernel<4><<<grid, threads, smem, s>>>(
+      { pi_locate_tabulate_kernel<4><<<grid, threads, smem, s>>>(
           m->nodes.p, m->cellgeo.p, m->x.p, cn, m->padding, sp->dofmap.p, rows->frames.p, rows->table.p, rows->w.p,
           rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, nq, Np, rows->cell.p, rows->ncoll.p, rows->points.p,
-          rows->coo_cols.p, rows->coo_vals.p, counters.p);
+          rows->coo_cols.p, rows->coo_vals.p, counters.p); FXII_LAUNCHED(1); }
     else
-      pi_locate_tabulate_kernel<10><<<grid, threads, smem, s>>>(
+      { pi_locate_tabulate_kernel<10><<<grid, threads, smem, s>>>(
           m->nodes.p, m->cellgeo.p, m->x.p, cn, m->padding, sp->dofmap.p, rows->frames.p, rows->table.p, rows->w.p,
           rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, nq, Np, rows->cell.p, rows->ncoll.p, rows->points.p,
-          rows->coo_cols.p, rows->coo_vals.p, counters.p);
+          rows->coo_cols.p, rows->coo_vals.p, counters.p); FXII_LAUNCHED(1); }
     FXII_CUDA(cudaGetLastError());
   }
   FXII_CUDA(cudaEventRecord(ev[2], s));
+  float ms_count = 0.f, ms_fill = 0.f;
   coo_segments_to_csr(rows->row_dofs.p, Nr, rows->n_rows_total, nq * nd, rows->coo_cols.p, rows->coo_vals.p, sp->n_dofs, s,
-                      out);
+                      out, &ms_count, &ms_fill);
   FXII_CUDA(cudaEventRecord(ev[3], s));
   PiCounters h;
   FXII_CUDA(cudaMemcpyAsync(&h, counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
@@ -754,6 +765,8 @@ void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr
     stats->ms_frames = elapsed_ms(ev[0], ev[1]);
     stats->ms_locate = elapsed_ms(ev[1], ev[2]);
     stats->ms_csr = elapsed_ms(ev[2], ev[3]);
+    stats->ms_csr_count = ms_count;
+    stats->ms_csr_fill = ms_fill;
   }
   for (auto& e : ev) cudaEventDestroy(e);
   if (h.not_found > 0)

@@ -57,6 +57,8 @@ const char* fxii_last_error(void);
 int fxii_device_count(int* n);
 int fxii_set_device(int device);
 int fxii_sm_count(int* n);
+/* number of kernels of THIS library launched so far by the calling process (CUB launches excluded) */
+int64_t fxii_launch_count(void);
 
 /* ---- Ω mesh (affine tetrahedra) ---------------------------------------------------------- */
 /* x: [n_nodes,3] f64, cell_nodes: [n_cells,4] i32 (mesh.geometry.x / mesh.geometry.dofmap).
@@ -101,6 +103,7 @@ typedef struct {
   int64_t n_ties;       /* points colliding with more than one cell */
   int64_t n_fallback;   /* points assigned by the nearest-cell fallback */
   float ms_frames, ms_locate, ms_csr; /* device time of the three stages (CUDA events) */
+  float ms_csr_count, ms_csr_fill;    /* the two row kernels inside ms_csr */
 } fxii_pi_stats;
 
 /* Builds Π (n_rows_total x n_dofs).  Leaves per-point diagnostics on `rows`

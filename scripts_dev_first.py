@@ -18,8 +18,8 @@ try:
     P=run('cfg2',V,K,PointwiseTrace(g))
     g3,r3=sy.vessel_tree(100000,1/128)
     K3=functionspace(g3,("Quadrature",10))
-    T=run('cfg2mesh-circle8',V,K3,Circle(g3,r3*2,degree=15))
-    T=run('cfg2mesh-disk49',V,K3,Disk(g3,r3*2,degree=7))
+    T=run('cfg2mesh-circle8',V,K3,Circle(g3,r3,degree=15))
+    T=run('cfg2mesh-disk49',V,K3,Disk(g3,r3,degree=7))
     t=time.time(); Tt=T.transpose(); torch.cuda.synchronize(); print('transpose',time.time()-t, Tt.nnz)
     t=time.time(); Z,ip=Tt.matmult(T,return_ip=True); torch.cuda.synchronize(); print('spgemm',time.time()-t, Z.nnz, ip)
     t=time.time(); Z,ip=Tt.matmult(T,return_ip=True); torch.cuda.synchronize(); print('spgemm2',time.time()-t, Z.nnz, ip)
