@@ -1,0 +1,49 @@
+"""Rebuilds the inputs of the golden Π cases (same specs as tests/golden/make_golden.py, which
+cannot be imported on the GPU box because it needs /root/reference)."""
+
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from fenicsx_ii_b200 import synthetic as sy
+from fenicsx_ii_b200.mesh import functionspace
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+CASES = {
+    "trace_line_on_edges": dict(n=(4, 4, 8), p=1, gamma=("line", 9), K=("Quadrature", 10), op=("trace",)),
+    "circle_line_R02": dict(n=(4, 4, 8), p=1, gamma=("line", 9), K=("Quadrature", 10), op=("circle", 0.2, 5)),
+    "disk_network_dg1": dict(n=(6, 6, 6), p=1, gamma=("network", 60, 1 / 6, 3), K=("DG", 1), op=("disk", 0.06, 3)),
+    "trace_network_p1_firstvisit": dict(n=(6, 6, 6), p=1, gamma=("network", 60, 1 / 6, 3), K=("Lagrange", 1), op=("trace",)),
+    "circle_network_p2k_firstvisit": dict(n=(5, 5, 5), p=1, gamma=("network", 40, 1 / 5, 2), K=("Lagrange", 2),
+                                          op=("circle", 0.05, 7)),
+    "circle_p2v_callable_radius": dict(n=(4, 4, 4), p=2, gamma=("network", 30, 1 / 4, 2), K=("Quadrature", 4),
+                                       op=("circle", "callable", 9)),
+    "disk_p2v_subset": dict(n=(4, 4, 4), p=2, gamma=("network", 30, 1 / 4, 2), K=("DG", 2), op=("disk", 0.05, 3)),
+}
+
+
+def callable_radius(x):
+    return 0.03 + 0.05 * x[2] ** 2
+
+
+def load_case(name):
+    """(mesh, V, gamma, K, op_name, radius, degree, cells_K, fixture) — Γ comes from the fixture
+    itself so the test does not depend on the generator's random stream."""
+    spec = CASES[name]
+    fx = np.load(os.path.join(GOLDEN_DIR, f"pi_{name}.npz"))
+    mesh = sy.kuhn_box(*spec["n"])
+    V = functionspace(mesh, ("Lagrange", 1)) if spec["p"] == 1 else sy.kuhn_p2_space(mesh)
+    from fenicsx_ii_b200.mesh import Mesh
+
+    gamma = Mesh(fx["gamma_x"], fx["gamma_cells"], tdim=1, name="gamma")
+    K = functionspace(gamma, spec["K"])
+    op = spec["op"]
+    radius = degree = None
+    if op[0] != "trace":
+        radius = callable_radius if op[1] == "callable" else op[1]
+        degree = op[2]
+    cells_K = fx["cells_K"] if bool(fx["has_cells_K"]) else None
+    return mesh, V, gamma, K, op[0], radius, degree, cells_K, fx
