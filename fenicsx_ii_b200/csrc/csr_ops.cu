@@ -97,55 +97,72 @@ void csr_transpose(const fxii_csr* a, cudaStream_t s, fxii_csr* out) {
 }
 
 // ---- SpGEMM -------------------------------------------------------------------------------------
-// upper bound of nnz(C_i): number of intermediate products of row i
+// Row-wise hash SpGEMM, two phases (symbolic count -> scan -> numeric), rows binned by size so that
+// every row gets a shared-memory table just big enough:
+//   symbolic: bins by the intermediate-product bound ub_i (table capacity >= 2*ub_i)
+//   numeric : bins by the exact nnz_i from the symbolic phase (capacity >= 2*nnz_i)
+// One GROUP (a warp, or a whole block for long rows) owns an output row.
+
+// upper bound of nnz(C_i): number of intermediate products of row i (one thread per row: rows of
+// Pi^T are short and mostly empty)
 __global__ void __launch_bounds__(256)
 spgemm_ub_kernel(const int64_t* __restrict__ a_ptr, const int32_t* __restrict__ a_idx, const int64_t* __restrict__ b_ptr,
                  int64_t row_begin, int64_t n_rows, int64_t* __restrict__ ub) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t i = warp; i < n_rows; i += nwarps) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t a0 = a_ptr[row_begin + i], a1 = a_ptr[row_begin + i + 1];
     long long sum = 0;
-    for (int64_t k = a0 + lane; k < a1; k += 32) {
+    for (int64_t k = a0; k < a1; ++k) {
       const int c = a_idx[k];
       sum += b_ptr[c + 1] - b_ptr[c];
     }
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) ub[i] = sum;
+    ub[i] = sum;
   }
 }
 
 constexpr int32_t kEmpty = -1;
+constexpr int kNumBins = 6;  // bins 0..4: shared-memory tables sized by the row; bin 5: the long rows
+// capacity of the table of bin b; a row goes to the first bin whose capacity is >= 2*size
+__host__ __device__ constexpr uint32_t bin_cap(int b) {
+  return b == 0 ? 64u : b == 1 ? 256u : b == 2 ? 1024u : b == 3 ? 4096u : b == 4 ? 8192u : 32768u;
+}
 
 __device__ __forceinline__ uint32_t hash_col(uint32_t c) { return c * 2654435761u; }
 
-// insert key into an open-addressing table of `cap` (power of two) slots; returns the slot
-__device__ __forceinline__ uint32_t hash_insert(int32_t* keys, uint32_t cap, int32_t key) {
-  uint32_t h = hash_col((uint32_t)key) & (cap - 1);
+// Insert `key` into an open-addressing table of `cap` (power of two) slots; returns the slot.
+// A plain load finds the (common) already-present key without an atomic.
+__device__ __forceinline__ uint32_t hash_insert(int32_t* keys, uint32_t cap, int32_t key, bool& is_new) {
+  uint32_t h = (hash_col((uint32_t)key) >> 7) & (cap - 1);
+  is_new = false;
   while (true) {
-    const int32_t prev = atomicCAS(&keys[h], kEmpty, key);
-    if (prev == kEmpty || prev == key) return h;
+    int32_t cur = *(volatile int32_t*)(keys + h);
+    if (cur == key) return h;
+    if (cur == kEmpty) {
+      cur = atomicCAS(&keys[h], kEmpty, key);
+      if (cur == kEmpty) {
+        is_new = true;
+        return h;
+      }
+      if (cur == key) return h;
+    }
     h = (h + 1) & (cap - 1);
   }
 }
 
-// One GROUP (warp or block) per output row.  Pass NUMERIC=false counts the distinct columns;
-// NUMERIC=true accumulates values — sequentially over k (A's column order), in parallel over the
-// entries of B's row k, whose columns are distinct, so no two lanes touch the same slot between two
-// group barriers and the sum order is fixed — then compacts the occupied slots into (col, slot)
-// keys, bitonic-sorts them and writes the row in ascending column order.
+// NUMERIC=false: row_size[i] = number of distinct columns of row i.
+// NUMERIC=true : accumulate values — sequentially over k (A's column order), in parallel over the
+//   entries of B's row k, whose columns are distinct, so no two lanes touch the same slot between two
+//   group barriers and the floating-point sum order is fixed — then compact the occupied slots into
+//   (col, slot) keys, bitonic-sort them and write the row in ascending column order.
 // Table storage: shared memory (g_keys == nullptr) or a per-row slice of global memory.
-// Layout per group for capacity cap: vals f64[cap] | sort u64[cap/2] | keys i32[cap]  (NUMERIC)
-//                                    keys i32[cap]                                     (count)
+// Shared layout per group: vals f64[cap] | sort u64[cap/2] | keys i32[cap] (NUMERIC); keys i32[cap].
 template <bool BLOCK, bool NUMERIC>
 __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int32_t* __restrict__ a_idx,
                                    const double* __restrict__ a_val, const int64_t* __restrict__ b_ptr,
                                    const int32_t* __restrict__ b_idx, const double* __restrict__ b_val,
                                    int64_t row_begin, const int32_t* __restrict__ row_list, int64_t n_list, uint32_t cap,
-                                   int32_t* __restrict__ g_keys, double* __restrict__ g_vals,
+                                   int overflow_limit, int* __restrict__ overflow_flag, int32_t* __restrict__ g_keys, double* __restrict__ g_vals,
                                    uint64_t* __restrict__ g_sort, const int64_t* __restrict__ g_off,
-                                   int64_t* __restrict__ row_nnz, const int64_t* __restrict__ c_ptr,
+                                   int64_t* __restrict__ row_size, const int64_t* __restrict__ c_ptr,
                                    int32_t* __restrict__ c_idx, double* __restrict__ c_val) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   const int nthreads = BLOCK ? blockDim.x : 32;
@@ -153,8 +170,13 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
   const int groups_per_block = BLOCK ? 1 : blockDim.x / 32;
   const int gid = BLOCK ? 0 : threadIdx.x / 32;
   __shared__ int s_cnt[32];
+  __shared__ int s_new;  // distinct keys inserted so far (only tracked when overflow_limit > 0)
   for (int64_t li = (int64_t)blockIdx.x * groups_per_block + gid; li < n_list; li += (int64_t)gridDim.x * groups_per_block) {
     const int64_t i = row_list[li];  // row index relative to row_begin
+    if (overflow_limit > 0) {
+      if (threadIdx.x == 0) s_new = 0;
+      __syncthreads();
+    }
     int32_t* keys;
     double* vals = nullptr;
     uint64_t* sortbuf = nullptr;
@@ -187,12 +209,16 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
       const int k = a_idx[ka];
       const double av = NUMERIC ? a_val[ka] : 0.0;
       const int64_t b0 = b_ptr[k], b1 = b_ptr[k + 1];
+      if (overflow_limit > 0 && *(volatile int*)&s_new > overflow_limit) break;  // uniform: read after a barrier
       for (int64_t kb = b0 + tid; kb < b1; kb += nthreads) {
-        const uint32_t slot = hash_insert(keys, tcap, b_idx[kb]);
-        if (NUMERIC) vals[slot] += av * b_val[kb];
+        bool is_new;
+        const uint32_t slot = hash_insert(keys, tcap, __ldg(&b_idx[kb]), is_new);
+        if (NUMERIC) vals[slot] += av * __ldg(&b_val[kb]);
+        if (overflow_limit > 0 && is_new) atomicAdd(&s_new, 1);
       }
-      if (NUMERIC) group_sync<BLOCK>();
+      if (NUMERIC || overflow_limit > 0) group_sync<BLOCK>();
     }
+    if (overflow_limit > 0 && *(volatile int*)&s_new > overflow_limit && tid == 0) *overflow_flag = 1;
     group_sync<BLOCK>();
     if (!NUMERIC) {
       int local = 0;
@@ -204,11 +230,12 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
         if (threadIdx.x == 0) {
           int tot = 0;
           for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_cnt[w];
-          row_nnz[i] = tot;
+          // -1: the table overflowed, the row is recounted with a global-memory table
+          row_size[i] = (overflow_limit > 0 && s_new > overflow_limit) ? -1 : tot;
         }
         __syncthreads();
       } else if (tid == 0) {
-        row_nnz[i] = local;
+        row_size[i] = local;
       }
       group_sync<BLOCK>();
     } else {
@@ -217,10 +244,9 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
       uint32_t scap = 2;
       while (scap < nnz) scap <<= 1;
       for (uint32_t t = tid; t < scap; t += nthreads) sortbuf[t] = ~0ULL;
-      group_sync<BLOCK>();
-      // compact occupied slots; order is irrelevant (sorted next), so a shared counter suffices
       if (tid == 0) s_cnt[gid] = 0;
       group_sync<BLOCK>();
+      // compact occupied slots; order is irrelevant (sorted next), so a shared counter suffices
       for (uint32_t t0 = 0; t0 < tcap; t0 += nthreads) {
         const uint32_t t = t0 + tid;
         const int32_t key = t < tcap ? keys[t] : kEmpty;
@@ -243,44 +269,94 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
   }
 }
 
+// bin index by size (0 -> skipped): first bin with capacity >= 2*size, else the global bin
 __global__ void __launch_bounds__(256)
-classify_rows_kernel(const int64_t* __restrict__ ub, int64_t n_rows, int64_t t0, int64_t t1, int64_t t2,
-                     int32_t* __restrict__ bin_of) {
+classify_rows_kernel(const int64_t* __restrict__ size, int64_t n_rows, uint8_t* __restrict__ bin_of, int32_t* __restrict__ rows,
+                     unsigned long long* __restrict__ bin_count) {
+  __shared__ unsigned int s_count[kNumBins + 1];
+  if (threadIdx.x <= kNumBins) s_count[threadIdx.x] = 0;
+  __syncthreads();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_rows; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t u = ub[i];
-    bin_of[i] = u == 0 ? -1 : (u <= t0 ? 0 : (u <= t1 ? 1 : (u <= t2 ? 2 : 3)));
+    const int64_t u = size[i];
+    int b = kNumBins;  // empty rows sort last and are never launched
+    if (u > 0) {
+      b = kNumBins - 1;  // long rows
+      for (int q = 0; q < kNumBins - 1; ++q)
+        if (2 * u <= (int64_t)bin_cap(q)) {
+          b = q;
+          break;
+        }
+    }
+    bin_of[i] = (uint8_t)b;
+    rows[i] = (int32_t)i;
+    atomicAdd(&s_count[b], 1u);
   }
+  __syncthreads();
+  if (threadIdx.x <= kNumBins && s_count[threadIdx.x]) atomicAdd(&bin_count[threadIdx.x], (unsigned long long)s_count[threadIdx.x]);
 }
 
-struct IsBin {
-  const int32_t* bin_of;
-  int b;
-  __device__ bool operator()(const int32_t& i) const { return bin_of[i] == b; }
-};
-
 __global__ void __launch_bounds__(256)
-global_table_sizes_kernel(const int32_t* __restrict__ row_list, int64_t n_list, const int64_t* __restrict__ ub,
-                          int64_t* __restrict__ sizes) {
+global_table_sizes_kernel(const int32_t* __restrict__ row_list, int64_t n_list, const int64_t* __restrict__ size,
+                          int64_t size_cap, int64_t* __restrict__ sizes) {
   for (int64_t li = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; li <= n_list; li += (int64_t)gridDim.x * blockDim.x) {
     if (li == n_list) {
       sizes[li] = 0;
       continue;
     }
-    uint64_t u = (uint64_t)ub[row_list[li]] * 2;
+    uint64_t u = (uint64_t)min(size[row_list[li]], size_cap) * 2;
     uint64_t cap = 1024;
     while (cap < u) cap <<= 1;
     sizes[li] = (int64_t)cap;
   }
 }
 
-// bins by intermediate-product bound: 0: warp/row, shared table 512; 1: warp/row, 2048;
-// 2: block/row, 8192; 3: block/row, global-memory table of 2*ub slots
+struct IsMinusOne {
+  const int64_t* v;
+  __device__ bool operator()(const int32_t& i) const { return v[i] == -1; }
+};
+
+// rows grouped by bin: sorted_rows holds the row ids ordered by bin, h_count the rows per bin
+struct RowBins {
+  DevBuf<int32_t> sorted_rows;
+  int64_t count[kNumBins + 1] = {0};
+  int64_t offset[kNumBins + 1] = {0};
+};
+
+static void bin_rows(const int64_t* size, int64_t m, cudaStream_t s, RowBins& rb) {
+  DevBuf<uint8_t> bin_of, bin_sorted;
+  DevBuf<int32_t> rows;
+  DevBuf<unsigned long long> counts;
+  bin_of.alloc(m, s);
+  bin_sorted.alloc(m, s);
+  rows.alloc(m, s);
+  rb.sorted_rows.alloc(m, s);
+  counts.alloc(kNumBins + 1, s);
+  FXII_CUDA(cudaMemsetAsync(counts.p, 0, sizeof(unsigned long long) * (kNumBins + 1), s));
+  { classify_rows_kernel<<<grid_for(m, 256, 8), 256, 0, s>>>(size, m, bin_of.p, rows.p, counts.p); FXII_LAUNCHED(1); }
+  FXII_CUDA(cudaGetLastError());
+  size_t tb = 0;
+  FXII_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, bin_of.p, bin_sorted.p, rows.p, rb.sorted_rows.p, m, 0, 3, s));
+  DevBuf<uint8_t> tmp;
+  tmp.alloc((int64_t)tb, s);
+  FXII_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, bin_of.p, bin_sorted.p, rows.p, rb.sorted_rows.p, m, 0, 3, s));
+  unsigned long long h[kNumBins + 1];
+  FXII_CUDA(cudaMemcpyAsync(h, counts.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  FXII_CUDA(cudaStreamSynchronize(s));
+  int64_t off = 0;
+  for (int b = 0; b <= kNumBins; ++b) {
+    rb.count[b] = (int64_t)h[b];
+    rb.offset[b] = off;
+    off += rb.count[b];
+  }
+}
+
 void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row_end, cudaStream_t s, fxii_csr* out,
             int64_t* ip_out) {
   FXII_CHECK(a->n_cols == b->n_rows, "spgemm: inner dimensions differ");
   if (row_end < 0) row_end = a->n_rows;
   FXII_CHECK(row_begin >= 0 && row_begin <= row_end && row_end <= a->n_rows, "spgemm: bad row window");
   const int64_t m = row_end - row_begin;
+  FXII_CHECK(m < ((int64_t)1 << 31), "spgemm: row window must fit int32");
   out->n_rows = m;
   out->n_cols = b->n_cols;
   DevBuf<int64_t> ub, row_nnz;
@@ -295,9 +371,8 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
     if (ip_out) *ip_out = 0;
     return;
   }
-  { spgemm_ub_kernel<<<grid_for(m * 32, 256, 8), 256, 0, s>>>(a->indptr.p, a->indices.p, b->indptr.p, row_begin, m, ub.p); FXII_LAUNCHED(1); }
+  { spgemm_ub_kernel<<<grid_for(m, 256, 8), 256, 0, s>>>(a->indptr.p, a->indices.p, b->indptr.p, row_begin, m, ub.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
-  // total intermediate products
   DevBuf<int64_t> ip_dev;
   ip_dev.alloc(1, s);
   {
@@ -307,89 +382,107 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
     tmp.alloc((int64_t)tb, s);
     FXII_CUDA(cub::DeviceReduce::Sum(tmp.p, tb, ub.p, ip_dev.p, m, s));
   }
-  const int64_t T0 = 256, T1 = 1024, T2 = 4096;
-  const uint32_t caps[3] = {512, 2048, 8192};
-  DevBuf<int32_t> bin_of, iota, lists[4];
-  bin_of.alloc(m, s);
-  iota.alloc(m, s);
-  { classify_rows_kernel<<<grid_for(m, 256, 8), 256, 0, s>>>(ub.p, m, T0, T1, T2, bin_of.p); FXII_LAUNCHED(1); }
-  { iota32_kernel<<<grid_for(m, 256, 8), 256, 0, s>>>(iota.p, m); FXII_LAUNCHED(1); }
-  DevBuf<int64_t> n_sel;
-  n_sel.alloc(4, s);
-  int64_t h_n[4] = {0, 0, 0, 0};
-  for (int bin = 0; bin < 4; ++bin) {
-    lists[bin].alloc(m, s);
-    size_t tb = 0;
-    IsBin pred{bin_of.p, bin};
-    FXII_CUDA(cub::DeviceSelect::If(nullptr, tb, iota.p, lists[bin].p, n_sel.p + bin, m, pred, s));
-    DevBuf<uint8_t> tmp;
-    tmp.alloc((int64_t)tb, s);
-    FXII_CUDA(cub::DeviceSelect::If(tmp.p, tb, iota.p, lists[bin].p, n_sel.p + bin, m, pred, s));
-  }
   int64_t h_ip = 0;
-  FXII_CUDA(cudaMemcpyAsync(h_n, n_sel.p, sizeof(h_n), cudaMemcpyDeviceToHost, s));
   FXII_CUDA(cudaMemcpyAsync(&h_ip, ip_dev.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-  FXII_CUDA(cudaStreamSynchronize(s));
-  if (ip_out) *ip_out = h_ip;
 
-  // global tables for bin 3
-  DevBuf<int64_t> g_sizes, g_off;
-  DevBuf<int32_t> g_keys;
-  DevBuf<double> g_vals;
-  DevBuf<uint64_t> g_sort;
-  if (h_n[3] > 0) {
-    g_sizes.alloc(h_n[3] + 1, s);
-    g_off.alloc(h_n[3] + 1, s);
-    { global_table_sizes_kernel<<<grid_for(h_n[3] + 1, 256, 8), 256, 0, s>>>(lists[3].p, h_n[3], ub.p, g_sizes.p); FXII_LAUNCHED(1); }
-    exclusive_scan_i64((const long long*)g_sizes.p, (long long*)g_off.p, h_n[3] + 1, s);
-    int64_t total = 0;
-    FXII_CUDA(cudaMemcpyAsync(&total, g_off.p + h_n[3], sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    FXII_CUDA(cudaStreamSynchronize(s));
-    g_keys.alloc(total, s);
-    g_vals.alloc(total, s);
-    g_sort.alloc(total / 2 + 1, s);
-  }
-
-  auto launch = [&](bool numeric) {
-    for (int bin = 0; bin < 4; ++bin) {
-      const int64_t nl = h_n[bin];
+  DevBuf<int> overflow;
+  overflow.alloc(1, s);
+  FXII_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
+  // one phase: launch every non-empty bin
+  // force_global: recount of the symbolic rows that overflowed the largest shared table
+  auto run_phase = [&](bool numeric, const int64_t* size, RowBins& rb, const int32_t* force_list, int64_t force_n) {
+    for (int bin = force_list ? kNumBins - 1 : 0; bin < kNumBins; ++bin) {
+      const int64_t nl = force_list ? force_n : rb.count[bin];
       if (nl == 0) continue;
-      const bool block = bin >= 2;
-      const bool global = bin == 3;
-      const uint32_t cap = global ? 0 : caps[bin];
-      const int threads = block ? 256 : (bin == 0 ? 256 : 128);
+      const int32_t* list = force_list ? force_list : rb.sorted_rows.p + rb.offset[bin];
+      // long rows: the symbolic phase counts them in a 32768-slot shared table (a row of C with more
+      // than 16384 distinct columns is reported as unsupported); the numeric phase, which knows nnz,
+      // uses exact-size tables in global memory
+      const bool global = (numeric || force_list) && bin == kNumBins - 1;
+      const bool block = bin >= 3;
+      const uint32_t cap = global ? 0 : bin_cap(bin);
+      const int overflow_limit = (!numeric && !force_list && bin == kNumBins - 1) ? 16384 : 0;
+      const int threads = block ? (bin >= 4 ? 256 : 128) : 256;
       const int groups = block ? 1 : threads / 32;
       const size_t smem = global ? 0 : (size_t)cap * (numeric ? 16 : 4) * groups;
       const int grid = (int)std::min<int64_t>((nl + groups - 1) / groups, (int64_t)num_sms() * 16);
+      DevBuf<int64_t> g_sizes, g_off;
+      DevBuf<int32_t> g_keys;
+      DevBuf<double> g_vals;
+      DevBuf<uint64_t> g_sort;
+      if (global) {
+        g_sizes.alloc(nl + 1, s);
+        g_off.alloc(nl + 1, s);
+        { global_table_sizes_kernel<<<grid_for(nl + 1, 256, 8), 256, 0, s>>>(list, nl, size, b->n_cols, g_sizes.p); FXII_LAUNCHED(1); }
+        exclusive_scan_i64((const long long*)g_sizes.p, (long long*)g_off.p, nl + 1, s);
+        int64_t total = 0;
+        FXII_CUDA(cudaMemcpyAsync(&total, g_off.p + nl, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        FXII_CUDA(cudaStreamSynchronize(s));
+        FXII_CHECK(total < ((int64_t)1 << 33), "spgemm: rows too long for the global-table fallback (shard the product)");
+        g_keys.alloc(total, s);
+        if (numeric) {
+          g_vals.alloc(total, s);
+          g_sort.alloc(total / 2 + 1, s);
+        }
+      }
 #define FXII_SPGEMM_LAUNCH(BLK, NUM)                                                                                  \
   do {                                                                                                                \
     if (smem > 48 * 1024)                                                                                             \
       FXII_CUDA(cudaFuncSetAttribute(spgemm_rows_kernel<BLK, NUM>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                      (int)smem));                                                                     \
-    { spgemm_rows_kernel<BLK, NUM><<<grid, threads, smem, s>>>(                                                         \
-        a->indptr.p, a->indices.p, a->values.p, b->indptr.p, b->indices.p, b->values.p, row_begin, lists[bin].p, nl,  \
-        cap, global ? g_keys.p : nullptr, global ? g_vals.p : nullptr, global ? g_sort.p : nullptr,                \
-        global ? g_off.p : nullptr, row_nnz.p,                                                                        \
-        out->indptr.p, out->indices.p, out->values.p);                                                                \
+    spgemm_rows_kernel<BLK, NUM><<<grid, threads, smem, s>>>(                                                         \
+        a->indptr.p, a->indices.p, a->values.p, b->indptr.p, b->indices.p, b->values.p, row_begin, list, nl, cap,     \
+        overflow_limit, overflow.p, global ? g_keys.p : nullptr, global ? g_vals.p : nullptr, global ? g_sort.p : nullptr,                        \
+        global ? g_off.p : nullptr, row_nnz.p, out->indptr.p, out->indices.p, out->values.p);                         \
     FXII_CUDA(cudaGetLastError());                                                                                    \
-    FXII_LAUNCHED(1); }                                                                                                 \
+    FXII_LAUNCHED(1);                                                                                                 \
   } while (0)
       if (block && numeric) FXII_SPGEMM_LAUNCH(true, true);
       else if (block && !numeric) FXII_SPGEMM_LAUNCH(true, false);
       else if (!block && numeric) FXII_SPGEMM_LAUNCH(false, true);
       else FXII_SPGEMM_LAUNCH(false, false);
 #undef FXII_SPGEMM_LAUNCH
+      if (global) FXII_CUDA(cudaStreamSynchronize(s));  // tables are freed when this scope ends
     }
   };
-  launch(false);
+
+  RowBins sym;
+  bin_rows(ub.p, m, s, sym);  // synchronises: h_ip is valid from here on
+  if (ip_out) *ip_out = h_ip;
+  run_phase(false, ub.p, sym, nullptr, 0);
   exclusive_scan_i64((const long long*)row_nnz.p, (long long*)out->indptr.p, m + 1, s);
   int64_t nnz = 0;
+  int h_overflow = 0;
   FXII_CUDA(cudaMemcpyAsync(&nnz, out->indptr.p + m, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-  FXII_CUDA(cudaStreamSynchronize(s));
+  FXII_CUDA(cudaMemcpyAsync(&h_overflow, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  RowBins num;
+  bin_rows(row_nnz.p, m, s, num);  // synchronises
+  if (h_overflow) {
+    // rare: rows with more than 16384 distinct columns are recounted in global-memory tables
+    DevBuf<int32_t> iota, over;
+    DevBuf<int64_t> n_over;
+    iota.alloc(m, s);
+    over.alloc(m, s);
+    n_over.alloc(1, s);
+    { iota32_kernel<<<grid_for(m, 256, 8), 256, 0, s>>>(iota.p, m); FXII_LAUNCHED(1); }
+    IsMinusOne pred{row_nnz.p};
+    size_t tb = 0;
+    FXII_CUDA(cub::DeviceSelect::If(nullptr, tb, iota.p, over.p, n_over.p, m, pred, s));
+    DevBuf<uint8_t> tmp;
+    tmp.alloc((int64_t)tb, s);
+    FXII_CUDA(cub::DeviceSelect::If(tmp.p, tb, iota.p, over.p, n_over.p, m, pred, s));
+    int64_t h_n = 0;
+    FXII_CUDA(cudaMemcpyAsync(&h_n, n_over.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    FXII_CUDA(cudaStreamSynchronize(s));
+    run_phase(false, ub.p, sym, over.p, h_n);
+    exclusive_scan_i64((const long long*)row_nnz.p, (long long*)out->indptr.p, m + 1, s);
+    FXII_CUDA(cudaMemcpyAsync(&nnz, out->indptr.p + m, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    bin_rows(row_nnz.p, m, s, num);
+  }
   out->nnz = nnz;
   out->indices.alloc(nnz, s);
   out->values.alloc(nnz, s);
-  if (nnz > 0) launch(true);
+  if (nnz > 0) run_phase(true, row_nnz.p, num, nullptr, 0);
 }
 
 // ---- row scaling, SpMV --------------------------------------------------------------------------

@@ -108,7 +108,7 @@ __device__ __forceinline__ double dot3(const double* a, const double* b) {
 
 // squared distance point-triangle (Ericson, Real-Time Collision Detection 5.1.5); mirrors
 // oracle/pi_oracle.py:_closest_point_triangle_d2
-__device__ double tri_dist2(const double* p, const double* a, const double* b, const double* c) {
+__device__ __noinline__ double tri_dist2(const double* p, const double* a, const double* b, const double* c) {
   double ab[3], ac[3], ap[3], bp[3], cp[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
@@ -179,7 +179,7 @@ __device__ __forceinline__ void pull_back(const CellGeo& g, const double* p, dou
 // Slow path of the leaf test (some barycentric coordinate negative): exact fp64 padded-box test
 // (dolfinx point_in_bbox, slack 1e-14*extent) and exact point-tetrahedron distance.
 // Returns false when the cell is not a candidate; otherwise d2.
-__device__ bool cell_distance2(const double* __restrict__ x, const int4* __restrict__ cell_nodes, int cell,
+__device__ __noinline__ bool cell_distance2(const double* __restrict__ x, const int4* __restrict__ cell_nodes, int cell,
                                const double* p, double padding, double& d2) {
   const int4 nd = __ldg(&cell_nodes[cell]);
   const int id[4] = {nd.x, nd.y, nd.z, nd.w};
@@ -222,6 +222,8 @@ __device__ LocateResult locate_point(const BvhNode* __restrict__ nodes, const do
   int best = 0x7fffffff, ncoll = 0;
   int fb_cell = -1;
   double fb_d2 = 1e300;
+  // 1.001: cells within 0.05% of the threshold still take the exact path
+  const double tau2 = fmax(kCollisionD2, padding * padding) * 1.001;
   while (true) {
     const float4* nf = reinterpret_cast<const float4*>(nodes + node);
     const float4 q0 = __ldg(nf), q1 = __ldg(nf + 1), q2 = __ldg(nf + 2);
@@ -249,8 +251,17 @@ __device__ LocateResult locate_point(const BvhNode* __restrict__ nodes, const do
           best = min(best, cell);
           ++ncoll;
         } else {
+          // Quick reject without touching the vertices: the distance to the tetrahedron is at least
+          // the distance to the plane of any face the point is outside of, -lambda_i / |grad lambda_i|
+          // (grad lambda_1..3 = rows of K, grad lambda_0 = -(row0+row1+row2)).  Cells farther than
+          // tau = max(collision distance, padding) can neither collide nor serve as fallback.
+          const double s0 = (g.K[0] + g.K[3]) + g.K[6], s1 = (g.K[1] + g.K[4]) + g.K[7], s2 = (g.K[2] + g.K[5]) + g.K[8];
+          bool far = (l0 < 0) && (l0 * l0 > tau2 * ((s0 * s0 + s1 * s1) + s2 * s2));
+          far = far || ((X[0] < 0) && (X[0] * X[0] > tau2 * ((g.K[0] * g.K[0] + g.K[1] * g.K[1]) + g.K[2] * g.K[2])));
+          far = far || ((X[1] < 0) && (X[1] * X[1] > tau2 * ((g.K[3] * g.K[3] + g.K[4] * g.K[4]) + g.K[5] * g.K[5])));
+          far = far || ((X[2] < 0) && (X[2] * X[2] > tau2 * ((g.K[6] * g.K[6] + g.K[7] * g.K[7]) + g.K[8] * g.K[8])));
           double d2;
-          if (cell_distance2(x, cell_nodes, cell, p, padding, d2)) {
+          if (!far && cell_distance2(x, cell_nodes, cell, p, padding, d2)) {
             if (d2 < kCollisionD2) {
               best = min(best, cell);
               ++ncoll;
@@ -290,7 +301,7 @@ struct PiCounters {
 
 // One thread per 3D point p = r*nq + l (interpolation.py:57).  ND = dofs per V cell.
 template <int ND>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 pi_locate_tabulate_kernel(const BvhNode* __restrict__ nodes, const double* __restrict__ cellgeo,
                           const double* __restrict__ x, const int4* __restrict__ cell_nodes, double padding,
                           const int32_t* __restrict__ dofmap, const double* __restrict__ frames,
@@ -732,7 +743,7 @@ void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr
   FXII_CUDA(cudaMemsetAsync(counters.p, 0, sizeof(PiCounters), s));
   if (Np > 0) {
     const int threads = 128;
-    const int grid = grid_for(Np, threads, 12);
+    const int grid = grid_for(Np, threads, 8);
     const size_t smem = (rows->kind == FXII_OP_CIRCLE || rows->kind == FXII_OP_DISK) ? sizeof(double) * 4 * (size_t)nq : 0;
     FXII_CHECK(smem <= 48 * 1024, "operator table too large for shared memory (nq > 1536)");
     const int4* cn = reinterpret_cast<const int4*>(m->cell_nodes.p);
