@@ -46,6 +46,7 @@ class PiStats(C.Structure):
         ("ms_csr", C.c_float),
         ("ms_csr_count", C.c_float),
         ("ms_csr_fill", C.c_float),
+        ("fused", C.c_int32),
     ]
 
 
@@ -74,6 +75,7 @@ SIGNATURES = {
     "fxii_rows_create_points": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _i64, _vp, C.POINTER(_vp)]),
     "fxii_rows_destroy": (C.c_int, [_vp]),
     "fxii_rows_keep_points": (C.c_int, [_vp, _i32]),
+    "fxii_rows_set_mode": (C.c_int, [_vp, _i32]),
     "fxii_pi_assemble": (C.c_int, [_vp, _vp, _vp, C.POINTER(_vp), C.POINTER(PiStats)]),
     "fxii_rows_download_diag": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "fxii_rows_download_coo": (C.c_int, [_vp, _vp, _vp, _vp]),

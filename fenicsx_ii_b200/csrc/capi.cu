@@ -199,6 +199,13 @@ int fxii_rows_keep_points(fxii_rows* r, int32_t flag) {
   });
 }
 
+int fxii_rows_set_mode(fxii_rows* r, int32_t mode) {
+  return guarded([&] {
+    FXII_CHECK(r && (mode == 0 || mode == 1), "bad mode");
+    r->mode = mode;
+  });
+}
+
 int fxii_pi_assemble(const fxii_space* space, fxii_rows* rows, void* stream, fxii_csr** out, fxii_pi_stats* stats) {
   fxii_csr* c = nullptr;
   int rc = guarded([&] {
@@ -239,6 +246,7 @@ int fxii_rows_download_coo(const fxii_rows* rows, int32_t* cols, double* vals, v
     cudaStream_t s = S(stream);
     const int64_t E = rows->n_point_rows * rows->nq * rows->nd;
     FXII_CHECK(rows->coo_cols.n == E && rows->nd > 0, "no assembly has run on this rows handle");
+    FXII_CHECK(!rows->last_fused, "the last assembly used the fused path: no COO was materialised (fxii_rows_set_mode(rows, 1))");
     if (cols && E) FXII_CUDA(cudaMemcpyAsync(cols, rows->coo_cols.p, sizeof(int32_t) * (size_t)E, cudaMemcpyDeviceToHost, s));
     if (vals && E) FXII_CUDA(cudaMemcpyAsync(vals, rows->coo_vals.p, sizeof(double) * (size_t)E, cudaMemcpyDeviceToHost, s));
     FXII_CUDA(cudaStreamSynchronize(s));

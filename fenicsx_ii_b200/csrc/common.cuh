@@ -150,6 +150,8 @@ struct fxii_rows {
   int64_t n_rows_total = 0;  // rows of Π
   int32_t radius_per_row = 0;
   bool keep_points = false;  // also write the generated 3D points (diagnostics only)
+  int mode = 0;              // 0: fused row reduction when possible; 1: always materialise the COO
+  bool last_fused = false;
   // Γ inputs
   fxii::DevBuf<double> gx;
   fxii::DevBuf<int32_t> gcells, cells_k, row_dofs;

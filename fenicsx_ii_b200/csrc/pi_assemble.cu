@@ -299,6 +299,81 @@ struct PiCounters {
   unsigned long long not_found, ties, fallback;
 };
 
+// The 3D averaging point p = r*nq + l with its weight W and scale S
+// (restriction_operators.py:191-205 / 301-315; PointwiseTrace :60-68; generic operators: uploaded).
+__device__ __forceinline__ void make_point(int kind, const double* __restrict__ frames, const double* s_tab,
+                                           const double* __restrict__ pts_in, const double* __restrict__ w_in,
+                                           const double* __restrict__ s_in, int64_t r, int l, int64_t pidx, double* p,
+                                           double& W, double& S) {
+  if (kind == FXII_OP_POINTS) {
+    p[0] = pts_in[3 * pidx];
+    p[1] = pts_in[3 * pidx + 1];
+    p[2] = pts_in[3 * pidx + 2];
+    W = w_in[pidx];
+    S = s_in[r];
+    return;
+  }
+  const double* f = frames + kFrame * r;
+  if (kind == FXII_OP_TRACE) {
+    p[0] = f[0]; p[1] = f[1]; p[2] = f[2];
+    W = 1.0;
+    S = 1.0;
+    return;
+  }
+  const double xp0 = s_tab[4 * l], xp1 = s_tab[4 * l + 1], xp2 = s_tab[4 * l + 2];
+  const double R = f[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double applied = (f[4 + 3 * d] * xp0 + f[5 + 3 * d] * xp1) + f[6 + 3 * d] * xp2;
+    p[d] = f[d] + applied * R;  // restriction_operators.py:191-199
+  }
+  W = s_tab[4 * l + 3] * f[13];
+  S = f[14];
+}
+
+// basis values of the owning cell at the point, scaled: (phi*W)/S  (interpolation.py:234-238)
+template <int ND>
+__device__ __forceinline__ void tabulate_vals(const double* __restrict__ cellgeo, int cell, const double* p, double W,
+                                              double S, double* vals) {
+  CellGeo g;
+  load_cellgeo(cellgeo, cell, g);
+  double X[3];
+  pull_back(g, p, X);
+  const double lam[4] = {((1.0 - X[0]) - X[1]) - X[2], X[0], X[1], X[2]};
+  double phi[ND];
+  if (ND == 4) {
+#pragma unroll
+    for (int d = 0; d < 4; ++d) phi[d] = lam[d];
+  } else {  // P2, basix order: vertices, then edges (2,3),(1,3),(1,2),(0,3),(0,2),(0,1)
+#pragma unroll
+    for (int d = 0; d < 4; ++d) phi[d] = lam[d] * (2.0 * lam[d] - 1.0);
+    phi[4 % ND] = 4.0 * lam[2] * lam[3];
+    phi[5 % ND] = 4.0 * lam[1] * lam[3];
+    phi[6 % ND] = 4.0 * lam[1] * lam[2];
+    phi[7 % ND] = 4.0 * lam[0] * lam[3];
+    phi[8 % ND] = 4.0 * lam[0] * lam[2];
+    phi[9 % ND] = 4.0 * lam[0] * lam[1];
+  }
+#pragma unroll
+  for (int d = 0; d < ND; ++d) vals[d] = (phi[d] * W) / S;
+}
+
+template <int ND>
+__device__ __forceinline__ void load_cols(const int32_t* __restrict__ dofmap, int cell, int32_t* cols) {
+  const int32_t* dm = dofmap + (int64_t)ND * cell;
+  if (ND == 4) {
+    const int4 d4 = __ldg(reinterpret_cast<const int4*>(dm));
+    cols[0] = d4.x; cols[1] = d4.y; cols[2] = d4.z; cols[3 % ND] = d4.w;
+  } else {
+#pragma unroll
+    for (int d = 0; d < ND; d += 2) {
+      const int2 d2 = __ldg(reinterpret_cast<const int2*>(dm + d));
+      cols[d] = d2.x;
+      cols[(d + 1) % ND] = d2.y;
+    }
+  }
+}
+
 // One thread per 3D point p = r*nq + l (interpolation.py:57).  ND = dofs per V cell.
 template <int ND>
 __global__ void __launch_bounds__(128, 8)
@@ -325,30 +400,7 @@ pi_locate_tabulate_kernel(const BvhNode* __restrict__ nodes, const double* __res
     const int64_t r = pidx / nq;
     const int l = (int)(pidx - r * nq);
     double p[3], W, S;
-    if (kind == FXII_OP_POINTS) {
-      p[0] = pts_in[3 * pidx];
-      p[1] = pts_in[3 * pidx + 1];
-      p[2] = pts_in[3 * pidx + 2];
-      W = w_in[pidx];
-      S = s_in[r];
-    } else {
-      const double* f = frames + kFrame * r;
-      if (kind == FXII_OP_TRACE) {
-        p[0] = f[0]; p[1] = f[1]; p[2] = f[2];
-        W = 1.0;
-        S = 1.0;
-      } else {
-        const double xp0 = s_tab[4 * l], xp1 = s_tab[4 * l + 1], xp2 = s_tab[4 * l + 2];
-        const double R = f[3];
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const double applied = (f[4 + 3 * d] * xp0 + f[5 + 3 * d] * xp1) + f[6 + 3 * d] * xp2;
-          p[d] = f[d] + applied * R;  // restriction_operators.py:191-199
-        }
-        W = s_tab[4 * l + 3] * f[13];
-        S = f[14];
-      }
-    }
+    make_point(kind, frames, s_tab, pts_in, w_in, s_in, r, l, pidx, p, W, S);
     const LocateResult res = locate_point(nodes, cellgeo, x, cell_nodes, padding, p);
     out_cell[pidx] = res.cell;
     out_ncoll[pidx] = (uint8_t)min(res.ncoll, 255);
@@ -369,39 +421,8 @@ pi_locate_tabulate_kernel(const BvhNode* __restrict__ nodes, const double* __res
         vals[d] = 0.0;
       }
     } else {
-      CellGeo g;
-      load_cellgeo(cellgeo, res.cell, g);
-      double X[3];
-      pull_back(g, p, X);
-      double lam[4] = {((1.0 - X[0]) - X[1]) - X[2], X[0], X[1], X[2]};
-      double phi[ND];
-      if (ND == 4) {
-#pragma unroll
-        for (int d = 0; d < 4; ++d) phi[d] = lam[d];
-      } else {  // P2, basix order: vertices, then edges (2,3),(1,3),(1,2),(0,3),(0,2),(0,1)
-#pragma unroll
-        for (int d = 0; d < 4; ++d) phi[d] = lam[d] * (2.0 * lam[d] - 1.0);
-        phi[4 % ND] = 4.0 * lam[2] * lam[3];
-        phi[5 % ND] = 4.0 * lam[1] * lam[3];
-        phi[6 % ND] = 4.0 * lam[1] * lam[2];
-        phi[7 % ND] = 4.0 * lam[0] * lam[3];
-        phi[8 % ND] = 4.0 * lam[0] * lam[2];
-        phi[9 % ND] = 4.0 * lam[0] * lam[1];
-      }
-      const int32_t* dm = dofmap + (int64_t)ND * res.cell;
-      if (ND == 4) {
-        const int4 d4 = __ldg(reinterpret_cast<const int4*>(dm));
-        cols[0] = d4.x; cols[1] = d4.y; cols[2] = d4.z; cols[3 % ND] = d4.w;
-      } else {
-#pragma unroll
-        for (int d = 0; d < ND; d += 2) {
-          const int2 d2 = __ldg(reinterpret_cast<const int2*>(dm + d));
-          cols[d] = d2.x;
-          cols[(d + 1) % ND] = d2.y;
-        }
-      }
-#pragma unroll
-      for (int d = 0; d < ND; ++d) vals[d] = (phi[d] * W) / S;  // interpolation.py:234-238
+      tabulate_vals<ND>(cellgeo, res.cell, p, W, S, vals);
+      load_cols<ND>(dofmap, res.cell, cols);
     }
     int32_t* oc = coo_cols + (int64_t)ND * pidx;
     double* ov = coo_vals + (int64_t)ND * pidx;
@@ -709,6 +730,318 @@ void coo_segments_to_csr(const int32_t* row_dofs, int64_t n_point_rows, int64_t 
   for (auto& e : ke) cudaEventDestroy(e);
 }
 
+// =================================================================================================
+// FUSED PATH.  When every matrix row is produced by exactly one point row (cell-local K: quadrature
+// or DG elements — all BASELINE configs), the block that located the points of a row also reduces it:
+// the COO never reaches HBM.  A TEAM of threads owns one point row (team = pow2 >= nq inside a warp,
+// or whole warps for nq > 32):
+//   A  locate + tabulate: every thread its point                     -> s_cell, s_val
+//   B  cell-level dedupe: the first point of every distinct cell sums the values of all points of
+//      that cell in l order (points of one cell share the column set, so nd entries collapse at once)
+//   C  leaders emit nd (column, value) entries                       -> s_ekey / s_eval
+//   D  team-local bitonic sort of the (column, slot) keys — stable
+//   E  duplicates (dofs shared by neighbouring cells) are summed left to right; sorted unique
+//      entries go to the row's slice of a staging buffer, the row length to row_cnt
+// then one scan and a compaction kernel produce the CSR.  Summation order differs from the
+// unfused path only in association (per cell first); it is fixed, so results are reproducible.
+// =================================================================================================
+__device__ __forceinline__ void team_sync(int team, int team_id) {
+  if (team <= 32) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(team_id + 1), "r"(team) : "memory");
+}
+
+// exclusive prefix of a flag over the threads of a team (+ team total); two team barriers for
+// multi-warp teams
+__device__ __forceinline__ int team_prefix(bool flag, int team, int team_id, int l, int* s_wcnt, int& total) {
+  const unsigned ball = __ballot_sync(0xffffffffu, flag);
+  const int lane = threadIdx.x & 31;
+  if (team <= 32) {
+    const unsigned tmask = (team == 32 ? 0xffffffffu : ((1u << team) - 1u)) << (lane & ~(team - 1));
+    total = __popc(ball & tmask);
+    return __popc(ball & tmask & ((1u << lane) - 1u));
+  }
+  const int warp = threadIdx.x >> 5;
+  const int wpt = team >> 5;               // warps per team
+  const int w0 = team_id * wpt;            // first warp of the team
+  if (lane == 0) s_wcnt[warp] = __popc(ball);
+  team_sync(team, team_id);
+  int before = 0, tot = 0;
+  for (int w = 0; w < wpt; ++w) {
+    const int c = s_wcnt[w0 + w];
+    if (w0 + w < warp) before += c;
+    tot += c;
+  }
+  team_sync(team, team_id);
+  total = tot;
+  return before + __popc(ball & ((1u << lane) - 1u));
+}
+
+template <int ND>
+__global__ void __launch_bounds__(256, 4)
+pi_fused_kernel(const BvhNode* __restrict__ nodes, const double* __restrict__ cellgeo, const double* __restrict__ x,
+                const int4* __restrict__ cell_nodes, double padding, const int32_t* __restrict__ dofmap,
+                const double* __restrict__ frames, const double* __restrict__ table, const double* __restrict__ wq,
+                const double* __restrict__ pts_in, const double* __restrict__ w_in, const double* __restrict__ s_in,
+                int kind, int nq, int team, uint32_t scap, int64_t n_point_rows, int64_t n_rows_total,
+                const int32_t* __restrict__ row_dofs,
+                int32_t* __restrict__ out_cell, uint8_t* __restrict__ out_ncoll, double* __restrict__ out_points,
+                int32_t* __restrict__ stage_col, double* __restrict__ stage_val, int64_t* __restrict__ row_cnt,
+                int32_t* __restrict__ src_row, int* __restrict__ conflict, PiCounters* counters) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const int B = blockDim.x;
+  const int rpb = B / team;  // point rows per block
+  // layout: s_tab f64[nq*4] | s_val f64[B*ND] | s_eval f64[B*ND] | s_ekey u64[rpb*scap] | s_cell i32[B] | s_wcnt i32[B/32]
+  double* s_tab = reinterpret_cast<double*>(s_raw);
+  double* s_val = s_tab + 4 * (size_t)nq;
+  double* s_eval = s_val + (size_t)B * ND;
+  uint64_t* s_ekey = reinterpret_cast<uint64_t*>(s_eval + (size_t)B * ND);
+  int32_t* s_cell = reinterpret_cast<int32_t*>(s_ekey + (size_t)rpb * scap);
+  int* s_wcnt = s_cell + B;
+  if (kind == FXII_OP_CIRCLE || kind == FXII_OP_DISK) {
+    for (int k = threadIdx.x; k < nq; k += B) {
+      s_tab[4 * k + 0] = table[3 * k + 0];
+      s_tab[4 * k + 1] = table[3 * k + 1];
+      s_tab[4 * k + 2] = table[3 * k + 2];
+      s_tab[4 * k + 3] = wq[k];
+    }
+  }
+  __syncthreads();
+  const int tid = threadIdx.x;
+  const int team_id = tid / team;
+  const int l = tid - team_id * team;
+  const int t0 = team_id * team;           // first thread of the team
+  uint64_t* ekey = s_ekey + (size_t)team_id * scap;
+  double* eval = s_eval + (size_t)t0 * ND;
+  const int seg = nq * ND;
+  const bool in_team = team_id < rpb;      // threads beyond the last whole team idle (B % team != 0 never happens)
+  const int64_t n_groups = (n_point_rows + rpb - 1) / rpb;
+  for (int64_t rb = blockIdx.x; rb < n_groups; rb += gridDim.x) {
+    const int64_t r = rb * rpb + team_id;
+    const bool active = in_team && r < n_point_rows && l < nq;
+    // ---- A: locate + tabulate ------------------------------------------------------------------
+    int cell = -1;
+    double vals[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) vals[d] = 0.0;
+    if (active) {
+      const int64_t pidx = r * nq + l;
+      double p[3], W, S;
+      make_point(kind, frames, s_tab, pts_in, w_in, s_in, r, l, pidx, p, W, S);
+      const LocateResult res = locate_point(nodes, cellgeo, x, cell_nodes, padding, p);
+      out_cell[pidx] = res.cell;
+      out_ncoll[pidx] = (uint8_t)min(res.ncoll, 255);
+      if (out_points) {
+        out_points[3 * pidx] = p[0];
+        out_points[3 * pidx + 1] = p[1];
+        out_points[3 * pidx + 2] = p[2];
+      }
+      if (res.ncoll > 1) atomicAdd(&counters->ties, 1ULL);
+      if (res.fallback) atomicAdd(&counters->fallback, 1ULL);
+      cell = res.cell;
+      if (cell < 0) atomicAdd(&counters->not_found, 1ULL);
+      else tabulate_vals<ND>(cellgeo, cell, p, W, S, vals);
+    }
+    s_cell[tid] = cell;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) s_val[(size_t)tid * ND + d] = vals[d];
+    team_sync(team, team_id);
+    // ---- B: first point of every distinct cell sums that cell's points in l order ----------------
+    bool leader = cell >= 0;
+    for (int j = 0; j < l && leader; ++j) leader = s_cell[t0 + j] != cell;
+    if (leader) {
+      for (int j = l + 1; j < nq; ++j) {
+        if (s_cell[t0 + j] == cell) {
+#pragma unroll
+          for (int d = 0; d < ND; ++d) vals[d] += s_val[(size_t)(t0 + j) * ND + d];
+        }
+      }
+    }
+    // ---- C: leaders emit nd entries ---------------------------------------------------------------
+    int n_cells;
+    const int u = team_prefix(leader, team, team_id, l, s_wcnt, n_cells);
+    const uint32_t M = (uint32_t)n_cells * ND;
+    uint32_t S = 2;
+    while (S < M) S <<= 1;
+    if (team < 32) {  // teams sharing a warp iterate in lockstep: use the warp-wide maximum
+      for (int o = 16; o > 0; o >>= 1) S = max(S, __shfl_xor_sync(0xffffffffu, S, o));
+    }
+    for (uint32_t e = M + l; e < S; e += team) ekey[e] = ~0ULL;
+    if (leader) {
+      int32_t cols[ND];
+      load_cols<ND>(dofmap, cell, cols);
+#pragma unroll
+      for (int d = 0; d < ND; ++d) {
+        const uint32_t idx = (uint32_t)u * ND + d;
+        ekey[idx] = ((uint64_t)(uint32_t)cols[d] << 32) | idx;
+        eval[idx] = vals[d];
+      }
+    }
+    team_sync(team, team_id);
+    // ---- D: team-local bitonic sort -----------------------------------------------------------------
+    for (uint32_t k = 2; k <= S; k <<= 1) {
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint32_t t = l; t < S / 2; t += team) {
+          const uint32_t i = 2 * t - (t & (j - 1));
+          const uint32_t ixj = i | j;
+          const bool up = (i & k) == 0;
+          const uint64_t a = ekey[i], b = ekey[ixj];
+          if ((a > b) == up) {
+            ekey[i] = b;
+            ekey[ixj] = a;
+          }
+        }
+        team_sync(team, team_id);
+      }
+    }
+    // ---- E: heads, left-to-right sums, staging ------------------------------------------------------
+    uint32_t Mloop = M;
+    if (team < 32) {
+      for (int o = 16; o > 0; o >>= 1) Mloop = max(Mloop, __shfl_xor_sync(0xffffffffu, Mloop, o));
+    }
+    int base = 0;
+    const int64_t out0 = r * (int64_t)seg;
+    for (uint32_t e0 = 0; e0 < Mloop; e0 += team) {
+      const uint32_t e = e0 + l;
+      bool head = false;
+      uint32_t col = 0;
+      if (e < M) {
+        col = (uint32_t)(ekey[e] >> 32);
+        head = (e == 0) || ((uint32_t)(ekey[e - 1] >> 32) != col);
+      }
+      int chunk_total;
+      const int pos = team_prefix(head, team, team_id, l, s_wcnt, chunk_total);
+      if (head) {
+        double sum = 0.0;
+        for (uint32_t k = e; k < M && (uint32_t)(ekey[k] >> 32) == col; ++k) sum += eval[(uint32_t)(ekey[k] & 0xffffffffu)];
+        stage_col[out0 + base + pos] = (int32_t)col;
+        stage_val[out0 + base + pos] = sum;
+      }
+      base += chunk_total;
+    }
+    if (in_team && r < n_point_rows && l == 0) {
+      const int rho = row_dofs[r];
+      if (rho < 0 || rho >= n_rows_total) *conflict = 2;  // bad row index: reported by the general path
+      else if (atomicCAS(&src_row[rho], -1, (int32_t)r) != -1) *conflict = 1;  // row produced twice: not cell-local
+      else row_cnt[rho] = base;
+    }
+    team_sync(team, team_id);  // s_cell / s_val / ekey are rewritten by the next row group
+  }
+}
+
+// staging -> CSR: a group of G lanes copies one matrix row
+__global__ void __launch_bounds__(256)
+compact_rows_kernel(const int32_t* __restrict__ src_row, const int64_t* __restrict__ indptr, const int32_t* __restrict__ stage_col,
+                    const double* __restrict__ stage_val, int seg, int64_t n_rows, int G, int32_t* __restrict__ indices,
+                    double* __restrict__ values) {
+  const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+  const int lg = threadIdx.x % G;
+  const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / G;
+  for (int64_t rho = gid; rho < n_rows; rho += n_groups) {
+    const int32_t r = src_row[rho];
+    if (r < 0) continue;
+    const int64_t o0 = indptr[rho];
+    const int n = (int)(indptr[rho + 1] - o0);
+    const int64_t s0 = (int64_t)r * seg;
+    for (int k = lg; k < n; k += G) {
+      indices[o0 + k] = stage_col[s0 + k];
+      values[o0 + k] = stage_val[s0 + k];
+    }
+  }
+}
+
+// Returns false when the fused path cannot be used (caller falls back to the COO path).
+static bool pi_assemble_fused(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr* out, PiCounters* counters_dev,
+                              float* ms_locate, float* ms_csr) {
+  const fxii_mesh* m = sp->mesh;
+  const int nd = sp->nd, nq = rows->nq;
+  const int64_t Nr = rows->n_point_rows, Np = Nr * nq, E = Np * nd, n_rows = rows->n_rows_total;
+  if (nq > 256 || Nr == 0 || E >= ((int64_t)1 << 40)) return false;
+  int team = 1;
+  if (nq <= 32) {
+    while (team < nq) team <<= 1;
+  } else {
+    team = 32 * ((nq + 31) / 32);
+  }
+  // block size: whole teams; 128 threads unless a team needs more
+  int B = team <= 128 ? 128 : 256;
+  if (team > 32 && B % team != 0) B = team * (256 / team > 0 ? 256 / team : 1);
+  if (B > 256 || B % 32 != 0) return false;
+  const int rpb = B / team;
+  uint32_t scap = 2;
+  while (scap < (uint32_t)team * nd) scap <<= 1;
+  const size_t smem = sizeof(double) * (4 * (size_t)nq + 2 * (size_t)B * nd) + sizeof(uint64_t) * (size_t)rpb * scap +
+                      sizeof(int32_t) * (size_t)(B + B / 32 + 1);
+  if (smem > 200 * 1024) return false;
+  cudaEvent_t ev[3];
+  for (auto& e : ev) FXII_CUDA(cudaEventCreate(&e));
+  DevBuf<int64_t> row_cnt;
+  DevBuf<int32_t> src_row;
+  DevBuf<int> conflict;
+  row_cnt.alloc(n_rows + 1, s);
+  src_row.alloc(n_rows, s);
+  conflict.alloc(1, s);
+  FXII_CUDA(cudaMemsetAsync(row_cnt.p, 0, sizeof(int64_t) * (size_t)(n_rows + 1), s));
+  FXII_CUDA(cudaMemsetAsync(src_row.p, 0xff, sizeof(int32_t) * (size_t)n_rows, s));
+  FXII_CUDA(cudaMemsetAsync(conflict.p, 0, sizeof(int), s));
+  FXII_CUDA(cudaEventRecord(ev[0], s));
+  const int64_t n_groups = (Nr + rpb - 1) / rpb;
+  auto launch = [&](auto kernel) {
+    if (smem > 48 * 1024) FXII_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    FXII_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, B, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int grid = (int)std::min<int64_t>(n_groups, (int64_t)num_sms() * per_sm);
+    const int4* cn = reinterpret_cast<const int4*>(m->cell_nodes.p);
+    kernel<<<grid, B, smem, s>>>(m->nodes.p, m->cellgeo.p, m->x.p, cn, m->padding, sp->dofmap.p, rows->frames.p,
+                                 rows->table.p, rows->w.p, rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, nq, team,
+                                 scap, Nr, n_rows, rows->row_dofs.p, rows->cell.p, rows->ncoll.p, rows->points.p, rows->coo_cols.p,
+                                 rows->coo_vals.p, row_cnt.p, src_row.p, conflict.p, counters_dev);
+    FXII_LAUNCHED(1);
+    FXII_CUDA(cudaGetLastError());
+  };
+  if (nd == 4) launch(pi_fused_kernel<4>);
+  else launch(pi_fused_kernel<10>);
+  FXII_CUDA(cudaEventRecord(ev[1], s));
+  out->n_rows = n_rows;
+  out->n_cols = sp->n_dofs;
+  out->indptr.alloc(n_rows + 1, s);
+  {
+    size_t tb = 0;
+    FXII_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, (const long long*)row_cnt.p, (long long*)out->indptr.p,
+                                            (int64_t)(n_rows + 1), s));
+    DevBuf<uint8_t> tmp;
+    tmp.alloc((int64_t)tb, s);
+    FXII_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, (const long long*)row_cnt.p, (long long*)out->indptr.p,
+                                            (int64_t)(n_rows + 1), s));
+  }
+  int64_t nnz = 0;
+  int h_conflict = 0;
+  FXII_CUDA(cudaMemcpyAsync(&nnz, out->indptr.p + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  FXII_CUDA(cudaMemcpyAsync(&h_conflict, conflict.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  FXII_CUDA(cudaStreamSynchronize(s));
+  if (h_conflict) {
+    for (auto& e : ev) cudaEventDestroy(e);
+    return false;  // K dofs shared between point rows: the general path handles first-visit-wins
+  }
+  out->nnz = nnz;
+  out->indices.alloc(nnz, s);
+  out->values.alloc(nnz, s);
+  if (nnz > 0) {
+    int G = 4;
+    const int64_t avg = nnz / std::max<int64_t>(1, Nr);
+    while (G < 32 && G < avg) G <<= 1;
+    { compact_rows_kernel<<<grid_for(n_rows * G, 256, 8), 256, 0, s>>>(src_row.p, out->indptr.p, rows->coo_cols.p, rows->coo_vals.p,
+                                                                    nq * nd, n_rows, G, out->indices.p, out->values.p); FXII_LAUNCHED(1); }
+    FXII_CUDA(cudaGetLastError());
+  }
+  FXII_CUDA(cudaEventRecord(ev[2], s));
+  FXII_CUDA(cudaEventSynchronize(ev[2]));
+  *ms_locate = elapsed_ms(ev[0], ev[1]);
+  *ms_csr = elapsed_ms(ev[1], ev[2]);
+  for (auto& e : ev) cudaEventDestroy(e);
+  return true;
+}
+
 // -------------------------------------------------------------------------------------------------
 void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr* out, fxii_pi_stats* stats,
                  bool keep_points) {
@@ -736,34 +1069,45 @@ void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr
   rows->ncoll.alloc(Np, s);
   if (keep_points) rows->points.alloc(3 * Np, s);
   else rows->points.release();
-  rows->coo_cols.alloc(E, s);
+  rows->coo_cols.alloc(E, s);  // COO (unfused) or per-row staging (fused)
   rows->coo_vals.alloc(E, s);
   DevBuf<PiCounters> counters;
   counters.alloc(1, s);
   FXII_CUDA(cudaMemsetAsync(counters.p, 0, sizeof(PiCounters), s));
-  if (Np > 0) {
-    const int threads = 128;
-    const int grid = grid_for(Np, threads, 8);
-    const size_t smem = (rows->kind == FXII_OP_CIRCLE || rows->kind == FXII_OP_DISK) ? sizeof(double) * 4 * (size_t)nq : 0;
-    FXII_CHECK(smem <= 48 * 1024, "operator table too large for shared memory (nq > 1536)");
-    const int4* cn = reinterpret_cast<const int4*>(m->cell_nodes.p);
-    if (nd == 4)
-      { pi_locate_tabulate_kernel<4><<<grid, threads, smem, s>>>(
-          m->nodes.p, m->cellgeo.p, m->x.p, cn, m->padding, sp->dofmap.p, rows->frames.p, rows->table.p, rows->w.p,
-          rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, nq, Np, rows->cell.p, rows->ncoll.p, rows->points.p,
-          rows->coo_cols.p, rows->coo_vals.p, counters.p); FXII_LAUNCHED(1); }
-    else
-      { pi_locate_tabulate_kernel<10><<<grid, threads, smem, s>>>(
-          m->nodes.p, m->cellgeo.p, m->x.p, cn, m->padding, sp->dofmap.p, rows->frames.p, rows->table.p, rows->w.p,
-          rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, nq, Np, rows->cell.p, rows->ncoll.p, rows->points.p,
-          rows->coo_cols.p, rows->coo_vals.p, counters.p); FXII_LAUNCHED(1); }
-    FXII_CUDA(cudaGetLastError());
+  const size_t tab_smem = (rows->kind == FXII_OP_CIRCLE || rows->kind == FXII_OP_DISK) ? sizeof(double) * 4 * (size_t)nq : 0;
+  FXII_CHECK(tab_smem <= 48 * 1024, "operator table too large for shared memory (nq > 1536)");
+  float ms_count = 0.f, ms_fill = 0.f, ms_loc_f = 0.f, ms_csr_f = 0.f;
+  bool fused = false;
+  if (rows->mode != 1) fused = pi_assemble_fused(sp, rows, s, out, counters.p, &ms_loc_f, &ms_csr_f);
+  rows->last_fused = fused;
+  if (!fused) {
+    FXII_CUDA(cudaMemsetAsync(counters.p, 0, sizeof(PiCounters), s));
+    FXII_CUDA(cudaEventRecord(ev[1], s));
+    if (Np > 0) {
+      const int threads = 128;
+      const int grid = grid_for(Np, threads, 8);
+      const size_t smem = tab_smem;
+      const int4* cn = reinterpret_cast<const int4*>(m->cell_nodes.p);
+      if (nd == 4)
+        { pi_locate_tabulate_kernel<4><<<grid, threads, smem, s>>>(
+            m->nodes.p, m->cellgeo.p, m->x.p, cn, m->padding, sp->dofmap.p, rows->frames.p, rows->table.p, rows->w.p,
+            rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, nq, Np, rows->cell.p, rows->ncoll.p, rows->points.p,
+            rows->coo_cols.p, rows->coo_vals.p, counters.p); FXII_LAUNCHED(1); }
+      else
+        { pi_locate_tabulate_kernel<10><<<grid, threads, smem, s>>>(
+            m->nodes.p, m->cellgeo.p, m->x.p, cn, m->padding, sp->dofmap.p, rows->frames.p, rows->table.p, rows->w.p,
+            rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, nq, Np, rows->cell.p, rows->ncoll.p, rows->points.p,
+            rows->coo_cols.p, rows->coo_vals.p, counters.p); FXII_LAUNCHED(1); }
+      FXII_CUDA(cudaGetLastError());
+    }
+    FXII_CUDA(cudaEventRecord(ev[2], s));
+    coo_segments_to_csr(rows->row_dofs.p, Nr, rows->n_rows_total, nq * nd, rows->coo_cols.p, rows->coo_vals.p, sp->n_dofs, s,
+                        out, &ms_count, &ms_fill);
+    FXII_CUDA(cudaEventRecord(ev[3], s));
+  } else {
+    FXII_CUDA(cudaEventRecord(ev[2], s));
+    FXII_CUDA(cudaEventRecord(ev[3], s));
   }
-  FXII_CUDA(cudaEventRecord(ev[2], s));
-  float ms_count = 0.f, ms_fill = 0.f;
-  coo_segments_to_csr(rows->row_dofs.p, Nr, rows->n_rows_total, nq * nd, rows->coo_cols.p, rows->coo_vals.p, sp->n_dofs, s,
-                      out, &ms_count, &ms_fill);
-  FXII_CUDA(cudaEventRecord(ev[3], s));
   PiCounters h;
   FXII_CUDA(cudaMemcpyAsync(&h, counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
   FXII_CUDA(cudaStreamSynchronize(s));
@@ -774,10 +1118,11 @@ void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr
     stats->n_ties = (int64_t)h.ties;
     stats->n_fallback = (int64_t)h.fallback;
     stats->ms_frames = elapsed_ms(ev[0], ev[1]);
-    stats->ms_locate = elapsed_ms(ev[1], ev[2]);
-    stats->ms_csr = elapsed_ms(ev[2], ev[3]);
+    stats->ms_locate = fused ? ms_loc_f : elapsed_ms(ev[1], ev[2]);
+    stats->ms_csr = fused ? ms_csr_f : elapsed_ms(ev[2], ev[3]);
     stats->ms_csr_count = ms_count;
     stats->ms_csr_fill = ms_fill;
+    stats->fused = fused ? 1 : 0;
   }
   for (auto& e : ev) cudaEventDestroy(e);
   if (h.not_found > 0)

@@ -148,6 +148,10 @@ class DeviceRows:
     def keep_points(self, flag: bool = True):
         _lib.check(_lib.load().fxii_rows_keep_points(self._h, 1 if flag else 0))
 
+    def set_mode(self, mode: int):
+        """0: fused row reduction when possible (default); 1: always materialise the COO."""
+        _lib.check(_lib.load().fxii_rows_set_mode(self._h, int(mode)))
+
     def assemble(self, space: DeviceSpace, stream=None, allow_not_found: bool = False):
         """Run the Π assembly; returns (DeviceCSR, PiStats)."""
         out = C.c_void_p()
@@ -253,7 +257,7 @@ def device_rows(K, red_op, cells_K=None) -> DeviceRows:
 
 
 def create_interpolation_matrix(V, K, red_op, tol: float = 1.0e-8, use_petsc: bool = False, cells_K=None,
-                                complex_dtype: bool = False):
+                                complex_dtype: bool = False, materialize_coo: bool = False):
     """Create an interpolation matrix from `V` to `K` with a specific reduction operator applied to
     the interpolation points of `K`.
 
@@ -265,6 +269,7 @@ def create_interpolation_matrix(V, K, red_op, tol: float = 1.0e-8, use_petsc: bo
         use_petsc: Return a PETSc AIJ matrix (requires petsc4py) instead of a ``MatrixCSR``.
         cells_K: Optional subset of the cells of K to process.
         complex_dtype: Not supported on the device path.
+        materialize_coo: (extension) force the unfused COO path, e.g. to inspect the COO.
 
     Returns:
         ``(A, imap_K, imap_V)``: the matrix and the (serial: unchanged) index maps of K and V.
@@ -273,6 +278,8 @@ def create_interpolation_matrix(V, K, red_op, tol: float = 1.0e-8, use_petsc: bo
         raise NotImplementedError("complex matrices are not supported on the device path")
     dspace = device_space(V, tol)
     rows = device_rows(K, red_op, cells_K)
+    if materialize_coo:
+        rows.set_mode(1)
     csr, stats = rows.assemble(dspace)
     A = MatrixCSR(csr, stats=stats, rows=rows)
     imap_K, imap_V = K.dofmap.index_map, V.dofmap.index_map

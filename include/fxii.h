@@ -94,6 +94,10 @@ int fxii_rows_destroy(fxii_rows* r);
 /* diagnostics: also materialise the generated 3D points [Np,3] (off by default: the points are
  * otherwise never written to HBM) */
 int fxii_rows_keep_points(fxii_rows* r, int32_t flag);
+/* mode 0 (default): reduce rows inside the locate kernel when every matrix row comes from one point row
+ * (cell-local K), falling back to the COO path otherwise; mode 1: always materialise the COO
+ * (needed by fxii_rows_download_coo). */
+int fxii_rows_set_mode(fxii_rows* r, int32_t mode);
 
 /* ---- Π assembly -------------------------------------------------------------------------- */
 typedef struct {
@@ -103,7 +107,8 @@ typedef struct {
   int64_t n_ties;       /* points colliding with more than one cell */
   int64_t n_fallback;   /* points assigned by the nearest-cell fallback */
   float ms_frames, ms_locate, ms_csr; /* device time of the three stages (CUDA events) */
-  float ms_csr_count, ms_csr_fill;    /* the two row kernels inside ms_csr */
+  float ms_csr_count, ms_csr_fill;    /* the two row kernels inside ms_csr (COO path) */
+  int32_t fused;                      /* 1: rows were reduced inside the locate kernel (no COO in HBM) */
 } fxii_pi_stats;
 
 /* Builds Π (n_rows_total x n_dofs).  Leaves per-point diagnostics on `rows`

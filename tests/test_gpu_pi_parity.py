@@ -14,19 +14,27 @@ from tests.helpers import assert_csr_parity, make_operator, oracle_pi, small_cfg
 pytestmark = pytest.mark.gpu
 
 
-def run_case(V, K, gamma, op_name, radius=None, degree=None, cells_K=None, cell_radius=None):
+def run_case(V, K, gamma, op_name, radius=None, degree=None, cells_K=None, cell_radius=None, expect_fused=None):
+    """Both device paths against the oracle: the default one (rows reduced inside the locate kernel
+    when K is cell-local) and the forced COO path (whose COO is compared entry by entry)."""
     rad = cell_radius if cell_radius is not None else radius
     op = make_operator(op_name, gamma, rad, degree)
-    A, imap_K, imap_V = create_interpolation_matrix(V, K, op, cells_K=cells_K)
     ref = oracle_pi(V, K, gamma, op_name, radius, degree, cells_K=cells_K, return_coo=True, cell_radius=cell_radius)
-    cell, ncoll = A.rows.diagnostics()
-    np.testing.assert_array_equal(cell, ref["cell"])
-    np.testing.assert_array_equal(ncoll.astype(np.int64), np.minimum(ref["n_colliding"], 255))
-    cols, vals = A.rows.coo()
-    np.testing.assert_array_equal(cols, ref["cols"])
-    assert_csr_parity((A.indptr, A.indices, A.data), ref)
-    assert A.shape == (K.num_dofs, V.num_dofs)
-    assert imap_K is K.dofmap.index_map and imap_V is V.dofmap.index_map
+    A = None
+    for materialize in (True, False):
+        A, imap_K, imap_V = create_interpolation_matrix(V, K, op, cells_K=cells_K, materialize_coo=materialize)
+        cell, ncoll = A.rows.diagnostics()
+        np.testing.assert_array_equal(cell, ref["cell"])
+        np.testing.assert_array_equal(ncoll.astype(np.int64), np.minimum(ref["n_colliding"], 255))
+        if materialize:
+            assert A.stats["fused"] == 0
+            cols, vals = A.rows.coo()
+            np.testing.assert_array_equal(cols, ref["cols"])
+        elif expect_fused is not None:
+            assert bool(A.stats["fused"]) == expect_fused
+        assert_csr_parity((A.indptr, A.indices, A.data), ref)
+        assert A.shape == (K.num_dofs, V.num_dofs)
+        assert imap_K is K.dofmap.index_map and imap_V is V.dofmap.index_map
     return A, ref
 
 
@@ -38,7 +46,7 @@ def test_config1_straight_line_ties(cuda, op_name, radius, degree):
     mesh, V = small_cfg(8, 8, 16)
     gamma = sy.straight_line(17)
     K = functionspace(gamma, ("Quadrature", 10))
-    A, ref = run_case(V, K, gamma, op_name, radius, degree)
+    A, ref = run_case(V, K, gamma, op_name, radius, degree, expect_fused=True)
     assert (ref["n_colliding"] > 1).any()
     np.testing.assert_allclose(np.asarray(A.to_scipy().sum(axis=1)).ravel(), 1.0, atol=1e-13)
 
@@ -50,7 +58,8 @@ def test_network_generic_position(cuda, kspace, op_name, radius, degree):
     mesh, V = small_cfg(12, 12, 12)
     gamma = sy.polyline_network(400, 1 / 12, n_lines=5)
     K = functionspace(gamma, kspace)
-    A, ref = run_case(V, K, gamma, op_name, radius, degree)
+    # continuous K shares dofs between Γ cells: the fused path must detect it and fall back
+    A, ref = run_case(V, K, gamma, op_name, radius, degree, expect_fused=kspace[0] != "Lagrange")
 
 
 @pytest.mark.parametrize("op_name,degree", [("circle", 15), ("circle", 126), ("disk", 7)])
@@ -60,7 +69,7 @@ def test_p2_vessel_tree_per_segment_radius(cuda, op_name, degree):
     h = 1 / 10
     gamma, seg_r = sy.vessel_tree(300, h / 2, r_min=0.2 * h, r_max=1.5 * h, branch_len=40)
     K = functionspace(gamma, ("Quadrature", 10))
-    run_case(V, K, gamma, op_name, None, degree, cell_radius=seg_r)
+    run_case(V, K, gamma, op_name, None, degree, cell_radius=seg_r, expect_fused=True)
 
 
 def test_cells_subset_and_callable_radius(cuda):
@@ -130,3 +139,21 @@ def test_run_to_run_bitwise_reproducible(cuda):
     A2, _, _ = create_interpolation_matrix(V, K, op)
     np.testing.assert_array_equal(A1.indices, A2.indices)
     assert A1.data.tobytes() == A2.data.tobytes()
+
+
+@pytest.mark.parametrize("nq_degree", [3, 4, 11, 17, 31, 33, 47, 65, 95, 129])
+def test_fused_team_sizes(cuda, nq_degree):
+    """Circle rules with 2..65 points exercise every team shape of the fused kernel (sub-warp teams,
+    one warp, several warps, block sizes 128/192/256)."""
+    mesh, V = small_cfg(6, 6, 6)
+    gamma = sy.polyline_network(40, 1 / 6, n_lines=2, lo=0.3, hi=0.7)
+    K = functionspace(gamma, ("DG", 1))
+    run_case(V, K, gamma, "circle", 0.08, nq_degree, expect_fused=True)
+
+
+def test_fused_p2_disk_many_points(cuda):
+    mesh, V = small_cfg(6, 6, 6, degree=2)
+    gamma = sy.polyline_network(30, 1 / 6, n_lines=2, lo=0.35, hi=0.65)
+    K = functionspace(gamma, ("Quadrature", 2))
+    run_case(V, K, gamma, "disk", 0.12, 11, expect_fused=True)  # 121 points per row
+    run_case(V, K, gamma, "disk", 0.12, 17, expect_fused=False)  # 289 points per row: COO path
