@@ -843,7 +843,7 @@ pi_fused_kernel(const BvhNode* __restrict__ nodes, const double* __restrict__ ce
     }
     s_cell[tid] = cell;
 #pragma unroll
-    for (int d = 0; d < ND; ++d) s_val[(size_t)tid * ND + d] = vals[d];
+    for (int d = 0; d < ND; ++d) s_val[(size_t)d * B + tid] = vals[d];  // [d][thread]: conflict-free
     team_sync(team, team_id);
     // ---- B: first point of every distinct cell sums that cell's points in l order ----------------
     bool leader = cell >= 0;
@@ -852,7 +852,7 @@ pi_fused_kernel(const BvhNode* __restrict__ nodes, const double* __restrict__ ce
       for (int j = l + 1; j < nq; ++j) {
         if (s_cell[t0 + j] == cell) {
 #pragma unroll
-          for (int d = 0; d < ND; ++d) vals[d] += s_val[(size_t)(t0 + j) * ND + d];
+          for (int d = 0; d < ND; ++d) vals[d] += s_val[(size_t)d * B + t0 + j];
         }
       }
     }
@@ -987,6 +987,12 @@ static bool pi_assemble_fused(const fxii_space* sp, fxii_rows* rows, cudaStream_
   const int64_t n_groups = (Nr + rpb - 1) / rpb;
   auto launch = [&](auto kernel) {
     if (smem > 48 * 1024) FXII_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // shared memory for 8 resident blocks of 128 threads (the register limit), the rest stays L1
+    int carve = (int)((smem + 1024) * (1024 / B) * 100 / (228 * 1024)) + 1;
+    if (carve > 100) carve = 100;
+    static const char* env_carve = getenv("FXII_CARVEOUT");  // tuning knob: -1 keeps the driver default
+    if (env_carve) carve = atoi(env_carve);
+    if (carve >= 0) FXII_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     int per_sm = 1;
     FXII_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, B, smem));
     if (per_sm < 1) per_sm = 1;
