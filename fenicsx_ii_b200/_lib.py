@@ -63,6 +63,7 @@ SIGNATURES = {
     "fxii_set_device": (C.c_int, [C.c_int]),
     "fxii_sm_count": (C.c_int, [C.POINTER(C.c_int)]),
     "fxii_launch_count": (C.c_int64, []),
+    "fxii_trim_memory": (C.c_int, []),
     "fxii_mesh_create": (C.c_int, [_vp, _i64, _vp, _i64, _dbl, _vp, C.POINTER(_vp)]),
     "fxii_mesh_info": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i32)]),
     "fxii_mesh_destroy": (C.c_int, [_vp]),

@@ -17,9 +17,100 @@ void csr_spmv(const fxii_csr* a, const double* u_host, double* y_host, cudaStrea
 }  // namespace fxii
 
 static thread_local std::string g_last_error;
+#include <chrono>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
 namespace fxii {
 int64_t g_launches = 0;
+double Trace::now() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+Trace::Trace(const char* w, cudaStream_t st) : s(st), what(w) {
+  static const bool enabled = getenv("FXII_TRACE") != nullptr;
+  on = enabled;
+  if (on) {
+    cudaStreamSynchronize(s);
+    t0 = now();
+  }
+}
+void Trace::mark(const char* label) {
+  if (!on) return;
+  cudaStreamSynchronize(s);
+  const double t = now();
+  fprintf(stderr, "[fxii %s] %-28s %9.3f ms\n", what, label, t - t0);
+  t0 = t;
+}
+
+// ---- size-class caching allocator -----------------------------------------------------------------
+namespace {
+struct Block {
+  void* p;
+  cudaStream_t last;
+};
+std::mutex g_mem_mutex;
+std::map<size_t, std::vector<Block>> g_free;      // size class -> free blocks
+std::unordered_map<void*, size_t> g_live;          // live block -> size class
+size_t g_cached_bytes = 0;
+
+size_t size_class(size_t bytes) {
+  if (bytes <= 512) return 512;
+  // round up to a multiple of 2^(floor(log2)-3): at most 12.5 % slack, 8 classes per octave
+  int lg = 63 - __builtin_clzll((unsigned long long)bytes);
+  const size_t step = (size_t)1 << (lg - 3);
+  return (bytes + step - 1) / step * step;
+}
+}  // namespace
+
+void* cached_alloc(size_t bytes, cudaStream_t s) {
+  const size_t cls = size_class(bytes);
+  {
+    std::lock_guard<std::mutex> lock(g_mem_mutex);
+    auto it = g_free.find(cls);
+    if (it != g_free.end() && !it->second.empty()) {
+      Block b = it->second.back();
+      it->second.pop_back();
+      g_cached_bytes -= cls;
+      g_live[b.p] = cls;
+      if (b.last != s) cudaStreamSynchronize(b.last);  // cross-stream reuse: wait for the old stream
+      return b.p;
+    }
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, cls);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    cache_trim();  // give cached blocks back and retry once
+    e = cudaMalloc(&p, cls);
+  }
+  if (e != cudaSuccess)
+    throw Error(FXII_E_CUDA, std::string("cudaMalloc of ") + std::to_string(cls) + " bytes: " + cudaGetErrorString(e));
+  std::lock_guard<std::mutex> lock(g_mem_mutex);
+  g_live[p] = cls;
+  return p;
+}
+
+void cached_free(void* p, cudaStream_t s) {
+  std::lock_guard<std::mutex> lock(g_mem_mutex);
+  auto it = g_live.find(p);
+  if (it == g_live.end()) return;
+  const size_t cls = it->second;
+  g_live.erase(it);
+  g_free[cls].push_back(Block{p, s});
+  g_cached_bytes += cls;
+}
+
+void cache_trim() {
+  std::lock_guard<std::mutex> lock(g_mem_mutex);
+  cudaDeviceSynchronize();
+  for (auto& kv : g_free)
+    for (auto& b : kv.second) cudaFree(b.p);
+  g_free.clear();
+  g_cached_bytes = 0;
+}
+}  // namespace fxii
 
 template <typename F>
 static int guarded(F&& f) {
@@ -55,6 +146,10 @@ int fxii_set_device(int device) {
 }
 
 int64_t fxii_launch_count(void) { return fxii::g_launches; }
+
+int fxii_trim_memory(void) {
+  return guarded([&] { fxii::cache_trim(); });
+}
 
 int fxii_sm_count(int* n) {
   return guarded([&] {

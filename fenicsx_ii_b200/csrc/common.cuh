@@ -48,6 +48,15 @@ inline int grid_for(int64_t work_items, int block, int blocks_per_sm) {
   return (int)(need < cap ? need : cap);
 }
 
+// Device memory comes from a size-class cache on top of cudaMalloc (capi.cu): blocks are rounded up to
+// 1/8-octave size classes and kept on free lists, so the repeated, differently sized temporaries of a
+// build never reach the driver again.  (The stream-ordered cudaMallocAsync pool stalled for up to 230 ms
+// when multi-GB temporaries fragmented it.)  A block is reused in stream order; reuse from a different
+// stream first synchronises the stream that last used it.
+void* cached_alloc(size_t bytes, cudaStream_t s);
+void cached_free(void* p, cudaStream_t s);
+void cache_trim();  // return all cached blocks to the driver
+
 // stream-ordered device buffer
 template <typename T>
 struct DevBuf {
@@ -66,14 +75,14 @@ struct DevBuf {
     release();
     n = count;
     st = s;
-    if (count > 0) FXII_CUDA(cudaMallocAsync((void**)&p, sizeof(T) * (size_t)count, s));
+    if (count > 0) p = static_cast<T*>(cached_alloc(sizeof(T) * (size_t)count, s));
   }
   void upload(const T* host, int64_t count, cudaStream_t s) {
     alloc(count, s);
     if (count > 0) FXII_CUDA(cudaMemcpyAsync(p, host, sizeof(T) * (size_t)count, cudaMemcpyHostToDevice, s));
   }
   void release() {
-    if (p) cudaFreeAsync(p, st);
+    if (p) cached_free(p, st);
     p = nullptr;
     n = 0;
   }
@@ -82,6 +91,17 @@ struct DevBuf {
 };
 
 void init_pool_once();
+
+// FXII_TRACE=1: print host wall time between marks (each mark synchronises the stream)
+struct Trace {
+  bool on;
+  cudaStream_t s;
+  const char* what;
+  double t0;
+  static double now();
+  Trace(const char* w, cudaStream_t st);
+  void mark(const char* label);
+};
 extern int64_t g_launches;  // kernels launched by this library (fxii_launch_count)
 #define FXII_LAUNCHED(n) (::fxii::g_launches += (n))
 

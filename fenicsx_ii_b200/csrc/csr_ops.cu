@@ -61,6 +61,7 @@ static void exclusive_scan_i64(const long long* in, long long* out, int64_t n, c
 // source rows in ascending order — the order MatTranspose produces.
 void csr_transpose(const fxii_csr* a, cudaStream_t s, fxii_csr* out) {
   FXII_CHECK(a->nnz < ((int64_t)1 << 31), "transpose: nnz must fit int32 (shard the matrix)");
+  Trace tr("transpose", s);
   out->n_rows = a->n_cols;
   out->n_cols = a->n_rows;
   out->nnz = a->nnz;
@@ -76,6 +77,7 @@ void csr_transpose(const fxii_csr* a, cudaStream_t s, fxii_csr* out) {
     FXII_CUDA(cudaGetLastError());
   }
   exclusive_scan_i64((const long long*)count.p, (long long*)out->indptr.p, a->n_cols + 1, s);
+  tr.mark("alloc + hist + scan");
   if (nnz == 0) return;
   DevBuf<int32_t> row_of, iota, perm, keys_sorted;
   row_of.alloc(nnz, s);
@@ -86,25 +88,29 @@ void csr_transpose(const fxii_csr* a, cudaStream_t s, fxii_csr* out) {
   { iota32_kernel<<<grid_for(nnz, 256, 8), 256, 0, s>>>(iota.p, nnz); FXII_LAUNCHED(1); }
   int end_bit = 1;
   while (end_bit < 31 && ((int64_t)1 << end_bit) < a->n_cols) ++end_bit;
+  tr.mark("alloc + expand + iota");
   size_t tb = 0;
   FXII_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, a->indices.p, keys_sorted.p, iota.p, perm.p, nnz, 0, end_bit, s));
   DevBuf<uint8_t> tmp;
   tmp.alloc((int64_t)tb, s);
   FXII_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, a->indices.p, keys_sorted.p, iota.p, perm.p, nnz, 0, end_bit, s));
+  tr.mark("radix sort");
   { gather_transposed_kernel<<<grid_for(nnz, 256, 8), 256, 0, s>>>(perm.p, row_of.p, a->values.p, nnz, out->indices.p,
                                                                  out->values.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
 }
 
 // ---- SpGEMM -------------------------------------------------------------------------------------
-// Row-wise hash SpGEMM, two phases (symbolic count -> scan -> numeric), rows binned by size so that
-// every row gets a shared-memory table just big enough:
-//   symbolic: bins by the intermediate-product bound ub_i (table capacity >= 2*ub_i)
-//   numeric : bins by the exact nnz_i from the symbolic phase (capacity >= 2*nnz_i)
-// One GROUP (a warp, or a whole block for long rows) owns an output row.
+// Row-wise hash SpGEMM, two phases (symbolic count -> scan -> numeric), one GROUP (a warp, or a
+// block for long rows) per output row, shared-memory tables sized by the row:
+//   symbolic: rows with at most 512 intermediate products get an exact table (>= 2*ub_i slots).
+//             Longer rows compress strongly in this problem (C_i is the union of overlapping
+//             neighbourhoods), so they first try a 2048-slot warp table; rows that overflow it retry
+//             in a 32768-slot block table, and what overflows that is counted in global memory.
+//   numeric : bins by the exact nnz_i from the symbolic phase (capacity >= 2*nnz_i).
+// (A device-wide cub segmented sort of the finished rows was measured and rejected: 54-230 ms for
+// 136 M entries in 17 M mostly empty segments, against ~18 ms for the in-kernel bitonic sort.)
 
-// upper bound of nnz(C_i): number of intermediate products of row i (one thread per row: rows of
-// Pi^T are short and mostly empty)
 __global__ void __launch_bounds__(256)
 spgemm_ub_kernel(const int64_t* __restrict__ a_ptr, const int32_t* __restrict__ a_idx, const int64_t* __restrict__ b_ptr,
                  int64_t row_begin, int64_t n_rows, int64_t* __restrict__ ub) {
@@ -120,20 +126,20 @@ spgemm_ub_kernel(const int64_t* __restrict__ a_ptr, const int32_t* __restrict__ 
 }
 
 constexpr int32_t kEmpty = -1;
-constexpr int kNumBins = 6;  // bins 0..4: shared-memory tables sized by the row; bin 5: the long rows
-// capacity of the table of bin b; a row goes to the first bin whose capacity is >= 2*size
+constexpr int kNumBins = 6;  // bins 0..4: shared-memory tables of bin_cap slots; bin 5: long rows
 __host__ __device__ constexpr uint32_t bin_cap(int b) {
-  return b == 0 ? 64u : b == 1 ? 256u : b == 2 ? 1024u : b == 3 ? 4096u : b == 4 ? 8192u : 32768u;
+  return b == 0 ? 64u : b == 1 ? 256u : b == 2 ? 1024u : b == 3 ? 4096u : 8192u;
 }
 
 __device__ __forceinline__ uint32_t hash_col(uint32_t c) { return c * 2654435761u; }
 
-// Insert `key` into an open-addressing table of `cap` (power of two) slots; returns the slot.
+// Insert `key` into an open-addressing table of `cap` (power of two) slots; returns the slot
+// (0xffffffff when the table is full).
 // A plain load finds the (common) already-present key without an atomic.
 __device__ __forceinline__ uint32_t hash_insert(int32_t* keys, uint32_t cap, int32_t key, bool& is_new) {
   uint32_t h = (hash_col((uint32_t)key) >> 7) & (cap - 1);
   is_new = false;
-  while (true) {
+  for (uint32_t probe = 0; probe < cap; ++probe) {
     int32_t cur = *(volatile int32_t*)(keys + h);
     if (cur == key) return h;
     if (cur == kEmpty) {
@@ -146,13 +152,15 @@ __device__ __forceinline__ uint32_t hash_insert(int32_t* keys, uint32_t cap, int
     }
     h = (h + 1) & (cap - 1);
   }
+  return 0xffffffffu;  // table full (only possible in an overflow-checked symbolic pass)
 }
 
-// NUMERIC=false: row_size[i] = number of distinct columns of row i.
+// NUMERIC=false: row_size[i] = number of distinct columns of row i, or -1 when more than
+//   overflow_limit (> 0) distinct columns were seen (the row is retried with a larger table).
 // NUMERIC=true : accumulate values — sequentially over k (A's column order), in parallel over the
 //   entries of B's row k, whose columns are distinct, so no two lanes touch the same slot between two
-//   group barriers and the floating-point sum order is fixed — then compact the occupied slots into
-//   (col, slot) keys, bitonic-sort them and write the row in ascending column order.
+//   group barriers and the floating-point sum order is fixed — then compact the occupied slots
+//   into (column, slot) keys, bitonic-sort them and write the row in ascending column order.
 // Table storage: shared memory (g_keys == nullptr) or a per-row slice of global memory.
 // Shared layout per group: vals f64[cap] | sort u64[cap/2] | keys i32[cap] (NUMERIC); keys i32[cap].
 template <bool BLOCK, bool NUMERIC>
@@ -160,8 +168,9 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
                                    const double* __restrict__ a_val, const int64_t* __restrict__ b_ptr,
                                    const int32_t* __restrict__ b_idx, const double* __restrict__ b_val,
                                    int64_t row_begin, const int32_t* __restrict__ row_list, int64_t n_list, uint32_t cap,
-                                   int overflow_limit, int* __restrict__ overflow_flag, int32_t* __restrict__ g_keys, double* __restrict__ g_vals,
-                                   uint64_t* __restrict__ g_sort, const int64_t* __restrict__ g_off,
+                                   int overflow_limit, int* __restrict__ overflow_flag, int32_t* __restrict__ g_keys,
+                                   double* __restrict__ g_vals, uint64_t* __restrict__ g_sort,
+                                   const int64_t* __restrict__ g_off,
                                    int64_t* __restrict__ row_size, const int64_t* __restrict__ c_ptr,
                                    int32_t* __restrict__ c_idx, double* __restrict__ c_val) {
   extern __shared__ __align__(16) unsigned char s_raw[];
@@ -170,13 +179,9 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
   const int groups_per_block = BLOCK ? 1 : blockDim.x / 32;
   const int gid = BLOCK ? 0 : threadIdx.x / 32;
   __shared__ int s_cnt[32];
-  __shared__ int s_new;  // distinct keys inserted so far (only tracked when overflow_limit > 0)
+  __shared__ int s_new[32];  // distinct keys inserted so far, per group (tracked when overflow_limit > 0)
   for (int64_t li = (int64_t)blockIdx.x * groups_per_block + gid; li < n_list; li += (int64_t)gridDim.x * groups_per_block) {
     const int64_t i = row_list[li];  // row index relative to row_begin
-    if (overflow_limit > 0) {
-      if (threadIdx.x == 0) s_new = 0;
-      __syncthreads();
-    }
     int32_t* keys;
     double* vals = nullptr;
     uint64_t* sortbuf = nullptr;
@@ -203,39 +208,49 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
       keys[t] = kEmpty;
       if (NUMERIC) vals[t] = 0.0;
     }
+    if (tid == 0) {
+      s_new[gid] = 0;
+      s_cnt[gid] = 0;
+    }
     group_sync<BLOCK>();
     const int64_t a0 = a_ptr[row_begin + i], a1 = a_ptr[row_begin + i + 1];
+    bool overflow = false;
     for (int64_t ka = a0; ka < a1; ++ka) {
       const int k = a_idx[ka];
       const double av = NUMERIC ? a_val[ka] : 0.0;
       const int64_t b0 = b_ptr[k], b1 = b_ptr[k + 1];
-      if (overflow_limit > 0 && *(volatile int*)&s_new > overflow_limit) break;  // uniform: read after a barrier
+      if (overflow_limit > 0) {  // group-uniform: read after a barrier
+        // B rows are shorter than the head-room left above the limit, so the table cannot fill up
+        // between two checks
+        overflow = *(volatile int*)&s_new[gid] > overflow_limit;
+        if (overflow) break;
+      }
       for (int64_t kb = b0 + tid; kb < b1; kb += nthreads) {
         bool is_new;
         const uint32_t slot = hash_insert(keys, tcap, __ldg(&b_idx[kb]), is_new);
         if (NUMERIC) vals[slot] += av * __ldg(&b_val[kb]);
-        if (overflow_limit > 0 && is_new) atomicAdd(&s_new, 1);
+        if (overflow_limit > 0 && is_new) atomicAdd(&s_new[gid], 1);
+        if (!NUMERIC && slot == 0xffffffffu) atomicAdd(&s_new[gid], (int)tcap);  // full: force the retry
       }
       if (NUMERIC || overflow_limit > 0) group_sync<BLOCK>();
     }
-    if (overflow_limit > 0 && *(volatile int*)&s_new > overflow_limit && tid == 0) *overflow_flag = 1;
     group_sync<BLOCK>();
     if (!NUMERIC) {
+      if (overflow_limit > 0) overflow = *(volatile int*)&s_new[gid] > overflow_limit;
       int local = 0;
       for (uint32_t t = tid; t < tcap; t += nthreads) local += keys[t] != kEmpty;
       for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
       if (BLOCK) {
-        if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = local;
+        if ((threadIdx.x & 31) == 0 && local) atomicAdd(&s_cnt[0], local);
         __syncthreads();
         if (threadIdx.x == 0) {
-          int tot = 0;
-          for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_cnt[w];
-          // -1: the table overflowed, the row is recounted with a global-memory table
-          row_size[i] = (overflow_limit > 0 && s_new > overflow_limit) ? -1 : tot;
+          row_size[i] = overflow ? -1 : s_cnt[0];
+          if (overflow) *overflow_flag = 1;
         }
         __syncthreads();
       } else if (tid == 0) {
-        row_size[i] = local;
+        row_size[i] = overflow ? -1 : local;
+        if (overflow) *overflow_flag = 1;
       }
       group_sync<BLOCK>();
     } else {
@@ -243,10 +258,8 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
       const uint32_t nnz = (uint32_t)(c_ptr[i + 1] - out0);
       uint32_t scap = 2;
       while (scap < nnz) scap <<= 1;
-      for (uint32_t t = tid; t < scap; t += nthreads) sortbuf[t] = ~0ULL;
-      if (tid == 0) s_cnt[gid] = 0;
-      group_sync<BLOCK>();
-      // compact occupied slots; order is irrelevant (sorted next), so a shared counter suffices
+      for (uint32_t t = nnz + tid; t < scap; t += nthreads) sortbuf[t] = ~0ULL;
+      // compact the occupied slots as (column, slot) keys; their order is irrelevant (sorted next)
       for (uint32_t t0 = 0; t0 < tcap; t0 += nthreads) {
         const uint32_t t = t0 + tid;
         const int32_t key = t < tcap ? keys[t] : kEmpty;
@@ -269,10 +282,10 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
   }
 }
 
-// bin index by size (0 -> skipped): first bin with capacity >= 2*size, else the global bin
+// bin index by size: first bin with capacity >= 2*size, long rows in the last bin, empty rows skipped
 __global__ void __launch_bounds__(256)
-classify_rows_kernel(const int64_t* __restrict__ size, int64_t n_rows, uint8_t* __restrict__ bin_of, int32_t* __restrict__ rows,
-                     unsigned long long* __restrict__ bin_count) {
+classify_rows_kernel(const int64_t* __restrict__ size, int64_t n_rows, int n_exact_bins, uint8_t* __restrict__ bin_of,
+                     int32_t* __restrict__ rows, unsigned long long* __restrict__ bin_count) {
   __shared__ unsigned int s_count[kNumBins + 1];
   if (threadIdx.x <= kNumBins) s_count[threadIdx.x] = 0;
   __syncthreads();
@@ -281,7 +294,7 @@ classify_rows_kernel(const int64_t* __restrict__ size, int64_t n_rows, uint8_t* 
     int b = kNumBins;  // empty rows sort last and are never launched
     if (u > 0) {
       b = kNumBins - 1;  // long rows
-      for (int q = 0; q < kNumBins - 1; ++q)
+      for (int q = 0; q < n_exact_bins; ++q)
         if (2 * u <= (int64_t)bin_cap(q)) {
           b = q;
           break;
@@ -315,14 +328,14 @@ struct IsMinusOne {
   __device__ bool operator()(const int32_t& i) const { return v[i] == -1; }
 };
 
-// rows grouped by bin: sorted_rows holds the row ids ordered by bin, h_count the rows per bin
+// rows grouped by bin: sorted_rows holds the row ids ordered by bin
 struct RowBins {
   DevBuf<int32_t> sorted_rows;
   int64_t count[kNumBins + 1] = {0};
   int64_t offset[kNumBins + 1] = {0};
 };
 
-static void bin_rows(const int64_t* size, int64_t m, cudaStream_t s, RowBins& rb) {
+static void bin_rows(const int64_t* size, int64_t m, int n_exact_bins, cudaStream_t s, RowBins& rb) {
   DevBuf<uint8_t> bin_of, bin_sorted;
   DevBuf<int32_t> rows;
   DevBuf<unsigned long long> counts;
@@ -332,7 +345,7 @@ static void bin_rows(const int64_t* size, int64_t m, cudaStream_t s, RowBins& rb
   rb.sorted_rows.alloc(m, s);
   counts.alloc(kNumBins + 1, s);
   FXII_CUDA(cudaMemsetAsync(counts.p, 0, sizeof(unsigned long long) * (kNumBins + 1), s));
-  { classify_rows_kernel<<<grid_for(m, 256, 8), 256, 0, s>>>(size, m, bin_of.p, rows.p, counts.p); FXII_LAUNCHED(1); }
+  { classify_rows_kernel<<<grid_for(m, 256, 8), 256, 0, s>>>(size, m, n_exact_bins, bin_of.p, rows.p, counts.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
   size_t tb = 0;
   FXII_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, bin_of.p, bin_sorted.p, rows.p, rb.sorted_rows.p, m, 0, 3, s));
@@ -357,6 +370,7 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
   FXII_CHECK(row_begin >= 0 && row_begin <= row_end && row_end <= a->n_rows, "spgemm: bad row window");
   const int64_t m = row_end - row_begin;
   FXII_CHECK(m < ((int64_t)1 << 31), "spgemm: row window must fit int32");
+  Trace tr("spgemm", s);
   out->n_rows = m;
   out->n_cols = b->n_cols;
   DevBuf<int64_t> ub, row_nnz;
@@ -384,105 +398,125 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
   }
   int64_t h_ip = 0;
   FXII_CUDA(cudaMemcpyAsync(&h_ip, ip_dev.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-
   DevBuf<int> overflow;
   overflow.alloc(1, s);
-  FXII_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
-  // one phase: launch every non-empty bin
-  // force_global: recount of the symbolic rows that overflowed the largest shared table
-  auto run_phase = [&](bool numeric, const int64_t* size, RowBins& rb, const int32_t* force_list, int64_t force_n) {
-    for (int bin = force_list ? kNumBins - 1 : 0; bin < kNumBins; ++bin) {
-      const int64_t nl = force_list ? force_n : rb.count[bin];
-      if (nl == 0) continue;
-      const int32_t* list = force_list ? force_list : rb.sorted_rows.p + rb.offset[bin];
-      // long rows: the symbolic phase counts them in a 32768-slot shared table (a row of C with more
-      // than 16384 distinct columns is reported as unsupported); the numeric phase, which knows nnz,
-      // uses exact-size tables in global memory
-      const bool global = (numeric || force_list) && bin == kNumBins - 1;
-      const bool block = bin >= 3;
-      const uint32_t cap = global ? 0 : bin_cap(bin);
-      const int overflow_limit = (!numeric && !force_list && bin == kNumBins - 1) ? 16384 : 0;
-      const int threads = block ? (bin >= 4 ? 256 : 128) : 256;
-      const int groups = block ? 1 : threads / 32;
-      const size_t smem = global ? 0 : (size_t)cap * (numeric ? 16 : 4) * groups;
-      const int grid = (int)std::min<int64_t>((nl + groups - 1) / groups, (int64_t)num_sms() * 16);
-      DevBuf<int64_t> g_sizes, g_off;
-      DevBuf<int32_t> g_keys;
-      DevBuf<double> g_vals;
-      DevBuf<uint64_t> g_sort;
-      if (global) {
-        g_sizes.alloc(nl + 1, s);
-        g_off.alloc(nl + 1, s);
-        { global_table_sizes_kernel<<<grid_for(nl + 1, 256, 8), 256, 0, s>>>(list, nl, size, b->n_cols, g_sizes.p); FXII_LAUNCHED(1); }
-        exclusive_scan_i64((const long long*)g_sizes.p, (long long*)g_off.p, nl + 1, s);
-        int64_t total = 0;
-        FXII_CUDA(cudaMemcpyAsync(&total, g_off.p + nl, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-        FXII_CUDA(cudaStreamSynchronize(s));
-        FXII_CHECK(total < ((int64_t)1 << 33), "spgemm: rows too long for the global-table fallback (shard the product)");
-        g_keys.alloc(total, s);
-        if (numeric) {
-          g_vals.alloc(total, s);
-          g_sort.alloc(total / 2 + 1, s);
-        }
+
+  // launch one kernel over a row list.  cap == 0: global-memory tables of 2*min(size, n_cols) slots.
+  auto launch = [&](bool numeric, const int32_t* list, int64_t nl, uint32_t cap, bool block, int threads, int overflow_limit,
+                    const int64_t* size, int32_t* c_idx, double* c_val) {
+    if (nl == 0) return;
+    const bool global = cap == 0;
+    const int groups = block ? 1 : threads / 32;
+    const size_t smem = global ? 0 : (size_t)cap * (numeric ? 16 : 4) * groups;
+    const int grid = (int)std::min<int64_t>((nl + groups - 1) / groups, (int64_t)num_sms() * 16);
+    DevBuf<int64_t> g_sizes, g_off;
+    DevBuf<int32_t> g_keys;
+    DevBuf<double> g_vals;
+    DevBuf<uint64_t> g_sort;
+    if (global) {
+      g_sizes.alloc(nl + 1, s);
+      g_off.alloc(nl + 1, s);
+      { global_table_sizes_kernel<<<grid_for(nl + 1, 256, 8), 256, 0, s>>>(list, nl, size, b->n_cols, g_sizes.p); FXII_LAUNCHED(1); }
+      exclusive_scan_i64((const long long*)g_sizes.p, (long long*)g_off.p, nl + 1, s);
+      int64_t total = 0;
+      FXII_CUDA(cudaMemcpyAsync(&total, g_off.p + nl, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+      FXII_CUDA(cudaStreamSynchronize(s));
+      FXII_CHECK(total < ((int64_t)1 << 33), "spgemm: rows too long for the global-table fallback (shard the product)");
+      g_keys.alloc(total, s);
+      if (numeric) {
+        g_vals.alloc(total, s);
+        g_sort.alloc(total / 2 + 1, s);
       }
+    }
 #define FXII_SPGEMM_LAUNCH(BLK, NUM)                                                                                  \
   do {                                                                                                                \
-    if (smem > 48 * 1024)                                                                                             \
+    if (smem + 1024 > 48 * 1024)                                                                                      \
       FXII_CUDA(cudaFuncSetAttribute(spgemm_rows_kernel<BLK, NUM>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                      (int)smem));                                                                     \
     spgemm_rows_kernel<BLK, NUM><<<grid, threads, smem, s>>>(                                                         \
         a->indptr.p, a->indices.p, a->values.p, b->indptr.p, b->indices.p, b->values.p, row_begin, list, nl, cap,     \
-        overflow_limit, overflow.p, global ? g_keys.p : nullptr, global ? g_vals.p : nullptr, global ? g_sort.p : nullptr,                        \
-        global ? g_off.p : nullptr, row_nnz.p, out->indptr.p, out->indices.p, out->values.p);                         \
+        overflow_limit, overflow.p, global ? g_keys.p : nullptr, global ? g_vals.p : nullptr,                         \
+        global ? g_sort.p : nullptr, global ? g_off.p : nullptr, row_nnz.p, out->indptr.p, c_idx, c_val);                                          \
     FXII_CUDA(cudaGetLastError());                                                                                    \
     FXII_LAUNCHED(1);                                                                                                 \
   } while (0)
-      if (block && numeric) FXII_SPGEMM_LAUNCH(true, true);
-      else if (block && !numeric) FXII_SPGEMM_LAUNCH(true, false);
-      else if (!block && numeric) FXII_SPGEMM_LAUNCH(false, true);
-      else FXII_SPGEMM_LAUNCH(false, false);
+    if (block && numeric) FXII_SPGEMM_LAUNCH(true, true);
+    else if (block && !numeric) FXII_SPGEMM_LAUNCH(true, false);
+    else if (!block && numeric) FXII_SPGEMM_LAUNCH(false, true);
+    else FXII_SPGEMM_LAUNCH(false, false);
 #undef FXII_SPGEMM_LAUNCH
-      if (global) FXII_CUDA(cudaStreamSynchronize(s));  // tables are freed when this scope ends
-    }
+    if (global) FXII_CUDA(cudaStreamSynchronize(s));  // tables are freed when this scope ends
   };
 
-  RowBins sym;
-  bin_rows(ub.p, m, s, sym);  // synchronises: h_ip is valid from here on
-  if (ip_out) *ip_out = h_ip;
-  run_phase(false, ub.p, sym, nullptr, 0);
-  exclusive_scan_i64((const long long*)row_nnz.p, (long long*)out->indptr.p, m + 1, s);
-  int64_t nnz = 0;
-  int h_overflow = 0;
-  FXII_CUDA(cudaMemcpyAsync(&nnz, out->indptr.p + m, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-  FXII_CUDA(cudaMemcpyAsync(&h_overflow, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-  RowBins num;
-  bin_rows(row_nnz.p, m, s, num);  // synchronises
-  if (h_overflow) {
-    // rare: rows with more than 16384 distinct columns are recounted in global-memory tables
-    DevBuf<int32_t> iota, over;
-    DevBuf<int64_t> n_over;
-    iota.alloc(m, s);
-    over.alloc(m, s);
-    n_over.alloc(1, s);
-    { iota32_kernel<<<grid_for(m, 256, 8), 256, 0, s>>>(iota.p, m); FXII_LAUNCHED(1); }
+  // rows whose count came back as -1 (table overflow) -> list
+  DevBuf<int32_t> iota, retry;
+  DevBuf<int64_t> n_retry;
+  auto select_overflowed = [&]() -> int64_t {
+    int h_over = 0;
+    FXII_CUDA(cudaMemcpyAsync(&h_over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    FXII_CUDA(cudaStreamSynchronize(s));
+    if (!h_over) return 0;
+    if (!iota.p) {
+      iota.alloc(m, s);
+      retry.alloc(m, s);
+      n_retry.alloc(1, s);
+      { iota32_kernel<<<grid_for(m, 256, 8), 256, 0, s>>>(iota.p, m); FXII_LAUNCHED(1); }
+    }
     IsMinusOne pred{row_nnz.p};
     size_t tb = 0;
-    FXII_CUDA(cub::DeviceSelect::If(nullptr, tb, iota.p, over.p, n_over.p, m, pred, s));
+    FXII_CUDA(cub::DeviceSelect::If(nullptr, tb, iota.p, retry.p, n_retry.p, m, pred, s));
     DevBuf<uint8_t> tmp;
     tmp.alloc((int64_t)tb, s);
-    FXII_CUDA(cub::DeviceSelect::If(tmp.p, tb, iota.p, over.p, n_over.p, m, pred, s));
+    FXII_CUDA(cub::DeviceSelect::If(tmp.p, tb, iota.p, retry.p, n_retry.p, m, pred, s));
     int64_t h_n = 0;
-    FXII_CUDA(cudaMemcpyAsync(&h_n, n_over.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    FXII_CUDA(cudaMemcpyAsync(&h_n, n_retry.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    FXII_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
     FXII_CUDA(cudaStreamSynchronize(s));
-    run_phase(false, ub.p, sym, over.p, h_n);
-    exclusive_scan_i64((const long long*)row_nnz.p, (long long*)out->indptr.p, m + 1, s);
-    FXII_CUDA(cudaMemcpyAsync(&nnz, out->indptr.p + m, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    bin_rows(row_nnz.p, m, s, num);
+    return h_n;
+  };
+
+  tr.mark("ub + alloc");
+  // ---- symbolic --------------------------------------------------------------------------------
+  RowBins sym;
+  bin_rows(ub.p, m, 3, s, sym);  // exact bins 0..2 (ub <= 512); synchronises, so h_ip is valid
+  tr.mark("bin rows (symbolic)");
+  if (ip_out) *ip_out = h_ip;
+  FXII_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
+  for (int bin = 0; bin < 3; ++bin)
+    launch(false, sym.sorted_rows.p + sym.offset[bin], sym.count[bin], bin_cap(bin), false, 256, 0, ub.p, nullptr, nullptr);
+  tr.mark("symbolic exact bins");
+  const int64_t n_long = sym.count[kNumBins - 1];
+  if (n_long > 0) {
+    // first attempt: 2048-slot warp tables, rows with more than 1536 distinct columns retry
+    launch(false, sym.sorted_rows.p + sym.offset[kNumBins - 1], n_long, 2048, false, 256, 1536, ub.p, nullptr, nullptr);
+    int64_t n2 = select_overflowed();
+    if (n2 > 0) {
+      launch(false, retry.p, n2, 32768, true, 256, 16384, ub.p, nullptr, nullptr);
+      const int64_t n3 = select_overflowed();
+      if (n3 > 0) launch(false, retry.p, n3, 0, true, 256, 0, ub.p, nullptr, nullptr);
+    }
   }
+  tr.mark("symbolic long rows");
+  exclusive_scan_i64((const long long*)row_nnz.p, (long long*)out->indptr.p, m + 1, s);
+  int64_t nnz = 0;
+  FXII_CUDA(cudaMemcpyAsync(&nnz, out->indptr.p + m, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  // ---- numeric ---------------------------------------------------------------------------------
+  RowBins num;
+  bin_rows(row_nnz.p, m, 5, s, num);  // synchronises
   out->nnz = nnz;
   out->indices.alloc(nnz, s);
   out->values.alloc(nnz, s);
-  if (nnz > 0) run_phase(true, row_nnz.p, num, nullptr, 0);
+  if (nnz == 0) return;
+  tr.mark("bin rows (numeric) + alloc");
+  for (int bin = 0; bin < kNumBins; ++bin) {
+    const int32_t* list = num.sorted_rows.p + num.offset[bin];
+    if (bin <= 1) launch(true, list, num.count[bin], bin_cap(bin), false, 256, 0, row_nnz.p, out->indices.p, out->values.p);
+    else if (bin == 2) launch(true, list, num.count[bin], bin_cap(bin), false, 128, 0, row_nnz.p, out->indices.p, out->values.p);
+    else if (bin == 3) launch(true, list, num.count[bin], bin_cap(bin), true, 128, 0, row_nnz.p, out->indices.p, out->values.p);
+    else if (bin == 4) launch(true, list, num.count[bin], bin_cap(bin), true, 256, 0, row_nnz.p, out->indices.p, out->values.p);
+    else launch(true, list, num.count[bin], 0, true, 256, 0, row_nnz.p, out->indices.p, out->values.p);
+  }
+  tr.mark("numeric");
 }
 
 // ---- row scaling, SpMV --------------------------------------------------------------------------

@@ -59,6 +59,8 @@ int fxii_set_device(int device);
 int fxii_sm_count(int* n);
 /* number of kernels of THIS library launched so far by the calling process (CUB launches excluded) */
 int64_t fxii_launch_count(void);
+/* the library caches freed device blocks for reuse; this returns them to the driver */
+int fxii_trim_memory(void);
 
 /* ---- Ω mesh (affine tetrahedra) ---------------------------------------------------------- */
 /* x: [n_nodes,3] f64, cell_nodes: [n_cells,4] i32 (mesh.geometry.x / mesh.geometry.dofmap).
