@@ -179,7 +179,7 @@ int fxii_mesh_info(const fxii_mesh* m, int64_t* n_cells, int64_t* n_nodes, int64
     FXII_CHECK(m, "null mesh");
     if (n_cells) *n_cells = m->n_cells;
     if (n_nodes) *n_nodes = m->n_nodes;
-    if (device_bytes) *device_bytes = m->x.bytes() + m->cell_nodes.bytes() + m->cellgeo.bytes() + m->nodes.bytes();
+    if (device_bytes) *device_bytes = m->x.bytes() + m->cell_nodes.bytes() + m->cellgeo.bytes() + m->wnodes.bytes();
     if (max_depth) *max_depth = m->max_depth;
   });
 }

@@ -114,6 +114,22 @@ struct alignas(16) BvhNode {  // 64 B: both child boxes live in the parent
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
 
+// 4-wide node, 64 B: the four grandchildren of a binary LBVH node with boxes quantised to 16 bits on
+// the scene grid (rounded outward).  lo[a][k] / hi[a][k]: axis a, slots (2k, 2k+1) packed as two
+// halfwords.  child >= 0: wide node index; child < 0: leaf, cell = ~child.  Empty slot: lo > hi.
+struct alignas(16) WideNode {
+  uint32_t lo[3][2];
+  uint32_t hi[3][2];
+  int32_t child[4];
+};
+static_assert(sizeof(WideNode) == 64, "WideNode must be 64 bytes");
+
+// scene grid of the quantised boxes: q(x) = floor((x - origin) * scale), clamped to [0, 65535]
+struct SceneGrid {
+  double origin[3];
+  double scale[3];
+};
+
 // ---- device helpers shared by the row kernels -----------------------------------------------------
 #ifdef __CUDACC__
 // bitonic sort of cap (power of two) 64-bit keys in shared memory by `nthreads` cooperating threads
@@ -152,7 +168,8 @@ struct fxii_mesh {
   fxii::DevBuf<double> x;            // [n_nodes,3]
   fxii::DevBuf<int32_t> cell_nodes;  // [n_cells,4]
   fxii::DevBuf<double> cellgeo;      // [n_cells,12]: v0 (3) + K=J^{-1} row-major (9), 96 B per cell
-  fxii::DevBuf<fxii::BvhNode> nodes; // [max(n_cells-1,1)]
+  fxii::DevBuf<fxii::WideNode> wnodes; // [max(n_cells-1,1)], indexed like the binary LBVH nodes
+  fxii::SceneGrid grid;
   int32_t root = 0;
   int32_t max_depth = 0;
 };

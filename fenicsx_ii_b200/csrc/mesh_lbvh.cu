@@ -7,8 +7,11 @@
 //   cub radix sort    : (key, cell)
 //   karras_internal   : 1 thread / internal node (Karras 2012), index tie-break on equal keys
 //   refit             : 1 thread / leaf climbing with atomic arrival flags; every parent stores
-//                       BOTH child boxes (fp32, rounded outward, padded) so one 64 B node
-//                       fetch decides both children during traversal
+//                       BOTH child boxes (fp32, rounded outward, padded)
+//   collapse_wide     : 1 thread / binary node: its four grandchildren with 16-bit boxes on the
+//                       scene grid become one 64 B wide node — half the levels and half the bytes
+//                       per level of the binary tree (the traversal is bound by the L1 data pipe
+//                       and by the length of its dependent-load chain)
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -239,6 +242,75 @@ refit_kernel(const double* __restrict__ x, const int4* __restrict__ cell_nodes, 
   }
 }
 
+
+// ---- 4-wide collapse --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t quant(double v, double origin, double scale) {
+  const double q = floor((v - origin) * scale);  // monotone in v: conservative for lo and hi alike
+  return (uint32_t)fmin(fmax(q, 0.0), 65535.0);
+}
+
+struct Slot {
+  uint32_t lo[3], hi[3];
+  int32_t child;
+};
+
+__device__ __forceinline__ Slot make_slot(const float* lo, const float* hi, int32_t child, const SceneGrid& g) {
+  Slot s;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    s.lo[a] = quant((double)lo[a], g.origin[a], g.scale[a]);
+    s.hi[a] = quant((double)hi[a], g.origin[a], g.scale[a]);
+  }
+  s.child = child;
+  return s;
+}
+
+// Wide node i = the grandchildren of binary node i (a leaf child fills one slot itself).  Traversal
+// starts at node 0 and only ever follows wide-node children, i.e. every second binary level.
+__global__ void __launch_bounds__(256)
+collapse_wide_kernel(const BvhNode* __restrict__ nodes, int n_internal, SceneGrid grid, WideNode* __restrict__ wide) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_internal; i += gridDim.x * blockDim.x) {
+    const BvhNode b = nodes[i];
+    Slot slots[4];
+    int ns = 0;
+    const int kids[2] = {b.left, b.right};
+    const float* klo[2] = {b.lo_l, b.lo_r};
+    const float* khi[2] = {b.hi_l, b.hi_r};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (klo[k][0] > khi[k][0]) continue;  // empty box (single-cell mesh)
+      if (kids[k] < 0) {
+        slots[ns++] = make_slot(klo[k], khi[k], kids[k], grid);
+      } else {
+        const BvhNode c = nodes[kids[k]];
+        slots[ns++] = make_slot(c.lo_l, c.hi_l, c.left, grid);
+        slots[ns++] = make_slot(c.lo_r, c.hi_r, c.right, grid);
+      }
+    }
+    WideNode w;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k >= ns) {  // empty slot: lo > hi on every axis
+        slots[k].child = -1;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          slots[k].lo[a] = 65535u;
+          slots[k].hi[a] = 0u;
+        }
+      }
+      w.child[k] = slots[k].child;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      w.lo[a][0] = slots[0].lo[a] | (slots[1].lo[a] << 16);
+      w.lo[a][1] = slots[2].lo[a] | (slots[3].lo[a] << 16);
+      w.hi[a][0] = slots[0].hi[a] | (slots[1].hi[a] << 16);
+      w.hi[a][1] = slots[2].hi[a] | (slots[3].hi[a] << 16);
+    }
+    wide[i] = w;
+  }
+}
+
 }  // namespace fxii
 
 using namespace fxii;
@@ -277,6 +349,24 @@ depth_kernel(const BvhNode* __restrict__ nodes, const int32_t* __restrict__ leaf
   if ((threadIdx.x & 31) == 0 && local > 0) atomicMax(max_depth, local);
 }
 
+// scene grid from the node bounds (widened by the padding and one part in 10^6) and the wide collapse
+static void finish_wide(fxii_mesh* m, DevBuf<BvhNode>& bnodes, DevBuf<unsigned long long>& bounds, int n_internal,
+                        cudaStream_t s) {
+  unsigned long long hb[6];
+  FXII_CUDA(cudaMemcpyAsync(hb, bounds.p, sizeof(hb), cudaMemcpyDeviceToHost, s));
+  FXII_CUDA(cudaStreamSynchronize(s));
+  for (int a = 0; a < 3; ++a) {
+    const double lo = dec_ordered(hb[a]), hi = dec_ordered(hb[3 + a]);
+    const double ext = (hi - lo) + 2.0 * m->padding;
+    const double margin = m->padding + 1e-6 * ext + 1e-300;
+    m->grid.origin[a] = lo - margin;
+    m->grid.scale[a] = 65535.0 / (ext + 2.0 * margin);
+  }
+  { collapse_wide_kernel<<<grid_for(n_internal, 256, 8), 256, 0, s>>>(bnodes.p, n_internal, m->grid, m->wnodes.p); FXII_LAUNCHED(1); }
+  FXII_CUDA(cudaGetLastError());
+  FXII_CUDA(cudaStreamSynchronize(s));
+}
+
 void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* cell_nodes, int64_t n_cells,
                 double padding, cudaStream_t s) {
   init_pool_once();
@@ -290,8 +380,10 @@ void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* c
   m->cellgeo.alloc(12 * n_cells, s);
   const int n = (int)n_cells;
   const int n_internal = n > 1 ? n - 1 : 1;
-  m->nodes.alloc(n_internal, s);
-  FXII_CUDA(cudaMemsetAsync(m->nodes.p, 0, sizeof(BvhNode) * (size_t)n_internal, s));
+  DevBuf<BvhNode> bnodes;  // binary LBVH, only needed until the wide collapse
+  bnodes.alloc(n_internal, s);
+  m->wnodes.alloc(n_internal, s);
+  FXII_CUDA(cudaMemsetAsync(bnodes.p, 0, sizeof(BvhNode) * (size_t)n_internal, s));
 
   DevBuf<unsigned long long> bounds;
   bounds.alloc(6, s);
@@ -334,25 +426,26 @@ void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* c
     root.left = ~0;
     root.right = ~0;
     root.parent = -1;
-    FXII_CUDA(cudaMemcpyAsync(m->nodes.p, &root, sizeof(root), cudaMemcpyHostToDevice, s));
+    FXII_CUDA(cudaMemcpyAsync(bnodes.p, &root, sizeof(root), cudaMemcpyHostToDevice, s));
     m->max_depth = 1;
-    FXII_CUDA(cudaStreamSynchronize(s));
+    finish_wide(m, bnodes, bounds, n_internal, s);
     return;
   }
   FXII_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int32_t) * (size_t)n_internal, s));
-  { karras_internal_kernel<<<grid_for(n - 1, 256, 8), 256, 0, s>>>(keys_sorted.p, ids_sorted.p, n, m->nodes.p, leaf_parent.p); FXII_LAUNCHED(1); }
+  { karras_internal_kernel<<<grid_for(n - 1, 256, 8), 256, 0, s>>>(keys_sorted.p, ids_sorted.p, n, bnodes.p, leaf_parent.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
   { refit_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(m->x.p, reinterpret_cast<const int4*>(m->cell_nodes.p), ids_sorted.p,
-                                                   leaf_parent.p, n, padding, m->nodes.p, flags.p); FXII_LAUNCHED(1); }
+                                                   leaf_parent.p, n, padding, bnodes.p, flags.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
   DevBuf<int32_t> depth;
   depth.alloc(1, s);
   FXII_CUDA(cudaMemsetAsync(depth.p, 0, sizeof(int32_t), s));
-  { depth_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(m->nodes.p, leaf_parent.p, n, depth.p); FXII_LAUNCHED(1); }
+  { depth_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(bnodes.p, leaf_parent.p, n, depth.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
   int32_t h = 0;
   FXII_CUDA(cudaMemcpyAsync(&h, depth.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   FXII_CUDA(cudaStreamSynchronize(s));
   m->max_depth = h;
+  finish_wide(m, bnodes, bounds, n_internal, s);
 }
 }  // namespace fxii

@@ -209,90 +209,185 @@ struct LocateResult {
   bool fallback;
 };
 
-// Full traversal (no early exit): every leaf whose fp32 box contains the point is tested and the
-// LOWEST colliding cell index wins, independent of tree shape (north_star tie-break).
-__device__ LocateResult locate_point(const BvhNode* __restrict__ nodes, const double* __restrict__ cellgeo,
-                                     const double* __restrict__ x, const int4* __restrict__ cell_nodes,
-                                     double padding, const double* p) {
-  const float plo[3] = {__double2float_rd(p[0]), __double2float_rd(p[1]), __double2float_rd(p[2])};
-  const float phi[3] = {__double2float_ru(p[0]), __double2float_ru(p[1]), __double2float_ru(p[2])};
-  int stack[kStack];
-  int sp = 0;
-  int node = 0;
-  int best = 0x7fffffff, ncoll = 0;
-  int fb_cell = -1;
+struct LocateState {
+  int best = 0x7fffffff;  // lowest colliding cell so far
+  int ncoll = 0;
+  int fb_cell = -1;       // nearest non-colliding candidate (fallback)
   double fb_d2 = 1e300;
-  // 1.001: cells within 0.05% of the threshold still take the exact path
-  const double tau2 = fmax(kCollisionD2, padding * padding) * 1.001;
-  while (true) {
-    const float4* nf = reinterpret_cast<const float4*>(nodes + node);
-    const float4 q0 = __ldg(nf), q1 = __ldg(nf + 1), q2 = __ldg(nf + 2);
-    const int4 ch = __ldg(reinterpret_cast<const int4*>(nf + 3));
-    // q0 = lo_l.xyz hi_l.x ; q1 = hi_l.yz lo_r.xy ; q2 = lo_r.z hi_r.xyz
-    const bool hit_l = q0.x <= phi[0] && q0.y <= phi[1] && q0.z <= phi[2] && q0.w >= plo[0] && q1.x >= plo[1] && q1.y >= plo[2];
-    const bool hit_r = q1.z <= phi[0] && q1.w <= phi[1] && q2.x <= phi[2] && q2.y >= plo[0] && q2.z >= plo[1] && q2.w >= plo[2];
-    int next = -1;
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-      const bool hit = side == 0 ? hit_l : hit_r;
-      const int child = side == 0 ? ch.x : ch.y;
-      if (!hit) continue;
-      if (child >= 0) {
-        if (next < 0) next = child;
-        else if (sp < kStack) stack[sp++] = child;
-      } else {
-        const int cell = ~child;
-        CellGeo g;
-        load_cellgeo(cellgeo, cell, g);
-        double X[3];
-        pull_back(g, p, X);
-        const double l0 = ((1.0 - X[0]) - X[1]) - X[2];
-        if (l0 >= 0 && X[0] >= 0 && X[1] >= 0 && X[2] >= 0) {
-          best = min(best, cell);
-          ++ncoll;
-        } else {
-          // Quick reject without touching the vertices: the distance to the tetrahedron is at least
-          // the distance to the plane of any face the point is outside of, -lambda_i / |grad lambda_i|
-          // (grad lambda_1..3 = rows of K, grad lambda_0 = -(row0+row1+row2)).  Cells farther than
-          // tau = max(collision distance, padding) can neither collide nor serve as fallback.
-          const double s0 = (g.K[0] + g.K[3]) + g.K[6], s1 = (g.K[1] + g.K[4]) + g.K[7], s2 = (g.K[2] + g.K[5]) + g.K[8];
-          bool far = (l0 < 0) && (l0 * l0 > tau2 * ((s0 * s0 + s1 * s1) + s2 * s2));
-          far = far || ((X[0] < 0) && (X[0] * X[0] > tau2 * ((g.K[0] * g.K[0] + g.K[1] * g.K[1]) + g.K[2] * g.K[2])));
-          far = far || ((X[1] < 0) && (X[1] * X[1] > tau2 * ((g.K[3] * g.K[3] + g.K[4] * g.K[4]) + g.K[5] * g.K[5])));
-          far = far || ((X[2] < 0) && (X[2] * X[2] > tau2 * ((g.K[6] * g.K[6] + g.K[7] * g.K[7]) + g.K[8] * g.K[8])));
-          double d2;
-          if (!far && cell_distance2(x, cell_nodes, cell, p, padding, d2)) {
-            if (d2 < kCollisionD2) {
-              best = min(best, cell);
-              ++ncoll;
-            } else if (d2 < fb_d2 || (d2 == fb_d2 && cell < fb_cell)) {
-              fb_d2 = d2;
-              fb_cell = cell;
-            }
-          }
-        }
-      }
-    }
-    if (next >= 0) {
-      node = next;
-    } else if (sp > 0) {
-      node = stack[--sp];
-    } else {
-      break;
+};
+
+// Leaf test of one candidate cell (dolfinx compute_first_colliding_cell semantics).
+__device__ __forceinline__ void test_cell(const double* __restrict__ cellgeo, const double* __restrict__ x,
+                                          const int4* __restrict__ cell_nodes, double padding, double tau2, int cell,
+                                          const double* p, LocateState& st) {
+  CellGeo g;
+  load_cellgeo(cellgeo, cell, g);
+  double X[3];
+  pull_back(g, p, X);
+  const double l0 = ((1.0 - X[0]) - X[1]) - X[2];
+  if (l0 >= 0 && X[0] >= 0 && X[1] >= 0 && X[2] >= 0) {
+    st.best = min(st.best, cell);
+    ++st.ncoll;
+    return;
+  }
+  // Quick reject without touching the vertices: the distance to the tetrahedron is at least the
+  // distance to the plane of any face the point is outside of, -lambda_i / |grad lambda_i|
+  // (grad lambda_1..3 = rows of K, grad lambda_0 = -(row0+row1+row2)).  Cells farther than
+  // tau = max(collision distance, padding) can neither collide nor serve as fallback.
+  const double s0 = (g.K[0] + g.K[3]) + g.K[6], s1 = (g.K[1] + g.K[4]) + g.K[7], s2 = (g.K[2] + g.K[5]) + g.K[8];
+  bool far = (l0 < 0) && (l0 * l0 > tau2 * ((s0 * s0 + s1 * s1) + s2 * s2));
+  far = far || ((X[0] < 0) && (X[0] * X[0] > tau2 * ((g.K[0] * g.K[0] + g.K[1] * g.K[1]) + g.K[2] * g.K[2])));
+  far = far || ((X[1] < 0) && (X[1] * X[1] > tau2 * ((g.K[3] * g.K[3] + g.K[4] * g.K[4]) + g.K[5] * g.K[5])));
+  far = far || ((X[2] < 0) && (X[2] * X[2] > tau2 * ((g.K[6] * g.K[6] + g.K[7] * g.K[7]) + g.K[8] * g.K[8])));
+  double d2;
+  if (!far && cell_distance2(x, cell_nodes, cell, p, padding, d2)) {
+    if (d2 < kCollisionD2) {
+      st.best = min(st.best, cell);
+      ++st.ncoll;
+    } else if (d2 < st.fb_d2 || (d2 == st.fb_d2 && cell < st.fb_cell)) {
+      st.fb_d2 = d2;
+      st.fb_cell = cell;
     }
   }
+}
+
+__device__ __forceinline__ LocateResult finish_locate(const LocateState& st, double padding) {
   LocateResult r;
-  r.ncoll = ncoll;
+  r.ncoll = st.ncoll;
   r.fallback = false;
-  if (best != 0x7fffffff) {
-    r.cell = best;
-  } else if (fb_cell >= 0 && fb_d2 <= padding * padding) {
-    r.cell = fb_cell;
+  if (st.best != 0x7fffffff) {
+    r.cell = st.best;
+  } else if (st.fb_cell >= 0 && st.fb_d2 <= padding * padding) {
+    r.cell = st.fb_cell;
     r.fallback = true;
   } else {
     r.cell = -1;
   }
   return r;
+}
+
+// The point on the scene grid of the quantised boxes, each coordinate replicated in both halfwords
+// for the two-slot SIMD compares.  q() is the same monotone map the builder applied to the box
+// corners, so a point inside a (fp32, outward-rounded) box is always inside its quantised box.
+struct QPoint {
+  uint32_t x2, y2, z2;
+};
+__device__ __forceinline__ QPoint quantise_point(const SceneGrid& g, const double* p, bool active) {
+  QPoint q;
+  uint32_t v[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) v[a] = (uint32_t)fmin(fmax(floor((p[a] - g.origin[a]) * g.scale[a]), 0.0), 65535.0);
+  q.x2 = v[0] | (v[0] << 16);
+  q.y2 = v[1] | (v[1] << 16);
+  q.z2 = v[2] | (v[2] << 16);
+  (void)active;
+  return q;
+}
+
+// one 64 B wide node: hit flags of its four slots
+struct WideHit {
+  int4 child;
+  uint32_t m01, m23;  // halfword masks: slots (0,1) and (2,3)
+};
+__device__ __forceinline__ WideHit load_test_node(const WideNode* __restrict__ nodes, int node, const QPoint& q) {
+  const uint4* wp = reinterpret_cast<const uint4*>(nodes + node);
+  // a = lo_x01 lo_x23 lo_y01 lo_y23 ; b = lo_z01 lo_z23 hi_x01 hi_x23 ; c = hi_y01 hi_y23 hi_z01 hi_z23
+  const uint4 a = __ldg(wp), b = __ldg(wp + 1), c = __ldg(wp + 2);
+  WideHit h;
+  h.child = __ldg(reinterpret_cast<const int4*>(wp + 3));
+  h.m01 = __vcmpleu2(a.x, q.x2) & __vcmpleu2(a.z, q.y2) & __vcmpleu2(b.x, q.z2) & __vcmpleu2(q.x2, b.z) &
+          __vcmpleu2(q.y2, c.x) & __vcmpleu2(q.z2, c.z);
+  h.m23 = __vcmpleu2(a.y, q.x2) & __vcmpleu2(a.w, q.y2) & __vcmpleu2(b.y, q.z2) & __vcmpleu2(q.x2, b.w) &
+          __vcmpleu2(q.y2, c.y) & __vcmpleu2(q.z2, c.w);
+  return h;
+}
+
+__device__ __forceinline__ void prefetch_l1(const void* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+
+// Per-thread traversal of the 4-wide tree (no early exit): every leaf whose box contains the point
+// is tested and the LOWEST colliding cell index wins, independent of tree shape (north_star
+// tie-break).
+__device__ LocateResult locate_point(const WideNode* __restrict__ nodes, const SceneGrid& grid,
+                                     const double* __restrict__ cellgeo, const double* __restrict__ x,
+                                     const int4* __restrict__ cell_nodes, double padding, const double* p) {
+  const QPoint q = quantise_point(grid, p, true);
+  // 1.001: cells within 0.05% of the threshold still take the exact path
+  const double tau2 = fmax(kCollisionD2, padding * padding) * 1.001;
+  int stack[kStack];
+  int sp = 0;
+  int node = 0;
+  LocateState st;
+  while (true) {
+    const WideHit h = load_test_node(nodes, node, q);
+    const int kids[4] = {h.child.x, h.child.y, h.child.z, h.child.w};
+    const bool hit[4] = {(h.m01 & 0xffffu) != 0, (h.m01 >> 16) != 0, (h.m23 & 0xffffu) != 0, (h.m23 >> 16) != 0};
+    // Memory-level parallelism: everything this node leads to is requested before anything is
+    // used — the hit children and the (up to four) candidate cells are otherwise a chain of
+    // dependent cold misses.
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!hit[k]) continue;
+      if (kids[k] >= 0) {
+        prefetch_l1(nodes + kids[k]);
+      } else {
+        const double* g = cellgeo + 12 * (int64_t)(~kids[k]);
+        prefetch_l1(g);
+        prefetch_l1(g + 11);
+      }
+    }
+    int next = -1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!hit[k]) continue;
+      if (kids[k] >= 0) {
+        if (next < 0) next = kids[k];
+        else if (sp < kStack) stack[sp++] = kids[k];
+      } else {
+        test_cell(cellgeo, x, cell_nodes, padding, tau2, ~kids[k], p, st);
+      }
+    }
+    if (next >= 0) node = next;
+    else if (sp > 0) node = stack[--sp];
+    else break;
+  }
+  return finish_locate(st, padding);
+}
+
+// Warp-cooperative (packet) traversal: the warp walks the UNION of its lanes' paths with one
+// warp-uniform stack; every node and candidate cell is fetched once per warp at a uniform address
+// and lanes vote with __ballot_sync on the children to descend into.  Results are identical to
+// locate_point.  All 32 lanes must call this (inactive lanes pass active=false).  Measured slower
+// than the per-thread walk on every BASELINE config (see packet_mode()).
+__device__ LocateResult locate_packet(const WideNode* __restrict__ nodes, const SceneGrid& grid,
+                                      const double* __restrict__ cellgeo, const double* __restrict__ x,
+                                      const int4* __restrict__ cell_nodes, double padding, const double* p, bool active) {
+  const QPoint q = quantise_point(grid, p, active);
+  const double tau2 = fmax(kCollisionD2, padding * padding) * 1.001;
+  int stack[kStack];  // warp-uniform contents
+  int sp = 0;
+  int node = 0;
+  LocateState st;
+  while (true) {
+    const WideHit h = load_test_node(nodes, node, q);  // uniform address: broadcast
+    const int kids[4] = {h.child.x, h.child.y, h.child.z, h.child.w};
+    const bool hit[4] = {active && (h.m01 & 0xffffu) != 0, active && (h.m01 >> 16) != 0, active && (h.m23 & 0xffffu) != 0,
+                         active && (h.m23 >> 16) != 0};
+    int next = -1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (__ballot_sync(0xffffffffu, hit[k]) == 0u) continue;  // no lane needs this child
+      if (kids[k] >= 0) {
+        if (next < 0) next = kids[k];
+        else if (sp < kStack) stack[sp++] = kids[k];
+      } else if (hit[k]) {
+        test_cell(cellgeo, x, cell_nodes, padding, tau2, ~kids[k], p, st);
+      }
+    }
+    if (next >= 0) node = next;
+    else if (sp > 0) node = stack[--sp];
+    else break;
+  }
+  return finish_locate(st, padding);
 }
 
 struct PiCounters {
@@ -377,12 +472,12 @@ __device__ __forceinline__ void load_cols(const int32_t* __restrict__ dofmap, in
 // One thread per 3D point p = r*nq + l (interpolation.py:57).  ND = dofs per V cell.
 template <int ND>
 __global__ void __launch_bounds__(128, 8)
-pi_locate_tabulate_kernel(const BvhNode* __restrict__ nodes, const double* __restrict__ cellgeo,
+pi_locate_tabulate_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const double* __restrict__ cellgeo,
                           const double* __restrict__ x, const int4* __restrict__ cell_nodes, double padding,
                           const int32_t* __restrict__ dofmap, const double* __restrict__ frames,
                           const double* __restrict__ table, const double* __restrict__ wq,
                           const double* __restrict__ pts_in, const double* __restrict__ w_in, const double* __restrict__ s_in,
-                          int kind, int nq, int64_t n_points, int32_t* __restrict__ out_cell,
+                          int kind, int nq, int packet, int64_t n_points, int32_t* __restrict__ out_cell,
                           uint8_t* __restrict__ out_ncoll, double* __restrict__ out_points,
                           int32_t* __restrict__ coo_cols, double* __restrict__ coo_vals, PiCounters* counters) {
   extern __shared__ double s_tab[];  // [nq*4]: xp (3) + w
@@ -395,13 +490,16 @@ pi_locate_tabulate_kernel(const BvhNode* __restrict__ nodes, const double* __res
     }
     __syncthreads();
   }
-  for (int64_t pidx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; pidx < n_points;
-       pidx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = pidx / nq;
-    const int l = (int)(pidx - r * nq);
-    double p[3], W, S;
-    make_point(kind, frames, s_tab, pts_in, w_in, s_in, r, l, pidx, p, W, S);
-    const LocateResult res = locate_point(nodes, cellgeo, x, cell_nodes, padding, p);
+  for (int64_t base = blockIdx.x * (int64_t)blockDim.x; base < n_points; base += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pidx = base + threadIdx.x;  // the loop is block-uniform: the packet traversal votes
+    const bool active = pidx < n_points;
+    const int64_t r = active ? pidx / nq : 0;
+    const int l = active ? (int)(pidx - r * nq) : 0;
+    double p[3] = {0.0, 0.0, 0.0}, W = 1.0, S = 1.0;
+    if (active) make_point(kind, frames, s_tab, pts_in, w_in, s_in, r, l, pidx, p, W, S);
+    const LocateResult res = packet ? locate_packet(nodes, grid, cellgeo, x, cell_nodes, padding, p, active)
+                                    : (active ? locate_point(nodes, grid, cellgeo, x, cell_nodes, padding, p) : LocateResult{-1, 0, false});
+    if (!active) continue;
     out_cell[pidx] = res.cell;
     out_ncoll[pidx] = (uint8_t)min(res.ncoll, 255);
     if (out_points) {
@@ -601,6 +699,18 @@ max_u64_kernel(const unsigned long long* __restrict__ a, int64_t n, unsigned lon
   if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
 
+// traversal flavour: per-thread walk by default.  FXII_TRAVERSAL=packet selects the warp-cooperative
+// packet traversal, which was measured 2-3x SLOWER on every BASELINE config (cfg2 0.107 vs 0.038 ms,
+// cfg5 38.7 vs 17.1 ms, cfg4 253 vs 120 ms): walking the union of 32 paths serialises their memory
+// latencies, while 32 independent walks overlap them.  Kept for workloads with identical paths.
+static int packet_mode() {
+  static const int mode = [] {
+    const char* e = getenv("FXII_TRAVERSAL");
+    return (e && std::string(e) == "packet") ? 1 : 0;
+  }();
+  return mode;
+}
+
 static float elapsed_ms(cudaEvent_t a, cudaEvent_t b) {
   float ms = 0.f;
   cudaEventElapsedTime(&ms, a, b);
@@ -778,11 +888,12 @@ __device__ __forceinline__ int team_prefix(bool flag, int team, int team_id, int
 
 template <int ND>
 __global__ void __launch_bounds__(256, 4)
-pi_fused_kernel(const BvhNode* __restrict__ nodes, const double* __restrict__ cellgeo, const double* __restrict__ x,
+pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const double* __restrict__ cellgeo,
+                const double* __restrict__ x,
                 const int4* __restrict__ cell_nodes, double padding, const int32_t* __restrict__ dofmap,
                 const double* __restrict__ frames, const double* __restrict__ table, const double* __restrict__ wq,
                 const double* __restrict__ pts_in, const double* __restrict__ w_in, const double* __restrict__ s_in,
-                int kind, int nq, int team, uint32_t scap, int64_t n_point_rows, int64_t n_rows_total,
+                int kind, int nq, int packet, int team, uint32_t scap, int64_t n_point_rows, int64_t n_rows_total,
                 const int32_t* __restrict__ row_dofs,
                 int32_t* __restrict__ out_cell, uint8_t* __restrict__ out_ncoll, double* __restrict__ out_points,
                 int32_t* __restrict__ stage_col, double* __restrict__ stage_val, int64_t* __restrict__ row_cnt,
@@ -823,23 +934,59 @@ pi_fused_kernel(const BvhNode* __restrict__ nodes, const double* __restrict__ ce
     double vals[ND];
 #pragma unroll
     for (int d = 0; d < ND; ++d) vals[d] = 0.0;
-    if (active) {
-      const int64_t pidx = r * nq + l;
-      double p[3], W, S;
-      make_point(kind, frames, s_tab, pts_in, w_in, s_in, r, l, pidx, p, W, S);
-      const LocateResult res = locate_point(nodes, cellgeo, x, cell_nodes, padding, p);
-      out_cell[pidx] = res.cell;
-      out_ncoll[pidx] = (uint8_t)min(res.ncoll, 255);
-      if (out_points) {
-        out_points[3 * pidx] = p[0];
-        out_points[3 * pidx + 1] = p[1];
-        out_points[3 * pidx + 2] = p[2];
+    {
+      const int64_t pidx = active ? r * nq + l : 0;
+      double p[3] = {0.0, 0.0, 0.0}, W = 1.0, S = 1.0;
+      if (active) make_point(kind, frames, s_tab, pts_in, w_in, s_in, r, l, pidx, p, W, S);
+      const LocateResult res = packet ? locate_packet(nodes, grid, cellgeo, x, cell_nodes, padding, p, active)
+                                      : (active ? locate_point(nodes, grid, cellgeo, x, cell_nodes, padding, p) : LocateResult{-1, 0, false});
+      if (active) {
+        out_cell[pidx] = res.cell;
+        out_ncoll[pidx] = (uint8_t)min(res.ncoll, 255);
+        if (out_points) {
+          out_points[3 * pidx] = p[0];
+          out_points[3 * pidx + 1] = p[1];
+          out_points[3 * pidx + 2] = p[2];
+        }
+        if (res.ncoll > 1) atomicAdd(&counters->ties, 1ULL);
+        if (res.fallback) atomicAdd(&counters->fallback, 1ULL);
+        cell = res.cell;
+        if (cell < 0) atomicAdd(&counters->not_found, 1ULL);
+        else tabulate_vals<ND>(cellgeo, cell, p, W, S, vals);
       }
-      if (res.ncoll > 1) atomicAdd(&counters->ties, 1ULL);
-      if (res.fallback) atomicAdd(&counters->fallback, 1ULL);
-      cell = res.cell;
-      if (cell < 0) atomicAdd(&counters->not_found, 1ULL);
-      else tabulate_vals<ND>(cellgeo, cell, p, W, S, vals);
+    }
+    if (team == 1) {
+      // one point per row (PointwiseTrace, mapped points): the row is the cell's nd (column, value)
+      // pairs — distinct columns — sorted by an odd-even transposition network in registers
+      if (in_team && r < n_point_rows) {
+        int32_t cols[ND];
+        int nrow = 0;
+        if (cell >= 0) {
+          load_cols<ND>(dofmap, cell, cols);
+#pragma unroll
+          for (int pass = 0; pass < ND; ++pass) {
+#pragma unroll
+            for (int i = pass & 1; i + 1 < ND; i += 2) {
+              if (cols[i] > cols[i + 1]) {
+                const int32_t tc = cols[i]; cols[i] = cols[i + 1]; cols[i + 1] = tc;
+                const double tv = vals[i]; vals[i] = vals[i + 1]; vals[i + 1] = tv;
+              }
+            }
+          }
+          const int64_t o = r * (int64_t)seg;
+#pragma unroll
+          for (int d = 0; d < ND; ++d) {
+            stage_col[o + d] = cols[d];
+            stage_val[o + d] = vals[d];
+          }
+          nrow = ND;
+        }
+        const int rho = row_dofs[r];
+        if (rho < 0 || rho >= n_rows_total) *conflict = 2;
+        else if (atomicCAS(&src_row[rho], -1, (int32_t)r) != -1) *conflict = 1;
+        else row_cnt[rho] = nrow;
+      }
+      continue;
     }
     s_cell[tid] = cell;
 #pragma unroll
@@ -993,13 +1140,13 @@ static bool pi_assemble_fused(const fxii_space* sp, fxii_rows* rows, cudaStream_
     static const char* env_carve = getenv("FXII_CARVEOUT");  // tuning knob: -1 keeps the driver default
     if (env_carve) carve = atoi(env_carve);
     if (carve >= 0) FXII_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-    int per_sm = 1;
-    FXII_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, B, smem));
-    if (per_sm < 1) per_sm = 1;
-    const int grid = (int)std::min<int64_t>(n_groups, (int64_t)num_sms() * per_sm);
+    // grid-stride over row groups: 2048 resident threads per SM at most, two waves of blocks so that
+    // the tail of slow row groups is shared out
+    const int grid = (int)std::min<int64_t>(n_groups, (int64_t)num_sms() * (2048 / B) * 2);
     const int4* cn = reinterpret_cast<const int4*>(m->cell_nodes.p);
-    kernel<<<grid, B, smem, s>>>(m->nodes.p, m->cellgeo.p, m->x.p, cn, m->padding, sp->dofmap.p, rows->frames.p,
-                                 rows->table.p, rows->w.p, rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, nq, team,
+    kernel<<<grid, B, smem, s>>>(m->wnodes.p, m->grid, m->cellgeo.p, m->x.p, cn, m->padding, sp->dofmap.p, rows->frames.p,
+                                 rows->table.p, rows->w.p, rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, nq,
+                                 (rows->kind != FXII_OP_POINTS) ? packet_mode() : 0, team,
                                  scap, Nr, n_rows, rows->row_dofs.p, rows->cell.p, rows->ncoll.p, rows->points.p, rows->coo_cols.p,
                                  rows->coo_vals.p, row_cnt.p, src_row.p, conflict.p, counters_dev);
     FXII_LAUNCHED(1);
@@ -1096,13 +1243,13 @@ void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr
       const int4* cn = reinterpret_cast<const int4*>(m->cell_nodes.p);
       if (nd == 4)
         { pi_locate_tabulate_kernel<4><<<grid, threads, smem, s>>>(
-            m->nodes.p, m->cellgeo.p, m->x.p, cn, m->padding, sp->dofmap.p, rows->frames.p, rows->table.p, rows->w.p,
-            rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, nq, Np, rows->cell.p, rows->ncoll.p, rows->points.p,
+            m->wnodes.p, m->grid, m->cellgeo.p, m->x.p, cn, m->padding, sp->dofmap.p, rows->frames.p, rows->table.p, rows->w.p,
+            rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, nq, (rows->kind != FXII_OP_POINTS) ? packet_mode() : 0, Np, rows->cell.p, rows->ncoll.p, rows->points.p,
             rows->coo_cols.p, rows->coo_vals.p, counters.p); FXII_LAUNCHED(1); }
       else
         { pi_locate_tabulate_kernel<10><<<grid, threads, smem, s>>>(
-            m->nodes.p, m->cellgeo.p, m->x.p, cn, m->padding, sp->dofmap.p, rows->frames.p, rows->table.p, rows->w.p,
-            rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, nq, Np, rows->cell.p, rows->ncoll.p, rows->points.p,
+            m->wnodes.p, m->grid, m->cellgeo.p, m->x.p, cn, m->padding, sp->dofmap.p, rows->frames.p, rows->table.p, rows->w.p,
+            rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, nq, (rows->kind != FXII_OP_POINTS) ? packet_mode() : 0, Np, rows->cell.p, rows->ncoll.p, rows->points.p,
             rows->coo_cols.p, rows->coo_vals.p, counters.p); FXII_LAUNCHED(1); }
       FXII_CUDA(cudaGetLastError());
     }
