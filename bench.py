@@ -71,6 +71,10 @@ def build_workload(cfg: dict, rank: int, pinned: bool):
         g2 = Mesh(pin(gamma.geometry.x), pin(gamma.geometry.dofmap), tdim=1, name=gamma.name)
         gamma = g2
     K = functionspace(gamma, ("Quadrature", K_QUAD_DEGREE))
+    if pinned:
+        K.dofmap.list = pin(K.dofmap.list)
+        if seg_r is not None:
+            seg_r = pin(seg_r)
     if cfg["op"] == "trace":
         op = PointwiseTrace(gamma)
     elif cfg["op"] == "circle":

@@ -189,6 +189,12 @@ struct fxii_rows {
   bool keep_points = false;  // also write the generated 3D points (diagnostics only)
   int mode = 0;              // 0: fused row reduction when possible; 1: always materialise the COO
   bool last_fused = false;
+  int64_t nnz_hint = 0;          // nnz of the previous fused build on this handle (0: unknown)
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // stage timers, created on first use
+  ~fxii_rows() {
+    for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
+  }
   // Γ inputs
   fxii::DevBuf<double> gx;
   fxii::DevBuf<int32_t> gcells, cells_k, row_dofs;

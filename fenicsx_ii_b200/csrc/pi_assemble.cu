@@ -983,7 +983,7 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
         }
         const int rho = row_dofs[r];
         if (rho < 0 || rho >= n_rows_total) *conflict = 2;
-        else if (atomicCAS(&src_row[rho], -1, (int32_t)r) != -1) *conflict = 1;
+        else if (atomicCAS(&src_row[rho], 0, (int32_t)r + 1) != 0) *conflict = 1;
         else row_cnt[rho] = nrow;
       }
       continue;
@@ -1068,23 +1068,25 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
     if (in_team && r < n_point_rows && l == 0) {
       const int rho = row_dofs[r];
       if (rho < 0 || rho >= n_rows_total) *conflict = 2;  // bad row index: reported by the general path
-      else if (atomicCAS(&src_row[rho], -1, (int32_t)r) != -1) *conflict = 1;  // row produced twice: not cell-local
+      else if (atomicCAS(&src_row[rho], 0, (int32_t)r + 1) != 0) *conflict = 1;  // row produced twice: not cell-local
       else row_cnt[rho] = base;
     }
     team_sync(team, team_id);  // s_cell / s_val / ekey are rewritten by the next row group
   }
 }
 
-// staging -> CSR: a group of G lanes copies one matrix row
+// staging -> CSR: a group of G lanes copies one matrix row.  Nothing is written when the matrix does
+// not fit `capacity` entries (the host then repeats the copy into exact-size arrays).
 __global__ void __launch_bounds__(256)
 compact_rows_kernel(const int32_t* __restrict__ src_row, const int64_t* __restrict__ indptr, const int32_t* __restrict__ stage_col,
-                    const double* __restrict__ stage_val, int seg, int64_t n_rows, int G, int32_t* __restrict__ indices,
-                    double* __restrict__ values) {
+                    const double* __restrict__ stage_val, int seg, int64_t n_rows, int G, int64_t capacity,
+                    int32_t* __restrict__ indices, double* __restrict__ values) {
+  if (indptr[n_rows] > capacity) return;
   const int64_t gid = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
   const int lg = threadIdx.x % G;
   const int64_t n_groups = ((int64_t)gridDim.x * blockDim.x) / G;
   for (int64_t rho = gid; rho < n_rows; rho += n_groups) {
-    const int32_t r = src_row[rho];
+    const int32_t r = src_row[rho] - 1;  // 0 = no point row produced this matrix row
     if (r < 0) continue;
     const int64_t o0 = indptr[rho];
     const int n = (int)(indptr[rho + 1] - o0);
@@ -1097,7 +1099,9 @@ compact_rows_kernel(const int32_t* __restrict__ src_row, const int64_t* __restri
 }
 
 // Returns false when the fused path cannot be used (caller falls back to the COO path).
-static bool pi_assemble_fused(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr* out, PiCounters* counters_dev,
+// One host synchronisation per build once the rows handle knows its nnz from an earlier build
+// (`nnz_hint`): the CSR arrays are then allocated before the kernels run.
+static bool pi_assemble_fused(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr* out, PiCounters* h_counters,
                               float* ms_locate, float* ms_csr) {
   const fxii_mesh* m = sp->mesh;
   const int nd = sp->nd, nq = rows->nq;
@@ -1119,27 +1123,26 @@ static bool pi_assemble_fused(const fxii_space* sp, fxii_rows* rows, cudaStream_
   const size_t smem = sizeof(double) * (4 * (size_t)nq + 2 * (size_t)B * nd) + sizeof(uint64_t) * (size_t)rpb * scap +
                       sizeof(int32_t) * (size_t)(B + B / 32 + 1);
   if (smem > 200 * 1024) return false;
-  cudaEvent_t ev[3];
-  for (auto& e : ev) FXII_CUDA(cudaEventCreate(&e));
-  DevBuf<int64_t> row_cnt;
-  DevBuf<int32_t> src_row;
-  DevBuf<int> conflict;
-  row_cnt.alloc(n_rows + 1, s);
-  src_row.alloc(n_rows, s);
-  conflict.alloc(1, s);
-  FXII_CUDA(cudaMemsetAsync(row_cnt.p, 0, sizeof(int64_t) * (size_t)(n_rows + 1), s));
-  FXII_CUDA(cudaMemsetAsync(src_row.p, 0xff, sizeof(int32_t) * (size_t)n_rows, s));
-  FXII_CUDA(cudaMemsetAsync(conflict.p, 0, sizeof(int), s));
+  if (!rows->ev[0]) {
+    for (auto& e : rows->ev) FXII_CUDA(cudaEventCreate(&e));
+  }
+  cudaEvent_t* ev = rows->ev;
+  // workspace, cleared by ONE memset: row_cnt i64[n_rows+1] | counters | conflict | src_row i32[n_rows]
+  const size_t off_counters = sizeof(int64_t) * (size_t)(n_rows + 1);
+  const size_t off_conflict = off_counters + sizeof(PiCounters);
+  const size_t off_src = off_conflict + 8;
+  const size_t ws_bytes = off_src + sizeof(int32_t) * (size_t)n_rows;
+  DevBuf<uint8_t> ws;
+  ws.alloc((int64_t)ws_bytes, s);
+  FXII_CUDA(cudaMemsetAsync(ws.p, 0, ws_bytes, s));
+  int64_t* row_cnt = reinterpret_cast<int64_t*>(ws.p);
+  PiCounters* counters_dev = reinterpret_cast<PiCounters*>(ws.p + off_counters);
+  int* conflict = reinterpret_cast<int*>(ws.p + off_conflict);
+  int32_t* src_row = reinterpret_cast<int32_t*>(ws.p + off_src);
   FXII_CUDA(cudaEventRecord(ev[0], s));
   const int64_t n_groups = (Nr + rpb - 1) / rpb;
   auto launch = [&](auto kernel) {
     if (smem > 48 * 1024) FXII_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // shared memory for 8 resident blocks of 128 threads (the register limit), the rest stays L1
-    int carve = (int)((smem + 1024) * (1024 / B) * 100 / (228 * 1024)) + 1;
-    if (carve > 100) carve = 100;
-    static const char* env_carve = getenv("FXII_CARVEOUT");  // tuning knob: -1 keeps the driver default
-    if (env_carve) carve = atoi(env_carve);
-    if (carve >= 0) FXII_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     // grid-stride over row groups: 2048 resident threads per SM at most, two waves of blocks so that
     // the tail of slow row groups is shared out
     const int grid = (int)std::min<int64_t>(n_groups, (int64_t)num_sms() * (2048 / B) * 2);
@@ -1148,7 +1151,7 @@ static bool pi_assemble_fused(const fxii_space* sp, fxii_rows* rows, cudaStream_
                                  rows->table.p, rows->w.p, rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, nq,
                                  (rows->kind != FXII_OP_POINTS) ? packet_mode() : 0, team,
                                  scap, Nr, n_rows, rows->row_dofs.p, rows->cell.p, rows->ncoll.p, rows->points.p, rows->coo_cols.p,
-                                 rows->coo_vals.p, row_cnt.p, src_row.p, conflict.p, counters_dev);
+                                 rows->coo_vals.p, row_cnt, src_row, conflict, counters_dev);
     FXII_LAUNCHED(1);
     FXII_CUDA(cudaGetLastError());
   };
@@ -1160,38 +1163,43 @@ static bool pi_assemble_fused(const fxii_space* sp, fxii_rows* rows, cudaStream_
   out->indptr.alloc(n_rows + 1, s);
   {
     size_t tb = 0;
-    FXII_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, (const long long*)row_cnt.p, (long long*)out->indptr.p,
+    FXII_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, (const long long*)row_cnt, (long long*)out->indptr.p,
                                             (int64_t)(n_rows + 1), s));
     DevBuf<uint8_t> tmp;
     tmp.alloc((int64_t)tb, s);
-    FXII_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, (const long long*)row_cnt.p, (long long*)out->indptr.p,
+    FXII_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, (const long long*)row_cnt, (long long*)out->indptr.p,
                                             (int64_t)(n_rows + 1), s));
   }
+  auto compact = [&](int64_t capacity) {
+    out->indices.alloc(capacity, s);
+    out->values.alloc(capacity, s);
+    if (capacity == 0) return;
+    int G = 4;
+    const int64_t avg = capacity / std::max<int64_t>(1, Nr);
+    while (G < 32 && G < avg) G <<= 1;
+    { compact_rows_kernel<<<grid_for(n_rows * G, 256, 8), 256, 0, s>>>(src_row, out->indptr.p, rows->coo_cols.p, rows->coo_vals.p,
+                                                                    nq * nd, n_rows, G, capacity, out->indices.p, out->values.p); FXII_LAUNCHED(1); }
+    FXII_CUDA(cudaGetLastError());
+  };
+  const int64_t hint = rows->nnz_hint;
+  if (hint > 0) compact(hint);  // speculative: no host round trip before the copy
   int64_t nnz = 0;
   int h_conflict = 0;
   FXII_CUDA(cudaMemcpyAsync(&nnz, out->indptr.p + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-  FXII_CUDA(cudaMemcpyAsync(&h_conflict, conflict.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-  FXII_CUDA(cudaStreamSynchronize(s));
-  if (h_conflict) {
-    for (auto& e : ev) cudaEventDestroy(e);
-    return false;  // K dofs shared between point rows: the general path handles first-visit-wins
-  }
-  out->nnz = nnz;
-  out->indices.alloc(nnz, s);
-  out->values.alloc(nnz, s);
-  if (nnz > 0) {
-    int G = 4;
-    const int64_t avg = nnz / std::max<int64_t>(1, Nr);
-    while (G < 32 && G < avg) G <<= 1;
-    { compact_rows_kernel<<<grid_for(n_rows * G, 256, 8), 256, 0, s>>>(src_row.p, out->indptr.p, rows->coo_cols.p, rows->coo_vals.p,
-                                                                    nq * nd, n_rows, G, out->indices.p, out->values.p); FXII_LAUNCHED(1); }
-    FXII_CUDA(cudaGetLastError());
-  }
+  FXII_CUDA(cudaMemcpyAsync(&h_conflict, conflict, sizeof(int), cudaMemcpyDeviceToHost, s));
+  FXII_CUDA(cudaMemcpyAsync(h_counters, counters_dev, sizeof(PiCounters), cudaMemcpyDeviceToHost, s));
   FXII_CUDA(cudaEventRecord(ev[2], s));
-  FXII_CUDA(cudaEventSynchronize(ev[2]));
+  FXII_CUDA(cudaStreamSynchronize(s));
+  if (h_conflict) return false;  // K dofs shared between point rows: the general path handles first-visit-wins
+  out->nnz = nnz;
+  if (hint <= 0 || nnz > hint) {
+    compact(nnz);
+    FXII_CUDA(cudaEventRecord(ev[2], s));
+    FXII_CUDA(cudaStreamSynchronize(s));
+  }
+  rows->nnz_hint = nnz;
   *ms_locate = elapsed_ms(ev[0], ev[1]);
   *ms_csr = elapsed_ms(ev[1], ev[2]);
-  for (auto& e : ev) cudaEventDestroy(e);
   return true;
 }
 
@@ -1225,15 +1233,16 @@ void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr
   rows->coo_cols.alloc(E, s);  // COO (unfused) or per-row staging (fused)
   rows->coo_vals.alloc(E, s);
   DevBuf<PiCounters> counters;
-  counters.alloc(1, s);
-  FXII_CUDA(cudaMemsetAsync(counters.p, 0, sizeof(PiCounters), s));
+  PiCounters h;
+  memset(&h, 0, sizeof(h));
   const size_t tab_smem = (rows->kind == FXII_OP_CIRCLE || rows->kind == FXII_OP_DISK) ? sizeof(double) * 4 * (size_t)nq : 0;
   FXII_CHECK(tab_smem <= 48 * 1024, "operator table too large for shared memory (nq > 1536)");
   float ms_count = 0.f, ms_fill = 0.f, ms_loc_f = 0.f, ms_csr_f = 0.f;
   bool fused = false;
-  if (rows->mode != 1) fused = pi_assemble_fused(sp, rows, s, out, counters.p, &ms_loc_f, &ms_csr_f);
+  if (rows->mode != 1) fused = pi_assemble_fused(sp, rows, s, out, &h, &ms_loc_f, &ms_csr_f);
   rows->last_fused = fused;
   if (!fused) {
+    counters.alloc(1, s);
     FXII_CUDA(cudaMemsetAsync(counters.p, 0, sizeof(PiCounters), s));
     FXII_CUDA(cudaEventRecord(ev[1], s));
     if (Np > 0) {
@@ -1257,13 +1266,9 @@ void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr
     coo_segments_to_csr(rows->row_dofs.p, Nr, rows->n_rows_total, nq * nd, rows->coo_cols.p, rows->coo_vals.p, sp->n_dofs, s,
                         out, &ms_count, &ms_fill);
     FXII_CUDA(cudaEventRecord(ev[3], s));
-  } else {
-    FXII_CUDA(cudaEventRecord(ev[2], s));
-    FXII_CUDA(cudaEventRecord(ev[3], s));
+    FXII_CUDA(cudaMemcpyAsync(&h, counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    FXII_CUDA(cudaStreamSynchronize(s));
   }
-  PiCounters h;
-  FXII_CUDA(cudaMemcpyAsync(&h, counters.p, sizeof(h), cudaMemcpyDeviceToHost, s));
-  FXII_CUDA(cudaStreamSynchronize(s));
   if (stats) {
     stats->n_points = Np;
     stats->n_entries = E;

@@ -240,7 +240,9 @@ def device_rows(K, red_op, cells_K=None) -> DeviceRows:
     if getattr(K.dofmap, "bs", 1) != 1:
         raise NotImplementedError("blocked K spaces (bs > 1) are not supported yet")
     k_list = np.asarray(K.dofmap.list)
-    row_dofs = k_list[cells_K].reshape(-1)
+    all_cells = cells_K.shape[0] == k_list.shape[0] and (cells_K.shape[0] == 0 or (cells_K[0] == 0 and cells_K[-1] == k_list.shape[0] - 1
+                                                                  and bool(np.all(np.diff(cells_K) == 1))))
+    row_dofs = k_list.reshape(-1) if all_cells else k_list[cells_K].reshape(-1)  # no copy for the default cells_K
     n_rows_total = (K.dofmap.index_map.size_local + K.dofmap.index_map.num_ghosts) * K.dofmap.index_map_bs
     if k_list.shape[1] != ref_points.shape[0]:
         raise ValueError("K must have one dof per interpolation point")
