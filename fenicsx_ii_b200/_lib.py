@@ -87,6 +87,7 @@ SIGNATURES = {
     "fxii_csr_download": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "fxii_csr_destroy": (C.c_int, [_vp]),
     "fxii_csr_transpose": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "fxii_csr_transpose_window": (C.c_int, [_vp, _i64, _i64, _vp, C.POINTER(_vp)]),
     "fxii_spgemm": (C.c_int, [_vp, _vp, _i64, _i64, _vp, C.POINTER(_vp), C.POINTER(_i64)]),
     "fxii_csr_scale_rows": (C.c_int, [_vp, _vp, _vp]),
     "fxii_csr_spmv": (C.c_int, [_vp, _vp, _vp, _vp]),

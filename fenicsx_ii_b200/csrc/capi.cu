@@ -9,7 +9,7 @@ void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* c
                 double padding, cudaStream_t s);
 void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr* out, fxii_pi_stats* stats,
                  bool keep_points);
-void csr_transpose(const fxii_csr* a, cudaStream_t s, fxii_csr* out);
+void csr_transpose(const fxii_csr* a, int64_t c0, int64_t c1, cudaStream_t s, fxii_csr* out);
 void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row_end, cudaStream_t s, fxii_csr* out,
             int64_t* ip_out);
 void csr_scale_rows(fxii_csr* a, const double* d_host, cudaStream_t s);
@@ -427,7 +427,22 @@ int fxii_csr_transpose(const fxii_csr* a, void* stream, fxii_csr** out) {
     FXII_CHECK(a && out, "null argument");
     auto* c = new fxii_csr();
     try {
-      fxii::csr_transpose(a, S(stream), c);
+      fxii::csr_transpose(a, 0, -1, S(stream), c);
+      FXII_CUDA(cudaStreamSynchronize(S(stream)));
+    } catch (...) {
+      delete c;
+      throw;
+    }
+    *out = c;
+  });
+}
+
+int fxii_csr_transpose_window(const fxii_csr* a, int64_t col_begin, int64_t col_end, void* stream, fxii_csr** out) {
+  return guarded([&] {
+    FXII_CHECK(a && out, "null argument");
+    auto* c = new fxii_csr();
+    try {
+      fxii::csr_transpose(a, col_begin, col_end, S(stream), c);
       FXII_CUDA(cudaStreamSynchronize(S(stream)));
     } catch (...) {
       delete c;
@@ -471,7 +486,7 @@ int fxii_csr_spmv_t(const fxii_csr* a, const double* u, double* y, void* stream)
   return guarded([&] {
     FXII_CHECK(a && u && y, "null argument");
     fxii_csr t;
-    fxii::csr_transpose(a, S(stream), &t);
+    fxii::csr_transpose(a, 0, -1, S(stream), &t);
     fxii::csr_spmv(&t, u, y, S(stream));
   });
 }

@@ -57,45 +57,88 @@ static void exclusive_scan_i64(const long long* in, long long* out, int64_t n, c
   FXII_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, in, out, n, s));
 }
 
+struct InWindow {
+  const int32_t* indices;
+  int32_t c0, c1;
+  __device__ bool operator()(const int32_t& k) const {
+    const int32_t c = indices[k];
+    return c >= c0 && c < c1;
+  }
+};
+
+__global__ void __launch_bounds__(256)
+window_keys_kernel(const int32_t* __restrict__ sel, int64_t n_sel, const int32_t* __restrict__ indices, int32_t c0,
+                   int32_t* __restrict__ keys, unsigned long long* __restrict__ count) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n_sel; k += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t key = indices[sel[k]] - c0;
+    keys[k] = key;
+    atomicAdd(&count[key], 1ULL);
+  }
+}
+
 // Stable sort of the entries by column (radix sort is stable), so every row of Aᵀ lists the
-// source rows in ascending order — the order MatTranspose produces.
-void csr_transpose(const fxii_csr* a, cudaStream_t s, fxii_csr* out) {
+// source rows in ascending order — the order MatTranspose produces.  With a column window
+// [c0, c1) only those columns are transposed (rows of the result: c1 - c0): the entries are first
+// compacted in order (cub select), so the sort touches only the shard.
+void csr_transpose(const fxii_csr* a, int64_t c0, int64_t c1, cudaStream_t s, fxii_csr* out) {
   FXII_CHECK(a->nnz < ((int64_t)1 << 31), "transpose: nnz must fit int32 (shard the matrix)");
+  if (c1 < 0) c1 = a->n_cols;
+  FXII_CHECK(c0 >= 0 && c0 <= c1 && c1 <= a->n_cols, "transpose: bad column window");
   Trace tr("transpose", s);
-  out->n_rows = a->n_cols;
+  const int64_t n_out_rows = c1 - c0;
+  const bool window = !(c0 == 0 && c1 == a->n_cols);
+  out->n_rows = n_out_rows;
   out->n_cols = a->n_rows;
-  out->nnz = a->nnz;
   const int64_t nnz = a->nnz;
   DevBuf<unsigned long long> count;
-  count.alloc(a->n_cols + 1, s);
-  FXII_CUDA(cudaMemsetAsync(count.p, 0, sizeof(unsigned long long) * (size_t)(a->n_cols + 1), s));
-  out->indptr.alloc(a->n_cols + 1, s);
-  out->indices.alloc(nnz, s);
-  out->values.alloc(nnz, s);
+  count.alloc(n_out_rows + 1, s);
+  FXII_CUDA(cudaMemsetAsync(count.p, 0, sizeof(unsigned long long) * (size_t)(n_out_rows + 1), s));
+  out->indptr.alloc(n_out_rows + 1, s);
+  DevBuf<int32_t> row_of, iota, sel, keys, perm, keys_sorted;
+  int64_t n_sel = nnz;
   if (nnz > 0) {
-    { col_hist_kernel<<<grid_for(nnz, 256, 8), 256, 0, s>>>(a->indices.p, nnz, count.p); FXII_LAUNCHED(1); }
+    row_of.alloc(nnz, s);
+    iota.alloc(nnz, s);
+    { expand_rows_kernel<<<grid_for(a->n_rows * 32, 256, 8), 256, 0, s>>>(a->indptr.p, a->n_rows, row_of.p); FXII_LAUNCHED(1); }
+    { iota32_kernel<<<grid_for(nnz, 256, 8), 256, 0, s>>>(iota.p, nnz); FXII_LAUNCHED(1); }
+    if (window) {
+      sel.alloc(nnz, s);
+      DevBuf<int64_t> n_sel_dev;
+      n_sel_dev.alloc(1, s);
+      InWindow pred{a->indices.p, (int32_t)c0, (int32_t)c1};
+      size_t tb = 0;
+      FXII_CUDA(cub::DeviceSelect::If(nullptr, tb, iota.p, sel.p, n_sel_dev.p, nnz, pred, s));
+      DevBuf<uint8_t> tmp;
+      tmp.alloc((int64_t)tb, s);
+      FXII_CUDA(cub::DeviceSelect::If(tmp.p, tb, iota.p, sel.p, n_sel_dev.p, nnz, pred, s));
+      FXII_CUDA(cudaMemcpyAsync(&n_sel, n_sel_dev.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+      FXII_CUDA(cudaStreamSynchronize(s));
+    }
+  }
+  out->nnz = n_sel;
+  out->indices.alloc(n_sel, s);
+  out->values.alloc(n_sel, s);
+  tr.mark("alloc + expand + select");
+  if (n_sel > 0) {
+    keys.alloc(n_sel, s);
+    { window_keys_kernel<<<grid_for(n_sel, 256, 8), 256, 0, s>>>(window ? sel.p : iota.p, n_sel, a->indices.p, (int32_t)c0, keys.p, count.p); FXII_LAUNCHED(1); }
     FXII_CUDA(cudaGetLastError());
   }
-  exclusive_scan_i64((const long long*)count.p, (long long*)out->indptr.p, a->n_cols + 1, s);
-  tr.mark("alloc + hist + scan");
-  if (nnz == 0) return;
-  DevBuf<int32_t> row_of, iota, perm, keys_sorted;
-  row_of.alloc(nnz, s);
-  iota.alloc(nnz, s);
-  perm.alloc(nnz, s);
-  keys_sorted.alloc(nnz, s);
-  { expand_rows_kernel<<<grid_for(a->n_rows * 32, 256, 8), 256, 0, s>>>(a->indptr.p, a->n_rows, row_of.p); FXII_LAUNCHED(1); }
-  { iota32_kernel<<<grid_for(nnz, 256, 8), 256, 0, s>>>(iota.p, nnz); FXII_LAUNCHED(1); }
+  exclusive_scan_i64((const long long*)count.p, (long long*)out->indptr.p, n_out_rows + 1, s);
+  tr.mark("keys + hist + scan");
+  if (n_sel == 0) return;
+  perm.alloc(n_sel, s);
+  keys_sorted.alloc(n_sel, s);
   int end_bit = 1;
-  while (end_bit < 31 && ((int64_t)1 << end_bit) < a->n_cols) ++end_bit;
-  tr.mark("alloc + expand + iota");
+  while (end_bit < 31 && ((int64_t)1 << end_bit) < n_out_rows) ++end_bit;
   size_t tb = 0;
-  FXII_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, a->indices.p, keys_sorted.p, iota.p, perm.p, nnz, 0, end_bit, s));
+  const int32_t* src = window ? sel.p : iota.p;
+  FXII_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys.p, keys_sorted.p, src, perm.p, n_sel, 0, end_bit, s));
   DevBuf<uint8_t> tmp;
   tmp.alloc((int64_t)tb, s);
-  FXII_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, a->indices.p, keys_sorted.p, iota.p, perm.p, nnz, 0, end_bit, s));
+  FXII_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.p, keys_sorted.p, src, perm.p, n_sel, 0, end_bit, s));
   tr.mark("radix sort");
-  { gather_transposed_kernel<<<grid_for(nnz, 256, 8), 256, 0, s>>>(perm.p, row_of.p, a->values.p, nnz, out->indices.p,
+  { gather_transposed_kernel<<<grid_for(n_sel, 256, 8), 256, 0, s>>>(perm.p, row_of.p, a->values.p, n_sel, out->indices.p,
                                                                  out->values.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
 }

@@ -23,34 +23,79 @@ def allgatherv_csr(indptr, indices, values, group=None):
 
     Every rank passes its shard (indptr int64[m_r+1] starting at 0, indices int32[nnz_r],
     values float64[nnz_r]) and receives the row-concatenated matrix (indptr, indices, values).
-    NCCL has no v-variant: shards are padded to the largest shard and trimmed after the gather."""
+    NCCL has no all-gather-v: after one small all-gather of the shard sizes, every rank's shard
+    is broadcast straight into its slice of the preallocated result (no padding, no concatenation
+    copies)."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
     dev = indptr.device
     sizes = torch.tensor([indptr.numel() - 1, indices.numel()], dtype=torch.int64, device=dev)
-    all_sizes = [torch.empty_like(sizes) for _ in range(world)]
-    dist.all_gather(all_sizes, sizes, group=group)
-    all_sizes = torch.stack(all_sizes).cpu().numpy()
-    m_max, nnz_max = int(all_sizes[:, 0].max()), int(all_sizes[:, 1].max())
-
-    def gather(t, n_max, dtype):
-        pad = torch.zeros(n_max, dtype=dtype, device=dev)
-        pad[: t.numel()] = t
-        out = torch.empty(world * n_max, dtype=dtype, device=dev)
-        dist.all_gather_into_tensor(out, pad, group=group)
-        return out.view(world, n_max)
-
-    counts = gather(indptr[1:] - indptr[:-1], m_max, torch.int64)
-    idx = gather(indices, nnz_max, torch.int32)
-    val = gather(values, nnz_max, torch.float64)
-    rows = torch.cat([counts[r, : all_sizes[r, 0]] for r in range(world)])
-    g_indptr = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(rows, 0, out=g_indptr[1:])
-    g_indices = torch.cat([idx[r, : all_sizes[r, 1]] for r in range(world)])
-    g_values = torch.cat([val[r, : all_sizes[r, 1]] for r in range(world)])
+    all_sizes = torch.empty(2 * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_sizes, sizes, group=group)
+    all_sizes = all_sizes.view(world, 2).cpu().numpy()
+    row_off = np.concatenate([[0], np.cumsum(all_sizes[:, 0])])
+    nnz_off = np.concatenate([[0], np.cumsum(all_sizes[:, 1])])
+    counts = torch.empty(int(row_off[-1]), dtype=torch.int64, device=dev)
+    g_indices = torch.empty(int(nnz_off[-1]), dtype=torch.int32, device=dev)
+    g_values = torch.empty(int(nnz_off[-1]), dtype=torch.float64, device=dev)
+    counts[row_off[rank]:row_off[rank + 1]] = indptr[1:] - indptr[:-1]
+    g_indices[nnz_off[rank]:nnz_off[rank + 1]] = indices
+    g_values[nnz_off[rank]:nnz_off[rank + 1]] = values
+    ranks = dist.get_process_group_ranks(group) if group is not None else list(range(world))
+    work = []
+    for r in range(world):
+        src = ranks[r]
+        for buf, off in ((counts, row_off), (g_indices, nnz_off), (g_values, nnz_off)):
+            if off[r + 1] > off[r]:
+                work.append(dist.broadcast(buf[off[r]:off[r + 1]], src=src, group=group, async_op=True))
+    for w in work:
+        w.wait()
+    g_indptr = torch.zeros(counts.numel() + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(counts, 0, out=g_indptr[1:])
     return g_indptr, g_indices, g_values
+
+
+def allgatherv_vector(v, group=None):
+    """All-gather of per-rank float64 vectors of different lengths (same broadcast scheme)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n = torch.tensor([v.numel()], dtype=torch.int64, device=v.device)
+    all_n = torch.empty(world, dtype=torch.int64, device=v.device)
+    dist.all_gather_into_tensor(all_n, n, group=group)
+    off = np.concatenate([[0], np.cumsum(all_n.cpu().numpy())])
+    out = torch.empty(int(off[-1]), dtype=v.dtype, device=v.device)
+    out[off[rank]:off[rank + 1]] = v
+    ranks = dist.get_process_group_ranks(group) if group is not None else list(range(world))
+    work = [dist.broadcast(out[off[r]:off[r + 1]], src=ranks[r], group=group, async_op=True) for r in range(world)
+            if off[r + 1] > off[r]]
+    for w in work:
+        w.wait()
+    return out
+
+
+def balanced_dof_windows(indices_t, n_cols: int, world: int):
+    """Contiguous ranges of 3D dofs (columns of the gathered Π) with equal numbers of Π entries — a
+    proxy for equal SpGEMM work (intermediate products of row j of Πᵀ ~ entries in column j of Π).
+    Every rank computes the same boundaries from the same gathered matrix."""
+    import torch
+
+    if world == 1:
+        return [(0, n_cols)]
+    counts = torch.bincount(indices_t.to(torch.int64), minlength=n_cols)
+    cum = torch.cumsum(counts, 0)
+    total = int(cum[-1].item())
+    targets = torch.tensor([total * (r + 1) // world for r in range(world - 1)], device=cum.device, dtype=cum.dtype)
+    cuts = torch.searchsorted(cum, targets, right=False).add_(1).clamp_(max=n_cols).cpu().tolist()
+    edges = [0] + cuts + [n_cols]
+    for i in range(1, len(edges)):  # keep the ranges monotone even for degenerate distributions
+        edges[i] = max(edges[i], edges[i - 1])
+    return [(edges[r], edges[r + 1]) for r in range(world)]
 
 
 def quadrature_mass_diagonal(gamma, K) -> np.ndarray:
@@ -82,24 +127,31 @@ def product_pt_m_p(pi_local, gamma, K, world: int, rank: int, steps: int = 5, fl
     n_dofs = pi_local.shape[1]
 
     def once():
-        t = {}
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-        e[0].record()
-        mp_local = pi_local.copy().scale_rows(diag)  # M_Γ Π (diagonal mass)
-        e[1].record()
+        import torch as _t
+
+        e = [_t.cuda.Event(enable_timing=True) for _ in range(5)]
         if world > 1:
-            gp = DeviceCSR.from_device_arrays(*allgatherv_csr(*pi_local.device_tensors()), (pi_local.shape[0] * world, n_dofs))
-            gmp = DeviceCSR.from_device_arrays(*allgatherv_csr(*mp_local.device_tensors()), (pi_local.shape[0] * world, n_dofs))
+            dist.barrier()  # start together: otherwise the first collective absorbs the ranks' skew
+        e[0].record()
+        if world > 1:
+            # the one exchange of the path: Π's row shards (and the mass diagonal) to every rank
+            g_ptr, g_idx, g_val = allgatherv_csr(*pi_local.device_tensors())
+            gp = DeviceCSR.from_device_arrays(g_ptr, g_idx, g_val, (pi_local.shape[0] * world, n_dofs))
+            gdiag = allgatherv_vector(_t.from_numpy(diag).to("cuda")).cpu().numpy()
+            r0, r1 = balanced_dof_windows(g_idx, n_dofs, world)[rank]
+            del g_ptr, g_idx, g_val
         else:
-            gp, gmp = pi_local, mp_local
+            gp, gdiag = pi_local, diag
+            r0, r1 = 0, n_dofs
+        e[1].record()
+        gmp = gp.copy().scale_rows(gdiag)  # M_Γ Π (diagonal quadrature mass)
         e[2].record()
-        pt = gp.transpose()
+        pt = gp.transpose(r0, r1)  # only the rows of Πᵀ this rank owns (3D dofs r0..r1)
         e[3].record()
-        r0, r1 = shard_range(n_dofs, world, rank)
-        c, ip = pt.matmult(gmp, r0, r1, return_ip=True)
+        c, ip = pt.matmult(gmp, return_ip=True)
         e[4].record()
-        torch.cuda.synchronize()
-        t = dict(scale_ms=e[0].elapsed_time(e[1]), allgather_ms=e[1].elapsed_time(e[2]), transpose_ms=e[2].elapsed_time(e[3]),
+        _t.cuda.synchronize()
+        t = dict(allgather_ms=e[0].elapsed_time(e[1]), scale_ms=e[1].elapsed_time(e[2]), transpose_ms=e[2].elapsed_time(e[3]),
                  spgemm_ms=e[3].elapsed_time(e[4]), total_ms=e[0].elapsed_time(e[4]))
         return t, c, ip, pt.nnz, (r1 - r0)
 
@@ -119,5 +171,5 @@ def product_pt_m_p(pi_local, gamma, K, world: int, rank: int, steps: int = 5, fl
     avg.update(ip=int(ip), nnz_c_local=int(c.nnz), nnz_a=int(nnz_a),
                spgemm_alg_GBps=alg_bytes / (avg["spgemm_ms"] * 1e-3) / 1e9 if avg["spgemm_ms"] > 0 else 0.0,
                spgemm_s=avg["spgemm_ms"] * 1e-3, pit_m_pi_s=avg["total_ms"] * 1e-3,
-               association="Pi^T (M Pi), rows sharded by 3D dof")
+               association="Pi^T (M Pi), rows sharded by 3D dof (windows balanced by Pi column counts)")
     return avg

@@ -101,9 +101,14 @@ class DeviceCSR:
         )
 
     # -- products --------------------------------------------------------------------------------
-    def transpose(self) -> "DeviceCSR":
+    def transpose(self, col_begin: int = 0, col_end: int = -1) -> "DeviceCSR":
+        """Aᵀ, or only its rows [col_begin, col_end) (the columns of A in that window) — the V-dof row
+        shard a rank needs for the multi-GPU product."""
         out = C.c_void_p()
-        _lib.check(_lib.load().fxii_csr_transpose(self._h, _lib.current_stream(), C.byref(out)))
+        if col_begin == 0 and col_end < 0:
+            _lib.check(_lib.load().fxii_csr_transpose(self._h, _lib.current_stream(), C.byref(out)))
+        else:
+            _lib.check(_lib.load().fxii_csr_transpose_window(self._h, col_begin, col_end, _lib.current_stream(), C.byref(out)))
         return DeviceCSR(out.value)
 
     def matmult(self, other: "DeviceCSR", row_begin: int = 0, row_end: int = -1, return_ip: bool = False):

@@ -139,6 +139,9 @@ int fxii_csr_destroy(fxii_csr* a);
 
 /* Mat.transpose (matrix_assembler.py:184,236): rows of the result keep the source row order */
 int fxii_csr_transpose(const fxii_csr* a, void* stream, fxii_csr** out);
+/* rows [col_begin, col_end) of Aᵀ only (col_end < 0: n_cols): the V-dof row shard of one rank */
+int fxii_csr_transpose_window(const fxii_csr* a, int64_t col_begin, int64_t col_end, void* stream,
+                              fxii_csr** out);
 /* Mat.matMult (matrix_assembler.py:185,210,237,245): symbolic pattern kept, columns sorted,
  * c_ij accumulated over k in A's column order.  ip (may be NULL) = intermediate products.
  * Optional row window [row_begin,row_end) of A (the V-dof row shard of SURVEY §8e);

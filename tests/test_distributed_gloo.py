@@ -62,3 +62,19 @@ def test_shard_range_partitions():
                 assert a[1] == b[0]
             sizes = [e[1] - e[0] for e in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_balanced_dof_windows_cover_and_balance():
+    from fenicsx_ii_b200.distributed import balanced_dof_windows
+
+    rng = np.random.default_rng(1)
+    n_cols = 5000
+    # entries concentrated in a narrow band of columns (a vessel in a big mesh)
+    idx = torch.from_numpy(np.concatenate([rng.integers(1000, 1200, 90_000), rng.integers(0, n_cols, 10_000)]).astype(np.int32))
+    for world in (1, 2, 3, 8):
+        w = balanced_dof_windows(idx, n_cols, world)
+        assert w[0][0] == 0 and w[-1][1] == n_cols and all(a[1] == b[0] for a, b in zip(w[:-1], w[1:]))
+        loads = [int(((idx >= a) & (idx < b)).sum()) for a, b in w]
+        assert sum(loads) == idx.numel()
+        if world > 1:
+            assert max(loads) <= 1.3 * idx.numel() / world + 600

@@ -143,3 +143,38 @@ def test_spmv_and_transpose_spmv(cuda):
     np.testing.assert_allclose(A.device.mult_transpose(bvec), S.T @ bvec, rtol=1e-12, atol=1e-13)
     # average_coefficient(u) of a linear function along the circle axis direction... row sums are one
     np.testing.assert_allclose(A.mult(np.ones(V.num_dofs)), 1.0, atol=1e-13)
+
+
+def test_transpose_window_and_sharded_product(cuda):
+    """The multi-GPU product on one device: every 'rank' transposes only its window of 3D dofs and
+    multiplies; the row-concatenation equals the unsharded Πᵀ(MΠ) bit for bit."""
+    from fenicsx_ii_b200.distributed import shard_range
+
+    mesh = sy.kuhn_box(8, 8, 8)
+    V = functionspace(mesh, ("Lagrange", 1))
+    gamma = sy.polyline_network(150, 1 / 8, n_lines=4, lo=0.2, hi=0.8)
+    W = functionspace(gamma, ("Quadrature", 10))
+    P, _, _ = create_interpolation_matrix(V, W, Circle(gamma, 0.06, degree=9))
+    diag = quadrature_mass_diagonal(gamma, W)
+    MP = P.device.copy().scale_rows(diag)
+    full_t = P.device.transpose()
+    ft = full_t.to_host()
+    C_full = full_t.matmult(MP).to_host()
+    parts = []
+    for world in (1, 3):
+        ind, idx, val = [np.zeros(1, dtype=np.int64)], [], []
+        for rank in range(world):
+            r0, r1 = shard_range(V.num_dofs, world, rank)
+            Tw = P.device.transpose(r0, r1)
+            assert Tw.shape == (r1 - r0, W.num_dofs)
+            ti, tj, tv = Tw.to_host()
+            np.testing.assert_array_equal(ti, ft[0][r0 : r1 + 1] - ft[0][r0])
+            np.testing.assert_array_equal(tj, ft[1][ft[0][r0] : ft[0][r1]])
+            assert tv.tobytes() == ft[2][ft[0][r0] : ft[0][r1]].tobytes()
+            ci, cj, cv = Tw.matmult(MP).to_host()
+            ind.append(ci[1:] + ind[-1][-1])
+            idx.append(cj)
+            val.append(cv)
+        np.testing.assert_array_equal(np.concatenate(ind), C_full[0])
+        np.testing.assert_array_equal(np.concatenate(idx), C_full[1])
+        assert np.concatenate(val).tobytes() == C_full[2].tobytes()
