@@ -77,6 +77,12 @@ struct DevBuf {
     st = s;
     if (count > 0) p = static_cast<T*>(cached_alloc(sizeof(T) * (size_t)count, s));
   }
+  // keep the allocation (and its address) when the size is unchanged; true if the buffer moved
+  bool ensure(int64_t count, cudaStream_t s) {
+    if (p && n == count) return false;
+    alloc(count, s);
+    return true;
+  }
   void upload(const T* host, int64_t count, cudaStream_t s) {
     alloc(count, s);
     if (count > 0) FXII_CUDA(cudaMemcpyAsync(p, host, sizeof(T) * (size_t)count, cudaMemcpyHostToDevice, s));
@@ -190,10 +196,26 @@ struct fxii_rows {
   int mode = 0;              // 0: fused row reduction when possible; 1: always materialise the COO
   bool last_fused = false;
   int64_t nnz_hint = 0;          // nnz of the previous fused build on this handle (0: unknown)
-  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // stage timers, created on first use
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // stage timers, created on first use
+  // fused path: workspace and, for graph replay, handle-owned CSR buffers + the captured graph
+  fxii::DevBuf<uint8_t> ws, scan_tmp;
+  fxii::DevBuf<int64_t> g_indptr;
+  fxii::DevBuf<int32_t> g_indices;
+  fxii::DevBuf<double> g_values;
+  void* host_result = nullptr;  // pinned FusedResult
+  cudaGraphExec_t graph_exec = nullptr;
+  const fxii_space* graph_space = nullptr;
+  cudaStream_t graph_stream = nullptr;
+  cudaStream_t capture_stream = nullptr;
+  int64_t graph_cap = 0;
+  int graph_kernels = 0;
+  bool buffers_moved = false, last_graph = false;
   ~fxii_rows() {
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    if (capture_stream) cudaStreamDestroy(capture_stream);
+    if (host_result) cudaFreeHost(host_result);
   }
   // Γ inputs
   fxii::DevBuf<double> gx;

@@ -1098,108 +1098,254 @@ compact_rows_kernel(const int32_t* __restrict__ src_row, const int64_t* __restri
   }
 }
 
-// Returns false when the fused path cannot be used (caller falls back to the COO path).
-// One host synchronisation per build once the rows handle knows its nnz from an earlier build
-// (`nnz_hint`): the CSR arrays are then allocated before the kernels run.
-static bool pi_assemble_fused(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr* out, PiCounters* h_counters,
-                              float* ms_locate, float* ms_csr) {
-  const fxii_mesh* m = sp->mesh;
+// ---- host side of the fused path -------------------------------------------------------------
+struct FusedPlan {
+  int team, B, rpb, grid;
+  uint32_t scap;
+  size_t smem;
+  size_t off_counters, off_conflict, off_src, ws_bytes;  // workspace layout
+  size_t scan_tmp_bytes;
+};
+
+// what a build reports back to the host, written by three small device-to-host copies
+struct FusedResult {
+  int64_t nnz;
+  PiCounters counters;
+  int conflict;
+};
+
+// false: the fused path does not apply (nq > 256, too much shared memory, empty)
+static bool make_fused_plan(const fxii_space* sp, const fxii_rows* rows, FusedPlan& p) {
   const int nd = sp->nd, nq = rows->nq;
-  const int64_t Nr = rows->n_point_rows, Np = Nr * nq, E = Np * nd, n_rows = rows->n_rows_total;
+  const int64_t Nr = rows->n_point_rows, E = Nr * nq * nd, n_rows = rows->n_rows_total;
   if (nq > 256 || Nr == 0 || E >= ((int64_t)1 << 40)) return false;
-  int team = 1;
+  p.team = 1;
   if (nq <= 32) {
-    while (team < nq) team <<= 1;
+    while (p.team < nq) p.team <<= 1;
   } else {
-    team = 32 * ((nq + 31) / 32);
+    p.team = 32 * ((nq + 31) / 32);
   }
   // block size: whole teams; 128 threads unless a team needs more
-  int B = team <= 128 ? 128 : 256;
-  if (team > 32 && B % team != 0) B = team * (256 / team > 0 ? 256 / team : 1);
-  if (B > 256 || B % 32 != 0) return false;
-  const int rpb = B / team;
-  uint32_t scap = 2;
-  while (scap < (uint32_t)team * nd) scap <<= 1;
-  const size_t smem = sizeof(double) * (4 * (size_t)nq + 2 * (size_t)B * nd) + sizeof(uint64_t) * (size_t)rpb * scap +
-                      sizeof(int32_t) * (size_t)(B + B / 32 + 1);
-  if (smem > 200 * 1024) return false;
-  if (!rows->ev[0]) {
-    for (auto& e : rows->ev) FXII_CUDA(cudaEventCreate(&e));
-  }
-  cudaEvent_t* ev = rows->ev;
+  p.B = p.team <= 128 ? 128 : 256;
+  if (p.team > 32 && p.B % p.team != 0) p.B = p.team * (256 / p.team > 0 ? 256 / p.team : 1);
+  if (p.B > 256 || p.B % 32 != 0) return false;
+  p.rpb = p.B / p.team;
+  p.scap = 2;
+  while (p.scap < (uint32_t)p.team * nd) p.scap <<= 1;
+  p.smem = sizeof(double) * (4 * (size_t)nq + 2 * (size_t)p.B * nd) + sizeof(uint64_t) * (size_t)p.rpb * p.scap +
+           sizeof(int32_t) * (size_t)(p.B + p.B / 32 + 1);
+  if (p.smem > 200 * 1024) return false;
+  const int64_t n_groups = (Nr + p.rpb - 1) / p.rpb;
+  // grid-stride over row groups: 2048 resident threads per SM at most, two waves of blocks so that
+  // the tail of slow row groups is shared out
+  p.grid = (int)std::min<int64_t>(n_groups, (int64_t)num_sms() * (2048 / p.B) * 2);
   // workspace, cleared by ONE memset: row_cnt i64[n_rows+1] | counters | conflict | src_row i32[n_rows]
-  const size_t off_counters = sizeof(int64_t) * (size_t)(n_rows + 1);
-  const size_t off_conflict = off_counters + sizeof(PiCounters);
-  const size_t off_src = off_conflict + 8;
-  const size_t ws_bytes = off_src + sizeof(int32_t) * (size_t)n_rows;
-  DevBuf<uint8_t> ws;
-  ws.alloc((int64_t)ws_bytes, s);
-  FXII_CUDA(cudaMemsetAsync(ws.p, 0, ws_bytes, s));
-  int64_t* row_cnt = reinterpret_cast<int64_t*>(ws.p);
-  PiCounters* counters_dev = reinterpret_cast<PiCounters*>(ws.p + off_counters);
-  int* conflict = reinterpret_cast<int*>(ws.p + off_conflict);
-  int32_t* src_row = reinterpret_cast<int32_t*>(ws.p + off_src);
-  FXII_CUDA(cudaEventRecord(ev[0], s));
-  const int64_t n_groups = (Nr + rpb - 1) / rpb;
+  p.off_counters = sizeof(int64_t) * (size_t)(n_rows + 1);
+  p.off_conflict = p.off_counters + sizeof(PiCounters);
+  p.off_src = p.off_conflict + 8;
+  p.ws_bytes = p.off_src + sizeof(int32_t) * (size_t)n_rows;
+  p.scan_tmp_bytes = 0;
+  FXII_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, p.scan_tmp_bytes, (const long long*)nullptr, (long long*)nullptr,
+                                          (int64_t)(n_rows + 1), (cudaStream_t)0));
+  return true;
+}
+
+static void launch_frames(fxii_rows* rows, cudaStream_t s) {
+  const int64_t Nr = rows->n_point_rows;
+  if (rows->kind == FXII_OP_POINTS || Nr == 0) return;
+  { row_frames_kernel<<<grid_for(Nr, 128, 16), 128, 0, s>>>(rows->gx.p, rows->gcells.p, rows->cells_k.p, rows->xref.p, rows->nip,
+                                                          rows->radius.p, rows->radius_per_row, rows->kind, Nr, rows->frames.p); FXII_LAUNCHED(1); }
+  FXII_CUDA(cudaGetLastError());
+}
+
+static void launch_compact(const fxii_space* sp, const fxii_rows* rows, const uint8_t* ws, const FusedPlan& p, const int64_t* indptr,
+                           int64_t capacity, int32_t* indices, double* values, cudaStream_t s) {
+  if (capacity <= 0) return;
+  const int64_t n_rows = rows->n_rows_total;
+  int G = 4;
+  const int64_t avg = capacity / std::max<int64_t>(1, rows->n_point_rows);
+  while (G < 32 && G < avg) G <<= 1;
+  { compact_rows_kernel<<<grid_for(n_rows * G, 256, 8), 256, 0, s>>>(reinterpret_cast<const int32_t*>(ws + p.off_src), indptr,
+                                                                  rows->coo_cols.p, rows->coo_vals.p, rows->nq * sp->nd, n_rows, G,
+                                                                  capacity, indices, values); FXII_LAUNCHED(1); }
+  FXII_CUDA(cudaGetLastError());
+}
+
+// Everything of one fused build, enqueued on `s` without any host synchronisation (so it can be
+// captured into a CUDA graph): clear workspace | frames | locate+reduce | scan | compact | results.
+// ev[0..3] bracket the three stages.  capacity == 0 skips the compaction (nnz still unknown).
+static void enqueue_fused(const fxii_space* sp, fxii_rows* rows, const FusedPlan& p, cudaStream_t s, uint8_t* ws, uint8_t* scan_tmp,
+                          int64_t* indptr, int32_t* indices, double* values, int64_t capacity, FusedResult* host_result,
+                          cudaEvent_t* ev) {
+  const fxii_mesh* m = sp->mesh;
+  const int64_t n_rows = rows->n_rows_total;
+  // inside a stream capture the stage timers become external event-record nodes of the graph
+  cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+  FXII_CUDA(cudaStreamIsCapturing(s, &cap_status));
+  const unsigned ev_flags = cap_status == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault;
+  FXII_CUDA(cudaMemsetAsync(ws, 0, p.ws_bytes, s));
+  FXII_CUDA(cudaEventRecordWithFlags(ev[0], s, ev_flags));
+  launch_frames(rows, s);
+  FXII_CUDA(cudaEventRecordWithFlags(ev[1], s, ev_flags));
+  int64_t* row_cnt = reinterpret_cast<int64_t*>(ws);
+  PiCounters* counters_dev = reinterpret_cast<PiCounters*>(ws + p.off_counters);
+  int* conflict = reinterpret_cast<int*>(ws + p.off_conflict);
+  int32_t* src_row = reinterpret_cast<int32_t*>(ws + p.off_src);
   auto launch = [&](auto kernel) {
-    if (smem > 48 * 1024) FXII_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // grid-stride over row groups: 2048 resident threads per SM at most, two waves of blocks so that
-    // the tail of slow row groups is shared out
-    const int grid = (int)std::min<int64_t>(n_groups, (int64_t)num_sms() * (2048 / B) * 2);
     const int4* cn = reinterpret_cast<const int4*>(m->cell_nodes.p);
-    kernel<<<grid, B, smem, s>>>(m->wnodes.p, m->grid, m->cellgeo.p, m->x.p, cn, m->padding, sp->dofmap.p, rows->frames.p,
-                                 rows->table.p, rows->w.p, rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, nq,
-                                 (rows->kind != FXII_OP_POINTS) ? packet_mode() : 0, team,
-                                 scap, Nr, n_rows, rows->row_dofs.p, rows->cell.p, rows->ncoll.p, rows->points.p, rows->coo_cols.p,
-                                 rows->coo_vals.p, row_cnt, src_row, conflict, counters_dev);
+    kernel<<<p.grid, p.B, p.smem, s>>>(m->wnodes.p, m->grid, m->cellgeo.p, m->x.p, cn, m->padding, sp->dofmap.p, rows->frames.p,
+                                       rows->table.p, rows->w.p, rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, rows->nq,
+                                       (rows->kind != FXII_OP_POINTS) ? packet_mode() : 0, p.team, p.scap, rows->n_point_rows,
+                                       n_rows, rows->row_dofs.p, rows->cell.p, rows->ncoll.p, rows->points.p, rows->coo_cols.p,
+                                       rows->coo_vals.p, row_cnt, src_row, conflict, counters_dev);
     FXII_LAUNCHED(1);
     FXII_CUDA(cudaGetLastError());
   };
-  if (nd == 4) launch(pi_fused_kernel<4>);
+  if (sp->nd == 4) launch(pi_fused_kernel<4>);
   else launch(pi_fused_kernel<10>);
-  FXII_CUDA(cudaEventRecord(ev[1], s));
+  FXII_CUDA(cudaEventRecordWithFlags(ev[2], s, ev_flags));
+  size_t tb = p.scan_tmp_bytes;
+  FXII_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, tb, (const long long*)row_cnt, (long long*)indptr, (int64_t)(n_rows + 1), s));
+  launch_compact(sp, rows, ws, p, indptr, capacity, indices, values, s);
+  FXII_CUDA(cudaMemcpyAsync(&host_result->nnz, indptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  FXII_CUDA(cudaMemcpyAsync(&host_result->conflict, conflict, sizeof(int), cudaMemcpyDeviceToHost, s));
+  FXII_CUDA(cudaMemcpyAsync(&host_result->counters, counters_dev, sizeof(PiCounters), cudaMemcpyDeviceToHost, s));
+  FXII_CUDA(cudaEventRecordWithFlags(ev[3], s, ev_flags));
+}
+
+static void set_fused_attributes(const fxii_space* sp, const FusedPlan& p) {
+  auto set = [&](auto kernel) {
+    if (p.smem > 48 * 1024) FXII_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    // shared memory for all blocks the register file can hold (1024 threads at 64 registers), the rest stays L1
+    int carve = (int)((p.smem + 1024) * (1024 / p.B) * 100 / (228 * 1024)) + 1;
+    if (carve > 100) carve = 100;
+    FXII_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+  };
+  if (sp->nd == 4) set(pi_fused_kernel<4>);
+  else set(pi_fused_kernel<10>);
+}
+
+static void destroy_graph(fxii_rows* rows) {
+  if (rows->graph_exec) cudaGraphExecDestroy(rows->graph_exec);
+  rows->graph_exec = nullptr;
+}
+
+static bool graphs_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("FXII_GRAPH");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+// Fused build.  Returns false when the fused path cannot be used (caller falls back to the COO path).
+// First build on a handle: the nnz is read back before the CSR arrays are allocated (two host
+// synchronisations).  Later builds know the nnz of the previous one (`nnz_hint`): a single
+// synchronisation, and for small and medium workloads the whole sequence is replayed as ONE CUDA
+// graph launch into buffers owned by the handle (launch-bound regime: config 2 runs ~9 launches of
+// 5-50 us each), followed by device-to-device copies into the caller's exact-size CSR.
+static bool pi_assemble_fused(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr* out, PiCounters* h_counters,
+                              float* ms_frames, float* ms_locate, float* ms_csr) {
+  FusedPlan p;
+  if (!make_fused_plan(sp, rows, p)) return false;
+  const int64_t n_rows = rows->n_rows_total;
+  const int64_t E = rows->n_point_rows * rows->nq * sp->nd;
+  if (!rows->ev[0]) {
+    for (auto& e : rows->ev) FXII_CUDA(cudaEventCreate(&e));
+  }
+  if (!rows->host_result) FXII_CUDA(cudaMallocHost((void**)&rows->host_result, sizeof(FusedResult)));
+  FusedResult* hr = static_cast<FusedResult*>(rows->host_result);
+  cudaEvent_t* ev = rows->ev;
+  set_fused_attributes(sp, p);
+  bool moved = rows->ws.ensure((int64_t)p.ws_bytes, s);
+  moved |= rows->scan_tmp.ensure((int64_t)p.scan_tmp_bytes + 16, s);
   out->n_rows = n_rows;
   out->n_cols = sp->n_dofs;
-  out->indptr.alloc(n_rows + 1, s);
-  {
-    size_t tb = 0;
-    FXII_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, (const long long*)row_cnt, (long long*)out->indptr.p,
-                                            (int64_t)(n_rows + 1), s));
-    DevBuf<uint8_t> tmp;
-    tmp.alloc((int64_t)tb, s);
-    FXII_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, (const long long*)row_cnt, (long long*)out->indptr.p,
-                                            (int64_t)(n_rows + 1), s));
-  }
-  auto compact = [&](int64_t capacity) {
-    out->indices.alloc(capacity, s);
-    out->values.alloc(capacity, s);
-    if (capacity == 0) return;
-    int G = 4;
-    const int64_t avg = capacity / std::max<int64_t>(1, Nr);
-    while (G < 32 && G < avg) G <<= 1;
-    { compact_rows_kernel<<<grid_for(n_rows * G, 256, 8), 256, 0, s>>>(src_row, out->indptr.p, rows->coo_cols.p, rows->coo_vals.p,
-                                                                    nq * nd, n_rows, G, capacity, out->indices.p, out->values.p); FXII_LAUNCHED(1); }
-    FXII_CUDA(cudaGetLastError());
-  };
   const int64_t hint = rows->nnz_hint;
-  if (hint > 0) compact(hint);  // speculative: no host round trip before the copy
-  int64_t nnz = 0;
-  int h_conflict = 0;
-  FXII_CUDA(cudaMemcpyAsync(&nnz, out->indptr.p + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-  FXII_CUDA(cudaMemcpyAsync(&h_conflict, conflict, sizeof(int), cudaMemcpyDeviceToHost, s));
-  FXII_CUDA(cudaMemcpyAsync(h_counters, counters_dev, sizeof(PiCounters), cudaMemcpyDeviceToHost, s));
-  FXII_CUDA(cudaEventRecord(ev[2], s));
+  auto times = [&] {
+    *ms_frames = elapsed_ms(ev[0], ev[1]);
+    *ms_locate = elapsed_ms(ev[1], ev[2]);
+    *ms_csr = elapsed_ms(ev[2], ev[3]);
+  };
+  // ---- graph replay -------------------------------------------------------------------------------
+  if (hint > 0 && graphs_enabled() && E <= ((int64_t)1 << 26)) {
+    moved |= rows->g_indptr.ensure(n_rows + 1, s);
+    moved |= rows->g_indices.ensure(hint, s);
+    moved |= rows->g_values.ensure(hint, s);
+    if (moved || rows->buffers_moved || rows->graph_space != sp || rows->graph_stream != s || rows->graph_cap != hint) destroy_graph(rows);
+    rows->buffers_moved = false;
+    if (!rows->graph_exec) {
+      cudaGraph_t graph = nullptr;
+      // capture on a private stream: the caller's stream may be the legacy default stream, which cannot capture
+      if (!rows->capture_stream) FXII_CUDA(cudaStreamCreateWithFlags(&rows->capture_stream, cudaStreamNonBlocking));
+      cudaStream_t cs = rows->capture_stream;
+      FXII_CUDA(cudaStreamSynchronize(s));
+      FXII_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+      const int64_t launches_before = g_launches;
+      try {
+        enqueue_fused(sp, rows, p, cs, rows->ws.p, rows->scan_tmp.p, rows->g_indptr.p, rows->g_indices.p, rows->g_values.p, hint, hr, ev);
+      } catch (...) {
+        cudaStreamEndCapture(cs, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      FXII_CUDA(cudaStreamEndCapture(cs, &graph));
+      rows->graph_kernels = (int)(g_launches - launches_before);  // kernels of this library inside the graph
+      g_launches = launches_before;                                // captured, not launched
+      const cudaError_t e = cudaGraphInstantiate(&rows->graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        rows->graph_exec = nullptr;
+      }
+      rows->graph_space = sp;
+      rows->graph_stream = s;
+      rows->graph_cap = hint;
+    }
+    if (rows->graph_exec) {
+      FXII_CUDA(cudaGraphLaunch(rows->graph_exec, s));
+      FXII_LAUNCHED(rows->graph_kernels);
+      FXII_CUDA(cudaStreamSynchronize(s));
+      if (!hr->conflict && hr->nnz <= hint) {
+        out->nnz = hr->nnz;
+        out->indptr.alloc(n_rows + 1, s);
+        out->indices.alloc(hr->nnz, s);
+        out->values.alloc(hr->nnz, s);
+        FXII_CUDA(cudaMemcpyAsync(out->indptr.p, rows->g_indptr.p, sizeof(int64_t) * (size_t)(n_rows + 1), cudaMemcpyDeviceToDevice, s));
+        if (hr->nnz) {
+          FXII_CUDA(cudaMemcpyAsync(out->indices.p, rows->g_indices.p, sizeof(int32_t) * (size_t)hr->nnz, cudaMemcpyDeviceToDevice, s));
+          FXII_CUDA(cudaMemcpyAsync(out->values.p, rows->g_values.p, sizeof(double) * (size_t)hr->nnz, cudaMemcpyDeviceToDevice, s));
+        }
+        *h_counters = hr->counters;
+        rows->nnz_hint = hr->nnz;
+        rows->last_graph = true;
+        times();
+        return true;
+      }
+      destroy_graph(rows);  // the matrix outgrew the hint (or the inputs changed): rebuild directly
+    }
+  }
+  // ---- direct enqueue -----------------------------------------------------------------------------
+  rows->last_graph = false;
+  out->indptr.alloc(n_rows + 1, s);
+  if (hint > 0) {  // speculative: the CSR arrays exist before the kernels run, no host round trip
+    out->indices.alloc(hint, s);
+    out->values.alloc(hint, s);
+  }
+  enqueue_fused(sp, rows, p, s, rows->ws.p, rows->scan_tmp.p, out->indptr.p, out->indices.p, out->values.p, hint, hr, ev);
   FXII_CUDA(cudaStreamSynchronize(s));
-  if (h_conflict) return false;  // K dofs shared between point rows: the general path handles first-visit-wins
-  out->nnz = nnz;
-  if (hint <= 0 || nnz > hint) {
-    compact(nnz);
-    FXII_CUDA(cudaEventRecord(ev[2], s));
+  *h_counters = hr->counters;
+  if (hr->conflict) return false;  // K dofs shared between point rows: the general path handles first-visit-wins
+  out->nnz = hr->nnz;
+  if (hint <= 0 || hr->nnz > hint) {
+    out->indices.alloc(hr->nnz, s);
+    out->values.alloc(hr->nnz, s);
+    launch_compact(sp, rows, rows->ws.p, p, out->indptr.p, hr->nnz, out->indices.p, out->values.p, s);
+    FXII_CUDA(cudaEventRecord(ev[3], s));
     FXII_CUDA(cudaStreamSynchronize(s));
   }
-  rows->nnz_hint = nnz;
-  *ms_locate = elapsed_ms(ev[0], ev[1]);
-  *ms_csr = elapsed_ms(ev[1], ev[2]);
+  rows->nnz_hint = hr->nnz;
+  times();
   return true;
 }
 
@@ -1215,35 +1361,33 @@ void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr
   rows->nd = nd;
   cudaEvent_t ev[4];
   for (auto& e : ev) FXII_CUDA(cudaEventCreate(&e));
-  FXII_CUDA(cudaEventRecord(ev[0], s));
-  if (rows->kind != FXII_OP_POINTS) {
-    rows->frames.alloc(kFrame * Nr, s);
-    if (Nr > 0) {
-      { row_frames_kernel<<<grid_for(Nr, 128, 16), 128, 0, s>>>(rows->gx.p, rows->gcells.p, rows->cells_k.p, rows->xref.p,
-                                                              rows->nip, rows->radius.p, rows->radius_per_row, rows->kind,
-                                                              Nr, rows->frames.p); FXII_LAUNCHED(1); }
-      FXII_CUDA(cudaGetLastError());
-    }
+  // per-build buffers keep their addresses while their sizes do not change (a captured graph refers to them)
+  bool moved = false;
+  if (rows->kind != FXII_OP_POINTS) moved |= rows->frames.ensure(kFrame * Nr, s);
+  moved |= rows->cell.ensure(Np, s);
+  moved |= rows->ncoll.ensure(Np, s);
+  if (keep_points) moved |= rows->points.ensure(3 * Np, s);
+  else if (rows->points.p) {
+    rows->points.release();
+    moved = true;
   }
-  FXII_CUDA(cudaEventRecord(ev[1], s));
-  rows->cell.alloc(Np, s);
-  rows->ncoll.alloc(Np, s);
-  if (keep_points) rows->points.alloc(3 * Np, s);
-  else rows->points.release();
-  rows->coo_cols.alloc(E, s);  // COO (unfused) or per-row staging (fused)
-  rows->coo_vals.alloc(E, s);
+  moved |= rows->coo_cols.ensure(E, s);  // COO (unfused) or per-row staging (fused)
+  moved |= rows->coo_vals.ensure(E, s);
+  rows->buffers_moved |= moved;
   DevBuf<PiCounters> counters;
   PiCounters h;
   memset(&h, 0, sizeof(h));
   const size_t tab_smem = (rows->kind == FXII_OP_CIRCLE || rows->kind == FXII_OP_DISK) ? sizeof(double) * 4 * (size_t)nq : 0;
   FXII_CHECK(tab_smem <= 48 * 1024, "operator table too large for shared memory (nq > 1536)");
-  float ms_count = 0.f, ms_fill = 0.f, ms_loc_f = 0.f, ms_csr_f = 0.f;
+  float ms_count = 0.f, ms_fill = 0.f, ms_fr_f = 0.f, ms_loc_f = 0.f, ms_csr_f = 0.f;
   bool fused = false;
-  if (rows->mode != 1) fused = pi_assemble_fused(sp, rows, s, out, &h, &ms_loc_f, &ms_csr_f);
+  if (rows->mode != 1) fused = pi_assemble_fused(sp, rows, s, out, &h, &ms_fr_f, &ms_loc_f, &ms_csr_f);
   rows->last_fused = fused;
   if (!fused) {
     counters.alloc(1, s);
     FXII_CUDA(cudaMemsetAsync(counters.p, 0, sizeof(PiCounters), s));
+    FXII_CUDA(cudaEventRecord(ev[0], s));
+    launch_frames(rows, s);
     FXII_CUDA(cudaEventRecord(ev[1], s));
     if (Np > 0) {
       const int threads = 128;
@@ -1275,12 +1419,12 @@ void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr
     stats->n_not_found = (int64_t)h.not_found;
     stats->n_ties = (int64_t)h.ties;
     stats->n_fallback = (int64_t)h.fallback;
-    stats->ms_frames = elapsed_ms(ev[0], ev[1]);
+    stats->ms_frames = fused ? ms_fr_f : elapsed_ms(ev[0], ev[1]);
     stats->ms_locate = fused ? ms_loc_f : elapsed_ms(ev[1], ev[2]);
     stats->ms_csr = fused ? ms_csr_f : elapsed_ms(ev[2], ev[3]);
     stats->ms_csr_count = ms_count;
     stats->ms_csr_fill = ms_fill;
-    stats->fused = fused ? 1 : 0;
+    stats->fused = fused ? (rows->last_graph ? 2 : 1) : 0;
   }
   for (auto& e : ev) cudaEventDestroy(e);
   if (h.not_found > 0)

@@ -110,7 +110,8 @@ typedef struct {
   int64_t n_fallback;   /* points assigned by the nearest-cell fallback */
   float ms_frames, ms_locate, ms_csr; /* device time of the three stages (CUDA events) */
   float ms_csr_count, ms_csr_fill;    /* the two row kernels inside ms_csr (COO path) */
-  int32_t fused;                      /* 1: rows were reduced inside the locate kernel (no COO in HBM) */
+  int32_t fused;                      /* 1: rows were reduced inside the locate kernel (no COO in HBM);
+                                         2: same, replayed as one CUDA graph launch */
 } fxii_pi_stats;
 
 /* Builds Π (n_rows_total x n_dofs).  Leaves per-point diagnostics on `rows`

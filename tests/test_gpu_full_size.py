@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 def test_config2_full_size_against_oracle(cuda):
     mesh, V, gamma, K, op, _ = build_workload(CONFIGS[2], 0, pinned=False)
     A, _, _ = create_interpolation_matrix(V, K, op)
-    assert A.stats["fused"] == 1 and A.stats["n_points"] == 60_000
+    assert A.stats["fused"] >= 1 and A.stats["n_points"] == 60_000
     ref = oracle_pi(V, K, gamma, "trace")
     cell, ncoll = A.rows.diagnostics()
     np.testing.assert_array_equal(cell, ref["cell"])
@@ -34,7 +34,7 @@ def test_config2_full_size_against_oracle(cuda):
 
 def _check_properties(A, B, gamma, K, n_dofs):
     """A: default (fused) build, B: COO-path build of the same Π."""
-    assert A.stats["fused"] == 1 and B.stats["fused"] == 0
+    assert A.stats["fused"] >= 1 and B.stats["fused"] == 0
     ia, ja, va = A.device.to_host()
     ib, jb, vb = B.device.to_host()
     np.testing.assert_array_equal(ia, ib)

@@ -157,3 +157,29 @@ def test_fused_p2_disk_many_points(cuda):
     K = functionspace(gamma, ("Quadrature", 2))
     run_case(V, K, gamma, "disk", 0.12, 11, expect_fused=True)  # 121 points per row
     run_case(V, K, gamma, "disk", 0.12, 17, expect_fused=False)  # 289 points per row: COO path
+
+
+@pytest.mark.parametrize("op_name,radius,degree,p", [("trace", None, None, 1), ("circle", 0.05, 15, 1), ("disk", 0.06, 5, 2)])
+def test_repeated_builds_on_one_handle(cuda, op_name, radius, degree, p):
+    """Build 1 reads the nnz back before allocating; build 2+ know it (one host sync) and are
+    replayed as one CUDA graph launch.  All builds must be bitwise identical."""
+    from fenicsx_ii_b200.interpolation import device_rows, device_space
+
+    mesh, V = small_cfg(8, 8, 8, degree=p)
+    gamma = sy.polyline_network(200, 1 / 8, n_lines=4, lo=0.25, hi=0.75)
+    K = functionspace(gamma, ("Quadrature", 6))
+    op = make_operator(op_name, gamma, radius, degree)
+    ds = device_space(V)
+    rows = device_rows(K, op)
+    results, modes = [], []
+    for _ in range(4):
+        csr, st = rows.assemble(ds)
+        results.append(csr.to_host())
+        modes.append(st["fused"])
+    assert modes[0] == 1 and modes[1:] == [2, 2, 2]
+    for r in results[1:]:
+        np.testing.assert_array_equal(r[0], results[0][0])
+        np.testing.assert_array_equal(r[1], results[0][1])
+        assert r[2].tobytes() == results[0][2].tobytes()
+    ref = oracle_pi(V, K, gamma, op_name, radius, degree)
+    assert_csr_parity(results[-1], ref)
