@@ -304,8 +304,14 @@ def run_ours(args):
     dom = max(cands, key=lambda k: cands[k][1])
     dom_bytes, dom_ms = cands[dom]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    traffic = None
+    try:  # per-launch DRAM bytes of the dominant kernel from the committed ncu capture of this workload
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            traffic = json.load(f).get(f"cfg{args.config}", {}).get(dom) if args.scale == 1.0 else None
+    except Exception:
+        traffic = None
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
                 "stages_ms": {k: v / args.steps for k, v in stage.items()},
                 "all": {k: {"GB/s": (b / (ms * 1e-3) / 1e9 if ms > 0 else 0.0), "ms": ms} for k, (b, ms) in cands.items()}}

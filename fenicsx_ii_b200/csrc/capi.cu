@@ -230,7 +230,6 @@ int fxii_rows_create(const double* gx, int64_t n_gnodes, const int32_t* gcells, 
     auto* r = new fxii_rows();
     cudaStream_t s = S(stream);
     try {
-      fxii::init_pool_once();
       r->kind = kind;
       r->nq = nq;
       r->nip = nip;
@@ -264,7 +263,6 @@ int fxii_rows_create_points(const double* points, const double* weights, const d
     auto* r = new fxii_rows();
     cudaStream_t s = S(stream);
     try {
-      fxii::init_pool_once();
       r->kind = FXII_OP_POINTS;
       r->nq = nq;
       r->nip = 1;
@@ -351,7 +349,6 @@ int fxii_rows_download_coo(const fxii_rows* rows, int32_t* cols, double* vals, v
 static fxii_csr* csr_from(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* indptr, const int32_t* indices,
                           const double* values, cudaMemcpyKind kind, cudaStream_t s) {
   FXII_CHECK(n_rows >= 0 && n_cols >= 0 && nnz >= 0 && indptr, "bad CSR arguments");
-  fxii::init_pool_once();
   auto* c = new fxii_csr();
   try {
     c->n_rows = n_rows;

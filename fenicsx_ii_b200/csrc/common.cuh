@@ -96,8 +96,6 @@ struct DevBuf {
   ~DevBuf() { release(); }
 };
 
-void init_pool_once();
-
 // FXII_TRACE=1: print host wall time between marks (each mark synchronises the stream)
 struct Trace {
   bool on;

@@ -29,12 +29,6 @@ expand_rows_kernel(const int64_t* __restrict__ indptr, int64_t n_rows, int32_t* 
 }
 
 __global__ void __launch_bounds__(256)
-col_hist_kernel(const int32_t* __restrict__ indices, int64_t nnz, unsigned long long* __restrict__ count) {
-  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x)
-    atomicAdd(&count[indices[k]], 1ULL);
-}
-
-__global__ void __launch_bounds__(256)
 gather_transposed_kernel(const int32_t* __restrict__ perm, const int32_t* __restrict__ row_of,
                          const double* __restrict__ values, int64_t nnz, int32_t* __restrict__ t_indices,
                          double* __restrict__ t_values) {

@@ -316,19 +316,6 @@ collapse_wide_kernel(const BvhNode* __restrict__ nodes, int n_internal, SceneGri
 using namespace fxii;
 
 namespace fxii {
-void init_pool_once() {
-  static bool done = false;
-  if (done) return;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return;
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-    uint64_t thr = UINT64_MAX;  // keep freed blocks cached: repeated Π builds reuse them
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-  }
-  done = true;
-}
-
 // height of the tree = longest root-to-leaf path; computed by one more bottom-up pass
 __global__ void __launch_bounds__(256)
 depth_kernel(const BvhNode* __restrict__ nodes, const int32_t* __restrict__ leaf_parent, int n, int32_t* max_depth) {
@@ -369,7 +356,6 @@ static void finish_wide(fxii_mesh* m, DevBuf<BvhNode>& bnodes, DevBuf<unsigned l
 
 void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* cell_nodes, int64_t n_cells,
                 double padding, cudaStream_t s) {
-  init_pool_once();
   FXII_CHECK(n_cells >= 1 && n_nodes >= 4, "mesh needs at least one tetrahedron");
   FXII_CHECK(n_cells < (int64_t)1 << 31, "n_cells must fit int32");
   m->n_cells = n_cells;

@@ -183,3 +183,56 @@ def test_repeated_builds_on_one_handle(cuda, op_name, radius, degree, p):
         assert r[2].tobytes() == results[0][2].tobytes()
     ref = oracle_pi(V, K, gamma, op_name, radius, degree)
     assert_csr_parity(results[-1], ref)
+
+
+def test_single_tetrahedron_mesh(cuda):
+    """Smallest possible Ω: the LBVH is one leaf."""
+    from fenicsx_ii_b200.mesh import Mesh
+
+    x = np.array([[0.0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]])
+    mesh = Mesh(x, np.array([[0, 1, 2, 3]]), tdim=3)
+    V = functionspace(mesh, ("Lagrange", 1))
+    gamma = sy.line_mesh(np.array([[0.1, 0.1, 0.1], [0.2, 0.25, 0.3], [0.3, 0.2, 0.35]]))
+    K = functionspace(gamma, ("DG", 2))
+    A, ref = run_case(V, K, gamma, "trace", expect_fused=True)
+    assert (ref["cell"] == 0).all()
+    run_case(V, K, gamma, "circle", 0.03, 9, expect_fused=True)
+
+
+@pytest.mark.parametrize("direction", [(0, 0, 1), (0, 0, -1), (1, 0, 0), (1e-9, 0, 1), (0.3, -0.5, 0.8)])
+def test_tangent_directions_including_ez(cuda, direction):
+    """rotation_matrix special case: the axis falls back to ez when ez x n vanishes (quadrature.py:46-51)."""
+    mesh, V = small_cfg(6, 6, 6)
+    d = np.array(direction, dtype=float)
+    d /= np.linalg.norm(d)
+    start = np.array([0.41, 0.47, 0.39])
+    nodes = start[None, :] + np.linspace(0, 0.2, 5)[:, None] * d[None, :] * np.array([1.0, 1.0, 1.0])
+    gamma = sy.line_mesh(nodes)
+    K = functionspace(gamma, ("Quadrature", 4))
+    run_case(V, K, gamma, "circle", 0.11, 11, expect_fused=True)
+    run_case(V, K, gamma, "disk", 0.11, 4, expect_fused=True)
+
+
+def test_points_on_domain_boundary_and_vertices(cuda):
+    """Γ running along a boundary edge of Ω and through mesh vertices: maximal tie sets."""
+    mesh, V = small_cfg(4, 4, 4)
+    nodes = np.array([[0.0, 0.0, 0.0], [0.0, 0.0, 0.25], [0.0, 0.0, 0.5], [0.25, 0.25, 0.75], [0.5, 0.5, 1.0]])
+    gamma = sy.line_mesh(nodes)
+    K = functionspace(gamma, ("Lagrange", 1))  # dofs at mesh vertices, shared between segments
+    A, ref = run_case(V, K, gamma, "trace", expect_fused=False)
+    assert ref["n_colliding"].max() >= 6
+
+
+def test_circle_leaving_the_domain_raises(cuda):
+    from fenicsx_ii_b200 import Circle
+    from fenicsx_ii_b200._lib import PointsNotFound
+
+    mesh, V = small_cfg(4, 4, 4)
+    gamma = sy.line_mesh(np.array([[0.5, 0.05, 0.2], [0.5, 0.05, 0.8]]))
+    K = functionspace(gamma, ("DG", 1))
+    with pytest.raises(PointsNotFound):
+        create_interpolation_matrix(V, K, Circle(gamma, 0.2, degree=9))
+    try:
+        create_interpolation_matrix(V, K, Circle(gamma, 0.2, degree=9))
+    except AssertionError as e:  # PointsNotFound is an AssertionError, like the reference's assert
+        assert "points lie in no cell" in str(e)

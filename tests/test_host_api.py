@@ -1,0 +1,67 @@
+"""CPU: host-side mirror of the reference interface (names, validation, quadrature contract)."""
+
+import numpy as np
+import pytest
+
+import fenicsx_ii_b200 as fx
+from fenicsx_ii_b200 import synthetic as sy
+from fenicsx_ii_b200.mesh import functionspace
+from tests.helpers import small_cfg
+
+
+def test_exports_reference_names():
+    for name in ("Circle", "Disk", "PointwiseTrace", "MappedRestriction", "ReductionOperator", "Quadrature",
+                 "create_interpolation_matrix"):
+        assert hasattr(fx, name)
+
+
+def test_operator_validation_errors_match_reference():
+    """restriction_operators.py:99-106,229-233: same exceptions for the same misuse (host-side, no GPU)."""
+    from fenicsx_ii_b200 import Circle, Disk
+
+    mesh, V = small_cfg(2, 2, 2)
+    gamma = sy.straight_line(3)
+    with pytest.raises(ValueError):
+        Circle(gamma, 0.1, degree=2)
+    with pytest.raises(ValueError):
+        Circle(mesh, 0.1)
+    with pytest.raises(ValueError):
+        Disk(mesh, 0.1)
+    gamma.geometry.cmap.degree = 2
+    with pytest.raises(NotImplementedError):
+        Circle(gamma, 0.1)
+    with pytest.raises(NotImplementedError):
+        Disk(gamma, 0.1)
+
+
+def test_compute_quadrature_contract_shapes():
+    """ReductionOperator.compute_quadrature: points [Nr,nq,3] (trace: [Nr,3]), weights [Nr,nq], scales [Nr]
+    (restriction_operators.py:17-47, quadrature.py:11-20)."""
+    gamma = sy.polyline_network(10, 0.1, n_lines=2, lo=0.3, hi=0.7)
+    X = np.array([[0.25], [0.75]])
+    cells = np.arange(4, dtype=np.int32)
+    q = fx.PointwiseTrace(gamma).compute_quadrature(cells, X)
+    assert q.points.shape == (8, 3) and q.weights.shape == (8, 1) and q.scales.shape == (8,)
+    c = fx.Circle(gamma, 0.05, degree=5)
+    q = c.compute_quadrature(cells, X)
+    assert c.num_points == 3 and q.points.shape == (8, 3, 3) and q.weights.shape == (8, 3) and q.scales.shape == (8,)
+    np.testing.assert_allclose(q.weights.sum(axis=1) / q.scales, 1.0, rtol=1e-14)
+    np.testing.assert_allclose(np.linalg.norm(q.points - q.points.mean(axis=1, keepdims=True) * 0 - fx.restriction_operators
+                                              .get_physical_points(gamma, cells, X)[:, None, :], axis=2), 0.05, rtol=1e-12)
+    d = fx.Disk(gamma, lambda x: 0.02 + 0 * x[0], degree=3)
+    q = d.compute_quadrature(cells, X)
+    assert d.num_points == 9 and q.points.shape == (8, 9, 3)
+    np.testing.assert_allclose(q.weights.sum(axis=1) / q.scales, 1.0, rtol=1e-14)
+    assert str(fx.PointwiseTrace(gamma)).startswith("PointwiseTrace(")
+
+
+def test_functionspace_standins():
+    mesh, V = small_cfg(3, 3, 3, degree=2)
+    assert V.dofmap.list.shape == (162, 10) and V.num_dofs == 7**3
+    V2 = functionspace(mesh, ("Lagrange", 2))
+    assert V2.num_dofs == V.num_dofs  # generic edge numbering agrees in count with the closed form
+    gamma = sy.straight_line(5)
+    assert functionspace(gamma, ("Quadrature", 10)).element.interpolation_points.shape == (6, 1)
+    assert functionspace(gamma, ("Lagrange", 2)).num_dofs == 5 + 4
+    with pytest.raises(NotImplementedError):
+        functionspace(mesh, ("Lagrange", 3))
