@@ -118,8 +118,9 @@ struct alignas(16) BvhNode {  // 64 B: both child boxes live in the parent
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
 
-// 4-wide node, 64 B: the four grandchildren of a binary LBVH node with boxes quantised to 16 bits on
-// the scene grid (rounded outward).  lo[a][k] / hi[a][k]: axis a, slots (2k, 2k+1) packed as two
+// 4-wide node, 64 B: the four grandchildren of a binary LBVH node with boxes quantised to 15 bits on
+// the scene grid (rounded outward); hi halfwords carry bit 15 set so that two halfword compares are one
+// 32-bit subtraction (SWAR).  lo[a][k] / hi[a][k]: axis a, slots (2k, 2k+1) packed as two
 // halfwords.  child >= 0: wide node index; child < 0: leaf, cell = ~child.  Empty slot: lo > hi.
 struct alignas(16) WideNode {
   uint32_t lo[3][2];
@@ -128,7 +129,7 @@ struct alignas(16) WideNode {
 };
 static_assert(sizeof(WideNode) == 64, "WideNode must be 64 bytes");
 
-// scene grid of the quantised boxes: q(x) = floor((x - origin) * scale), clamped to [0, 65535]
+// scene grid of the quantised boxes: q(x) = floor((x - origin) * scale), clamped to [0, 32767]
 struct SceneGrid {
   double origin[3];
   double scale[3];

@@ -246,7 +246,7 @@ refit_kernel(const double* __restrict__ x, const int4* __restrict__ cell_nodes, 
 // ---- 4-wide collapse --------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t quant(double v, double origin, double scale) {
   const double q = floor((v - origin) * scale);  // monotone in v: conservative for lo and hi alike
-  return (uint32_t)fmin(fmax(q, 0.0), 65535.0);
+  return (uint32_t)fmin(fmax(q, 0.0), 32767.0);
 }
 
 struct Slot {
@@ -294,7 +294,7 @@ collapse_wide_kernel(const BvhNode* __restrict__ nodes, int n_internal, SceneGri
         slots[k].child = -1;
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-          slots[k].lo[a] = 65535u;
+          slots[k].lo[a] = 32767u;
           slots[k].hi[a] = 0u;
         }
       }
@@ -304,8 +304,9 @@ collapse_wide_kernel(const BvhNode* __restrict__ nodes, int n_internal, SceneGri
     for (int a = 0; a < 3; ++a) {
       w.lo[a][0] = slots[0].lo[a] | (slots[1].lo[a] << 16);
       w.lo[a][1] = slots[2].lo[a] | (slots[3].lo[a] << 16);
-      w.hi[a][0] = slots[0].hi[a] | (slots[1].hi[a] << 16);
-      w.hi[a][1] = slots[2].hi[a] | (slots[3].hi[a] << 16);
+      // hi is stored with bit 15 of each halfword set: (hi|0x8000) - q keeps that bit iff q <= hi
+      w.hi[a][0] = (slots[0].hi[a] | (slots[1].hi[a] << 16)) | 0x80008000u;
+      w.hi[a][1] = (slots[2].hi[a] | (slots[3].hi[a] << 16)) | 0x80008000u;
     }
     wide[i] = w;
   }
@@ -347,7 +348,7 @@ static void finish_wide(fxii_mesh* m, DevBuf<BvhNode>& bnodes, DevBuf<unsigned l
     const double ext = (hi - lo) + 2.0 * m->padding;
     const double margin = m->padding + 1e-6 * ext + 1e-300;
     m->grid.origin[a] = lo - margin;
-    m->grid.scale[a] = 65535.0 / (ext + 2.0 * margin);
+    m->grid.scale[a] = 32767.0 / (ext + 2.0 * margin);
   }
   { collapse_wide_kernel<<<grid_for(n_internal, 256, 8), 256, 0, s>>>(bnodes.p, n_internal, m->grid, m->wnodes.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());

@@ -270,16 +270,16 @@ __device__ __forceinline__ LocateResult finish_locate(const LocateState& st, dou
 // for the two-slot SIMD compares.  q() is the same monotone map the builder applied to the box
 // corners, so a point inside a (fp32, outward-rounded) box is always inside its quantised box.
 struct QPoint {
-  uint32_t x2, y2, z2;
+  uint32_t x2, y2, z2;  // coordinate | 0x8000 in both halfwords
 };
 __device__ __forceinline__ QPoint quantise_point(const SceneGrid& g, const double* p, bool active) {
   QPoint q;
   uint32_t v[3];
 #pragma unroll
-  for (int a = 0; a < 3; ++a) v[a] = (uint32_t)fmin(fmax(floor((p[a] - g.origin[a]) * g.scale[a]), 0.0), 65535.0);
-  q.x2 = v[0] | (v[0] << 16);
-  q.y2 = v[1] | (v[1] << 16);
-  q.z2 = v[2] | (v[2] << 16);
+  for (int a = 0; a < 3; ++a) v[a] = (uint32_t)fmin(fmax(floor((p[a] - g.origin[a]) * g.scale[a]), 0.0), 32767.0);
+  q.x2 = (v[0] | (v[0] << 16)) | 0x80008000u;
+  q.y2 = (v[1] | (v[1] << 16)) | 0x80008000u;
+  q.z2 = (v[2] | (v[2] << 16)) | 0x80008000u;
   (void)active;
   return q;
 }
@@ -287,18 +287,20 @@ __device__ __forceinline__ QPoint quantise_point(const SceneGrid& g, const doubl
 // one 64 B wide node: hit flags of its four slots
 struct WideHit {
   int4 child;
-  uint32_t m01, m23;  // halfword masks: slots (0,1) and (2,3)
+  uint32_t m01, m23;  // bit 15 / bit 31: slots (0,1) and (2,3)
 };
+// 15-bit coordinates, two per word.  For halfwords a, b < 0x8000: bit 15 of ((b | 0x8000) - a) is set
+// iff a <= b, and the subtraction never borrows across halfwords — so one 32-bit SUB compares two slots.
+// The point carries the 0x8000 bits for `lo <= q`, the stored hi carries them for `q <= hi`.
 __device__ __forceinline__ WideHit load_test_node(const WideNode* __restrict__ nodes, int node, const QPoint& q) {
   const uint4* wp = reinterpret_cast<const uint4*>(nodes + node);
   // a = lo_x01 lo_x23 lo_y01 lo_y23 ; b = lo_z01 lo_z23 hi_x01 hi_x23 ; c = hi_y01 hi_y23 hi_z01 hi_z23
   const uint4 a = __ldg(wp), b = __ldg(wp + 1), c = __ldg(wp + 2);
   WideHit h;
   h.child = __ldg(reinterpret_cast<const int4*>(wp + 3));
-  h.m01 = __vcmpleu2(a.x, q.x2) & __vcmpleu2(a.z, q.y2) & __vcmpleu2(b.x, q.z2) & __vcmpleu2(q.x2, b.z) &
-          __vcmpleu2(q.y2, c.x) & __vcmpleu2(q.z2, c.z);
-  h.m23 = __vcmpleu2(a.y, q.x2) & __vcmpleu2(a.w, q.y2) & __vcmpleu2(b.y, q.z2) & __vcmpleu2(q.x2, b.w) &
-          __vcmpleu2(q.y2, c.y) & __vcmpleu2(q.z2, c.w);
+  const uint32_t qx = q.x2 & 0x7fff7fffu, qy = q.y2 & 0x7fff7fffu, qz = q.z2 & 0x7fff7fffu;
+  h.m01 = (q.x2 - a.x) & (q.y2 - a.z) & (q.z2 - b.x) & (b.z - qx) & (c.x - qy) & (c.z - qz) & 0x80008000u;
+  h.m23 = (q.x2 - a.y) & (q.y2 - a.w) & (q.z2 - b.y) & (b.w - qx) & (c.y - qy) & (c.w - qz) & 0x80008000u;
   return h;
 }
 
@@ -855,9 +857,20 @@ void coo_segments_to_csr(const int32_t* row_dofs, int64_t n_point_rows, int64_t 
 // then one scan and a compaction kernel produce the CSR.  Summation order differs from the
 // unfused path only in association (per cell first); it is fixed, so results are reproducible.
 // =================================================================================================
+// Barrier of one team.  Multi-warp teams use named barriers with COMPILE-TIME ids: a register id makes
+// ptxas reserve all 16 hardware barriers for the CTA, which capped residency at 4 CTAs per SM
+// (measured: 24 % achieved occupancy instead of 50 %).  At most 4 multi-warp teams fit a block.
 __device__ __forceinline__ void team_sync(int team, int team_id) {
-  if (team <= 32) __syncwarp();
-  else asm volatile("bar.sync %0, %1;" ::"r"(team_id + 1), "r"(team) : "memory");
+  if (team <= 32) {
+    __syncwarp();
+    return;
+  }
+  switch (team_id) {
+    case 0: asm volatile("bar.sync 1, %0;" ::"r"(team) : "memory"); break;
+    case 1: asm volatile("bar.sync 2, %0;" ::"r"(team) : "memory"); break;
+    case 2: asm volatile("bar.sync 3, %0;" ::"r"(team) : "memory"); break;
+    default: asm volatile("bar.sync 4, %0;" ::"r"(team) : "memory"); break;
+  }
 }
 
 // exclusive prefix of a flag over the threads of a team (+ team total); two team barriers for
@@ -905,8 +918,8 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
   double* s_tab = reinterpret_cast<double*>(s_raw);
   double* s_val = s_tab + 4 * (size_t)nq;
   double* s_eval = s_val + (size_t)B * ND;
-  uint64_t* s_ekey = reinterpret_cast<uint64_t*>(s_eval + (size_t)B * ND);
-  int32_t* s_cell = reinterpret_cast<int32_t*>(s_ekey + (size_t)rpb * scap);
+  uint64_t* s_ekey = reinterpret_cast<uint64_t*>(s_eval + (size_t)B * ND + 2 * (size_t)rpb);
+  int32_t* s_cell = reinterpret_cast<int32_t*>(s_ekey + (size_t)rpb * (scap + 2));
   int* s_wcnt = s_cell + B;
   if (kind == FXII_OP_CIRCLE || kind == FXII_OP_DISK) {
     for (int k = threadIdx.x; k < nq; k += B) {
@@ -921,8 +934,9 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
   const int team_id = tid / team;
   const int l = tid - team_id * team;
   const int t0 = team_id * team;           // first thread of the team
-  uint64_t* ekey = s_ekey + (size_t)team_id * scap;
-  double* eval = s_eval + (size_t)t0 * ND;
+  // team regions are padded by two entries: power-of-two strides would put the teams of a warp on the same banks
+  uint64_t* ekey = s_ekey + (size_t)team_id * (scap + 2);
+  double* eval = s_eval + (size_t)team_id * ((size_t)team * ND + 2);
   const int seg = nq * ND;
   const bool in_team = team_id < rpb;      // threads beyond the last whole team idle (B % team != 0 never happens)
   const int64_t n_groups = (n_point_rows + rpb - 1) / rpb;
@@ -1132,8 +1146,8 @@ static bool make_fused_plan(const fxii_space* sp, const fxii_rows* rows, FusedPl
   p.rpb = p.B / p.team;
   p.scap = 2;
   while (p.scap < (uint32_t)p.team * nd) p.scap <<= 1;
-  p.smem = sizeof(double) * (4 * (size_t)nq + 2 * (size_t)p.B * nd) + sizeof(uint64_t) * (size_t)p.rpb * p.scap +
-           sizeof(int32_t) * (size_t)(p.B + p.B / 32 + 1);
+  p.smem = sizeof(double) * (4 * (size_t)nq + 2 * (size_t)p.B * nd + 2 * (size_t)p.rpb) +
+           sizeof(uint64_t) * (size_t)p.rpb * (p.scap + 2) + sizeof(int32_t) * (size_t)(p.B + p.B / 32 + 1);
   if (p.smem > 200 * 1024) return false;
   const int64_t n_groups = (Nr + p.rpb - 1) / p.rpb;
   // grid-stride over row groups: 2048 resident threads per SM at most, two waves of blocks so that
