@@ -13,7 +13,8 @@ from pathlib import Path
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-_LIB_PATH = _HERE / "csrc" / "libfxii.so"
+# FXII_LIB: load a differently tuned build of the same ABI (kernel A/B experiments)
+_LIB_PATH = Path(os.environ["FXII_LIB"]) if os.environ.get("FXII_LIB") else _HERE / "csrc" / "libfxii.so"
 
 FXII_OK = 0
 FXII_E_INVALID = -1

@@ -214,6 +214,7 @@ struct LocateState {
   int ncoll = 0;
   int fb_cell = -1;       // nearest non-colliding candidate (fallback)
   double fb_d2 = 1e300;
+  bool done = false;      // the point is strictly inside a cell: the colliding set is final
 };
 
 // Leaf test of one candidate cell (dolfinx compute_first_colliding_cell semantics).
@@ -225,20 +226,29 @@ __device__ __forceinline__ void test_cell(const double* __restrict__ cellgeo, co
   double X[3];
   pull_back(g, p, X);
   const double l0 = ((1.0 - X[0]) - X[1]) - X[2];
+  // squared gradient norms of the barycentric coordinates (grad lambda_1..3 = rows of K,
+  // grad lambda_0 = -(row0+row1+row2)): |lambda_i| / |grad lambda_i| is the distance to face plane i
+  const double s0 = (g.K[0] + g.K[3]) + g.K[6], s1 = (g.K[1] + g.K[4]) + g.K[7], s2 = (g.K[2] + g.K[5]) + g.K[8];
+  const double t0 = tau2 * ((s0 * s0 + s1 * s1) + s2 * s2);
+  const double t1 = tau2 * ((g.K[0] * g.K[0] + g.K[1] * g.K[1]) + g.K[2] * g.K[2]);
+  const double t2 = tau2 * ((g.K[3] * g.K[3] + g.K[4] * g.K[4]) + g.K[5] * g.K[5]);
+  const double t3 = tau2 * ((g.K[6] * g.K[6] + g.K[7] * g.K[7]) + g.K[8] * g.K[8]);
   if (l0 >= 0 && X[0] >= 0 && X[1] >= 0 && X[2] >= 0) {
     st.best = min(st.best, cell);
     ++st.ncoll;
+    // Strictly inside by more than tau from every face plane: cells of a mesh have disjoint
+    // interiors, so every other cell is farther than tau from the point and can neither collide
+    // nor win the tie-break — the search is complete (colliding set = {cell}).
+    st.done = st.ncoll == 1 && l0 * l0 > t0 && X[0] * X[0] > t1 && X[1] * X[1] > t2 && X[2] * X[2] > t3;
     return;
   }
   // Quick reject without touching the vertices: the distance to the tetrahedron is at least the
-  // distance to the plane of any face the point is outside of, -lambda_i / |grad lambda_i|
-  // (grad lambda_1..3 = rows of K, grad lambda_0 = -(row0+row1+row2)).  Cells farther than
+  // distance to the plane of any face the point is outside of.  Cells farther than
   // tau = max(collision distance, padding) can neither collide nor serve as fallback.
-  const double s0 = (g.K[0] + g.K[3]) + g.K[6], s1 = (g.K[1] + g.K[4]) + g.K[7], s2 = (g.K[2] + g.K[5]) + g.K[8];
-  bool far = (l0 < 0) && (l0 * l0 > tau2 * ((s0 * s0 + s1 * s1) + s2 * s2));
-  far = far || ((X[0] < 0) && (X[0] * X[0] > tau2 * ((g.K[0] * g.K[0] + g.K[1] * g.K[1]) + g.K[2] * g.K[2])));
-  far = far || ((X[1] < 0) && (X[1] * X[1] > tau2 * ((g.K[3] * g.K[3] + g.K[4] * g.K[4]) + g.K[5] * g.K[5])));
-  far = far || ((X[2] < 0) && (X[2] * X[2] > tau2 * ((g.K[6] * g.K[6] + g.K[7] * g.K[7]) + g.K[8] * g.K[8])));
+  bool far = (l0 < 0) && (l0 * l0 > t0);
+  far = far || ((X[0] < 0) && (X[0] * X[0] > t1));
+  far = far || ((X[1] < 0) && (X[1] * X[1] > t2));
+  far = far || ((X[2] < 0) && (X[2] * X[2] > t3));
   double d2;
   if (!far && cell_distance2(x, cell_nodes, cell, p, padding, d2)) {
     if (d2 < kCollisionD2) {
@@ -306,9 +316,10 @@ __device__ __forceinline__ WideHit load_test_node(const WideNode* __restrict__ n
 
 __device__ __forceinline__ void prefetch_l1(const void* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
 
-// Per-thread traversal of the 4-wide tree (no early exit): every leaf whose box contains the point
-// is tested and the LOWEST colliding cell index wins, independent of tree shape (north_star
-// tie-break).
+// Per-thread traversal of the 4-wide tree.  Every leaf whose box contains the point is tested and the
+// LOWEST colliding cell index wins, independent of tree shape (north_star tie-break); the only early
+// exit is the provably final one: a point strictly inside a cell (by more than the collision distance)
+// cannot collide with any other cell of a mesh.
 __device__ LocateResult locate_point(const WideNode* __restrict__ nodes, const SceneGrid& grid,
                                      const double* __restrict__ cellgeo, const double* __restrict__ x,
                                      const int4* __restrict__ cell_nodes, double padding, const double* p) {
@@ -344,10 +355,11 @@ __device__ LocateResult locate_point(const WideNode* __restrict__ nodes, const S
       if (kids[k] >= 0) {
         if (next < 0) next = kids[k];
         else if (sp < kStack) stack[sp++] = kids[k];
-      } else {
+      } else if (!st.done) {
         test_cell(cellgeo, x, cell_nodes, padding, tau2, ~kids[k], p, st);
       }
     }
+    if (st.done) break;
     if (next >= 0) node = next;
     else if (sp > 0) node = stack[--sp];
     else break;
@@ -372,8 +384,9 @@ __device__ LocateResult locate_packet(const WideNode* __restrict__ nodes, const 
   while (true) {
     const WideHit h = load_test_node(nodes, node, q);  // uniform address: broadcast
     const int kids[4] = {h.child.x, h.child.y, h.child.z, h.child.w};
-    const bool hit[4] = {active && (h.m01 & 0xffffu) != 0, active && (h.m01 >> 16) != 0, active && (h.m23 & 0xffffu) != 0,
-                         active && (h.m23 >> 16) != 0};
+    const bool live = active && !st.done;  // finished lanes stop voting
+    const bool hit[4] = {live && (h.m01 & 0xffffu) != 0, live && (h.m01 >> 16) != 0, live && (h.m23 & 0xffffu) != 0,
+                         live && (h.m23 >> 16) != 0};
     int next = -1;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -381,7 +394,7 @@ __device__ LocateResult locate_packet(const WideNode* __restrict__ nodes, const 
       if (kids[k] >= 0) {
         if (next < 0) next = kids[k];
         else if (sp < kStack) stack[sp++] = kids[k];
-      } else if (hit[k]) {
+      } else if (hit[k] && !st.done) {
         test_cell(cellgeo, x, cell_nodes, padding, tau2, ~kids[k], p, st);
       }
     }
@@ -899,8 +912,11 @@ __device__ __forceinline__ int team_prefix(bool flag, int team, int team_id, int
   return before + __popc(ball & ((1u << lane) - 1u));
 }
 
+#ifndef FXII_FUSED_MINBLOCKS
+#define FXII_FUSED_MINBLOCKS 4
+#endif
 template <int ND>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, FXII_FUSED_MINBLOCKS)
 pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const double* __restrict__ cellgeo,
                 const double* __restrict__ x,
                 const int4* __restrict__ cell_nodes, double padding, const int32_t* __restrict__ dofmap,
