@@ -142,8 +142,9 @@ void csr_transpose(const fxii_csr* a, int64_t c0, int64_t c1, cudaStream_t s, fx
 // block for long rows) per output row, shared-memory tables sized by the row:
 //   symbolic: rows with at most 512 intermediate products get an exact table (>= 2*ub_i slots).
 //             Longer rows compress strongly in this problem (C_i is the union of overlapping
-//             neighbourhoods), so they first try a 2048-slot warp table; rows that overflow it retry
-//             in a 32768-slot block table, and what overflows that is counted in global memory.
+//             neighbourhoods), so they first try a 1024-slot warp table; rows that overflow it retry
+//             in a 4096-slot warp table, then a 32768-slot block table, and what overflows that is
+//             counted in global memory.
 //   numeric : bins by the exact nnz_i from the symbolic phase (capacity >= 2*nnz_i).
 // (A device-wide cub segmented sort of the finished rows was measured and rejected: 54-230 ms for
 // 136 M entries in 17 M mostly empty segments, against ~18 ms for the in-kernel bitonic sort.)
@@ -163,10 +164,8 @@ spgemm_ub_kernel(const int64_t* __restrict__ a_ptr, const int32_t* __restrict__ 
 }
 
 constexpr int32_t kEmpty = -1;
-constexpr int kNumBins = 6;  // bins 0..4: shared-memory tables of bin_cap slots; bin 5: long rows
-__host__ __device__ constexpr uint32_t bin_cap(int b) {
-  return b == 0 ? 64u : b == 1 ? 256u : b == 2 ? 1024u : b == 3 ? 4096u : 8192u;
-}
+constexpr int kNumBins = 9;  // bins 0..7: shared-memory tables of 64 << b slots; bin 8: long rows
+__host__ __device__ constexpr uint32_t bin_cap(int b) { return 64u << b; }  // 64 ... 8192
 
 __device__ __forceinline__ uint32_t hash_col(uint32_t c) { return c * 2654435761u; }
 
@@ -385,10 +384,10 @@ static void bin_rows(const int64_t* size, int64_t m, int n_exact_bins, cudaStrea
   { classify_rows_kernel<<<grid_for(m, 256, 8), 256, 0, s>>>(size, m, n_exact_bins, bin_of.p, rows.p, counts.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
   size_t tb = 0;
-  FXII_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, bin_of.p, bin_sorted.p, rows.p, rb.sorted_rows.p, m, 0, 3, s));
+  FXII_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, bin_of.p, bin_sorted.p, rows.p, rb.sorted_rows.p, m, 0, 4, s));
   DevBuf<uint8_t> tmp;
   tmp.alloc((int64_t)tb, s);
-  FXII_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, bin_of.p, bin_sorted.p, rows.p, rb.sorted_rows.p, m, 0, 3, s));
+  FXII_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, bin_of.p, bin_sorted.p, rows.p, rb.sorted_rows.p, m, 0, 4, s));
   unsigned long long h[kNumBins + 1];
   FXII_CUDA(cudaMemcpyAsync(h, counts.p, sizeof(h), cudaMemcpyDeviceToHost, s));
   FXII_CUDA(cudaStreamSynchronize(s));
@@ -515,23 +514,28 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
   tr.mark("ub + alloc");
   // ---- symbolic --------------------------------------------------------------------------------
   RowBins sym;
-  bin_rows(ub.p, m, 3, s, sym);  // exact bins 0..2 (ub <= 512); synchronises, so h_ip is valid
+  bin_rows(ub.p, m, 5, s, sym);  // exact bins 0..4 (ub <= 512); synchronises, so h_ip is valid
   tr.mark("bin rows (symbolic)");
   if (ip_out) *ip_out = h_ip;
   FXII_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
-  for (int bin = 0; bin < 3; ++bin)
+  for (int bin = 0; bin < 5; ++bin)
     launch(false, sym.sorted_rows.p + sym.offset[bin], sym.count[bin], bin_cap(bin), false, 256, 0, ub.p, nullptr, nullptr);
   tr.mark("symbolic exact bins");
   const int64_t n_long = sym.count[kNumBins - 1];
   if (n_long > 0) {
-    // first attempt: 2048-slot warp tables, rows with more than 1536 distinct columns retry
-    launch(false, sym.sorted_rows.p + sym.offset[kNumBins - 1], n_long, 2048, false, 256, 1536, ub.p, nullptr, nullptr);
-    int64_t n2 = select_overflowed();
-    if (n2 > 0) {
-      launch(false, retry.p, n2, 32768, true, 256, 16384, ub.p, nullptr, nullptr);
-      const int64_t n3 = select_overflowed();
-      if (n3 > 0) launch(false, retry.p, n3, 0, true, 256, 0, ub.p, nullptr, nullptr);
+    // escalating attempts: rows that overflow a table (more distinct columns than its limit) retry
+    // in the next, larger one; the last resort counts in global memory
+    launch(false, sym.sorted_rows.p + sym.offset[kNumBins - 1], n_long, 1024, false, 256, 768, ub.p, nullptr, nullptr);
+    int64_t n_retry_rows = select_overflowed();
+    if (n_retry_rows > 0) {
+      launch(false, retry.p, n_retry_rows, 4096, false, 128, 3072, ub.p, nullptr, nullptr);
+      n_retry_rows = select_overflowed();
     }
+    if (n_retry_rows > 0) {
+      launch(false, retry.p, n_retry_rows, 32768, true, 256, 16384, ub.p, nullptr, nullptr);
+      n_retry_rows = select_overflowed();
+    }
+    if (n_retry_rows > 0) launch(false, retry.p, n_retry_rows, 0, true, 256, 0, ub.p, nullptr, nullptr);
   }
   tr.mark("symbolic long rows");
   exclusive_scan_i64((const long long*)row_nnz.p, (long long*)out->indptr.p, m + 1, s);
@@ -539,7 +543,7 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
   FXII_CUDA(cudaMemcpyAsync(&nnz, out->indptr.p + m, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
   // ---- numeric ---------------------------------------------------------------------------------
   RowBins num;
-  bin_rows(row_nnz.p, m, 5, s, num);  // synchronises
+  bin_rows(row_nnz.p, m, 8, s, num);  // synchronises
   out->nnz = nnz;
   out->indices.alloc(nnz, s);
   out->values.alloc(nnz, s);
@@ -547,11 +551,13 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
   tr.mark("bin rows (numeric) + alloc");
   for (int bin = 0; bin < kNumBins; ++bin) {
     const int32_t* list = num.sorted_rows.p + num.offset[bin];
-    if (bin <= 1) launch(true, list, num.count[bin], bin_cap(bin), false, 256, 0, row_nnz.p, out->indices.p, out->values.p);
-    else if (bin == 2) launch(true, list, num.count[bin], bin_cap(bin), false, 128, 0, row_nnz.p, out->indices.p, out->values.p);
-    else if (bin == 3) launch(true, list, num.count[bin], bin_cap(bin), true, 128, 0, row_nnz.p, out->indices.p, out->values.p);
-    else if (bin == 4) launch(true, list, num.count[bin], bin_cap(bin), true, 256, 0, row_nnz.p, out->indices.p, out->values.p);
-    else launch(true, list, num.count[bin], 0, true, 256, 0, row_nnz.p, out->indices.p, out->values.p);
+    const uint32_t cap = bin < kNumBins - 1 ? bin_cap(bin) : 0;  // 0: exact-size tables in global memory
+    // warp per row while the tables of a block (16 B per slot and warp) stay within 64 KB; whole blocks above
+    if (bin <= 3) launch(true, list, num.count[bin], cap, false, 256, 0, row_nnz.p, out->indices.p, out->values.p);       // <= 512
+    else if (bin == 4) launch(true, list, num.count[bin], cap, false, 128, 0, row_nnz.p, out->indices.p, out->values.p);  // 1024
+    else if (bin == 5) launch(true, list, num.count[bin], cap, false, 64, 0, row_nnz.p, out->indices.p, out->values.p);   // 2048
+    else if (bin == 6) launch(true, list, num.count[bin], cap, true, 128, 0, row_nnz.p, out->indices.p, out->values.p);   // 4096
+    else launch(true, list, num.count[bin], cap, true, 256, 0, row_nnz.p, out->indices.p, out->values.p);                 // 8192, global
   }
   tr.mark("numeric");
 }
