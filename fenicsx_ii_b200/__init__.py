@@ -11,7 +11,7 @@ from .assembly import (
     restrict_rows,
     restrict_rows_and_columns,
 )
-from .interpolation import create_interpolation_matrix
+from .interpolation import clear_interpolation_cache, create_interpolation_matrix
 from .quadrature import Quadrature
 from .restriction_operators import Circle, Disk, MappedRestriction, PointwiseTrace, ReductionOperator
 from .sparse import DeviceCSR, MatrixCSR
@@ -27,6 +27,7 @@ __all__ = [
     "ReductionOperator",
     "assign_LG_map",
     "average_coefficient",
+    "clear_interpolation_cache",
     "create_interpolation_matrix",
     "restrict_columns",
     "restrict_rows",

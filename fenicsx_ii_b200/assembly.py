@@ -31,7 +31,7 @@ def _as_device(A) -> DeviceCSR:
 
 
 def _pi(space, target, red_op, tol):
-    A, _, _ = create_interpolation_matrix(space, target, red_op, tol=tol, use_petsc=False)
+    A, _, _ = create_interpolation_matrix(space, target, red_op, tol=tol, use_petsc=False, cache=True)
     return A.device
 
 

@@ -13,6 +13,7 @@ void csr_transpose(const fxii_csr* a, int64_t c0, int64_t c1, cudaStream_t s, fx
 void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row_end, cudaStream_t s, fxii_csr* out,
             int64_t* ip_out);
 void csr_scale_rows(fxii_csr* a, const double* d_host, cudaStream_t s);
+void csr_expand_blocks(const fxii_csr* a, int bs, cudaStream_t s, fxii_csr* out);
 void csr_spmv(const fxii_csr* a, const double* u_host, double* y_host, cudaStream_t s);
 }  // namespace fxii
 
@@ -456,6 +457,21 @@ int fxii_spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t
     auto* c = new fxii_csr();
     try {
       fxii::spgemm(a, b, row_begin, row_end, S(stream), c, ip);
+      FXII_CUDA(cudaStreamSynchronize(S(stream)));
+    } catch (...) {
+      delete c;
+      throw;
+    }
+    *out = c;
+  });
+}
+
+int fxii_csr_expand_blocks(const fxii_csr* a, int32_t bs, void* stream, fxii_csr** out) {
+  return guarded([&] {
+    FXII_CHECK(a && out, "null argument");
+    auto* c = new fxii_csr();
+    try {
+      fxii::csr_expand_blocks(a, bs, S(stream), c);
       FXII_CUDA(cudaStreamSynchronize(S(stream)));
     } catch (...) {
       delete c;

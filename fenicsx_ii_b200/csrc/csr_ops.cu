@@ -562,6 +562,56 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
   tr.mark("numeric");
 }
 
+// ---- blocked spaces ---------------------------------------------------------------------------------
+// Pi for blocked spaces (K.bs == V.bs == bs): every scalar entry (r, c, v) becomes the bs x bs block with
+// v on its diagonal and EXPLICIT zeros elsewhere — the reference inserts all nd*bs unrolled columns for
+// every component (interpolation.py:214-248 with utils.unroll_dofmap).
+__global__ void __launch_bounds__(256)
+expand_indptr_kernel(const int64_t* __restrict__ indptr, int64_t n_rows, int bs, int64_t* __restrict__ out_ptr) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q <= n_rows * bs; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = q / bs, b = q - r * bs;
+    // rows r*bs+b hold bs * nnz(r) entries each
+    out_ptr[q] = q == n_rows * bs ? indptr[n_rows] * bs * bs : indptr[r] * bs * bs + b * (indptr[r + 1] - indptr[r]) * bs;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+expand_blocks_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const double* __restrict__ values,
+                     int64_t n_rows, int bs, const int64_t* __restrict__ out_ptr, int32_t* __restrict__ out_idx,
+                     double* __restrict__ out_val) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n_rows; r += nwarps) {
+    const int64_t a = indptr[r], n = indptr[r + 1] - a;
+    for (int64_t t = lane; t < n * bs * bs; t += 32) {
+      const int64_t b = t / (n * bs);           // component row
+      const int64_t rem = t - b * n * bs;
+      const int64_t k = rem / bs, bc = rem - k * bs;  // scalar entry, component column
+      const int64_t o = out_ptr[r * bs + b] + rem;
+      out_idx[o] = indices[a + k] * bs + (int32_t)bc;
+      out_val[o] = bc == b ? values[a + k] : 0.0;
+    }
+  }
+}
+
+void csr_expand_blocks(const fxii_csr* a, int bs, cudaStream_t s, fxii_csr* out) {
+  FXII_CHECK(bs >= 1 && bs <= 16, "block size must be in 1..16");
+  FXII_CHECK(a->n_cols * bs < ((int64_t)1 << 31), "blocked column index must fit int32");
+  out->n_rows = a->n_rows * bs;
+  out->n_cols = a->n_cols * bs;
+  out->nnz = a->nnz * bs * bs;
+  out->indptr.alloc(out->n_rows + 1, s);
+  out->indices.alloc(out->nnz, s);
+  out->values.alloc(out->nnz, s);
+  { expand_indptr_kernel<<<grid_for(out->n_rows + 1, 256, 8), 256, 0, s>>>(a->indptr.p, a->n_rows, bs, out->indptr.p); FXII_LAUNCHED(1); }
+  if (a->n_rows > 0 && a->nnz > 0) {
+    { expand_blocks_kernel<<<grid_for(a->n_rows * 32, 256, 8), 256, 0, s>>>(a->indptr.p, a->indices.p, a->values.p, a->n_rows, bs,
+                                                                         out->indptr.p, out->indices.p, out->values.p); FXII_LAUNCHED(1); }
+  }
+  FXII_CUDA(cudaGetLastError());
+}
+
 // ---- row scaling, SpMV --------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 scale_rows_kernel(const int64_t* __restrict__ indptr, int64_t n_rows, const double* __restrict__ d, double* __restrict__ values) {

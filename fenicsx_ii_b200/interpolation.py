@@ -22,7 +22,8 @@ import numpy as np
 from . import _lib
 from .sparse import DeviceCSR, MatrixCSR
 
-__all__ = ["DeviceMesh", "DeviceRows", "DeviceSpace", "PiStats", "create_interpolation_matrix", "device_space"]
+__all__ = ["DeviceMesh", "DeviceRows", "DeviceSpace", "PiStats", "clear_interpolation_cache", "create_interpolation_matrix",
+           "device_space"]
 
 
 class PiStats(dict):
@@ -212,8 +213,6 @@ def device_space(V, tol: float = 1.0e-8) -> DeviceSpace:
     mesh = V.mesh
     if _comm_size(mesh) > 1:
         raise NotImplementedError("distributed 3D meshes are not supported on the device path (no CPU fallback)")
-    if getattr(V.dofmap, "bs", 1) != 1:
-        raise NotImplementedError("blocked function spaces (bs > 1) are not supported yet")
     cache = mesh.__dict__.setdefault("_fxii_meshes", {})
     dmesh = cache.get(float(tol))
     if dmesh is None:
@@ -237,13 +236,11 @@ def device_rows(K, red_op, cells_K=None) -> DeviceRows:
     cells_K = np.ascontiguousarray(cells_K, dtype=np.int32)
     assert K.element.interpolation_ident
     assert not K.element.needs_dof_transformations
-    if getattr(K.dofmap, "bs", 1) != 1:
-        raise NotImplementedError("blocked K spaces (bs > 1) are not supported yet")
     k_list = np.asarray(K.dofmap.list)
     all_cells = cells_K.shape[0] == k_list.shape[0] and (cells_K.shape[0] == 0 or (cells_K[0] == 0 and cells_K[-1] == k_list.shape[0] - 1
                                                                   and bool(np.all(np.diff(cells_K) == 1))))
     row_dofs = k_list.reshape(-1) if all_cells else k_list[cells_K].reshape(-1)  # no copy for the default cells_K
-    n_rows_total = (K.dofmap.index_map.size_local + K.dofmap.index_map.num_ghosts) * K.dofmap.index_map_bs
+    n_rows_total = K.dofmap.index_map.size_local + K.dofmap.index_map.num_ghosts  # scalar rows; blocks are expanded later
     if k_list.shape[1] != ref_points.shape[0]:
         raise ValueError("K must have one dof per interpolation point")
     on_device = hasattr(red_op, "device_descriptor") and red_op._mesh is mesh_to and mesh_to.topology.dim == 1 \
@@ -258,33 +255,65 @@ def device_rows(K, red_op, cells_K=None) -> DeviceRows:
     return DeviceRows.from_points(q.points, q.weights, q.scales, row_dofs, n_rows_total)
 
 
+# Π cache: the reference rebuilds Π for every integral of every block and twice per
+# assemble (matrix_assembler.py:177,203,229,239,267-294).  Entries hold strong references to their key
+# objects so that `id()` stays unique while an entry lives; least recently used entries are dropped.
+_PI_CACHE: "dict[tuple, tuple]" = {}
+_PI_CACHE_SIZE = 8
+
+
+def clear_interpolation_cache():
+    _PI_CACHE.clear()
+
+
+def _cache_key(V, K, red_op, tol, cells_K):
+    ck = None if cells_K is None else np.ascontiguousarray(cells_K, dtype=np.int32).tobytes()
+    return (id(V), id(K), id(red_op), float(tol), ck)
+
+
 def create_interpolation_matrix(V, K, red_op, tol: float = 1.0e-8, use_petsc: bool = False, cells_K=None,
-                                complex_dtype: bool = False, materialize_coo: bool = False):
+                                complex_dtype: bool = False, materialize_coo: bool = False, cache: bool = False):
     """Create an interpolation matrix from `V` to `K` with a specific reduction operator applied to
     the interpolation points of `K`.
 
     Args:
-        V: The function space to interpolate from (Lagrange P1/P2 on affine tetrahedra).
-        K: The function space to interpolate to (on the 1D mesh).
+        V: The function space to interpolate from (Lagrange P1/P2 on affine tetrahedra, scalar or blocked).
+        K: The function space to interpolate to (on the 1D mesh; same block size as V).
         red_op: Reduction operator for each interpolation point on `K`.
         tol: Tolerance (box padding) for determining point ownership.
         use_petsc: Return a PETSc AIJ matrix (requires petsc4py) instead of a ``MatrixCSR``.
         cells_K: Optional subset of the cells of K to process.
         complex_dtype: Not supported on the device path.
         materialize_coo: (extension) force the unfused COO path, e.g. to inspect the COO.
+        cache: (extension) reuse the matrix of an earlier call with the same `V`, `K`, `red_op`,
+            `tol` and `cells_K` objects (see ``clear_interpolation_cache``).
 
     Returns:
         ``(A, imap_K, imap_V)``: the matrix and the (serial: unchanged) index maps of K and V.
     """
     if complex_dtype:
         raise NotImplementedError("complex matrices are not supported on the device path")
+    imap_K, imap_V = K.dofmap.index_map, V.dofmap.index_map
+    key = _cache_key(V, K, red_op, tol, cells_K) if cache and not materialize_coo else None
+    if key is not None and key in _PI_CACHE:
+        A = _PI_CACHE.pop(key)[0]
+        _PI_CACHE[key] = (A, V, K, red_op)  # most recently used last
+        return (A.to_petsc() if use_petsc else A), imap_K, imap_V
+    bs = int(getattr(V.dofmap, "bs", 1))
+    if bs != int(getattr(K.dofmap, "bs", 1)):
+        raise NotImplementedError("V and K must have the same block size")
     dspace = device_space(V, tol)
     rows = device_rows(K, red_op, cells_K)
     if materialize_coo:
         rows.set_mode(1)
     csr, stats = rows.assemble(dspace)
+    if bs > 1:
+        csr = csr.expand_blocks(bs)  # device kernel: bs x bs blocks, explicit zeros off the diagonal
     A = MatrixCSR(csr, stats=stats, rows=rows)
-    imap_K, imap_V = K.dofmap.index_map, V.dofmap.index_map
+    if key is not None:
+        _PI_CACHE[key] = (A, V, K, red_op)
+        while len(_PI_CACHE) > _PI_CACHE_SIZE:
+            _PI_CACHE.pop(next(iter(_PI_CACHE)))
     if use_petsc:
         return A.to_petsc(), imap_K, imap_V
     return A, imap_K, imap_V

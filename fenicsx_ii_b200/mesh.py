@@ -6,7 +6,7 @@ is provided over plain numpy arrays: ``mesh.geometry.x``, ``mesh.geometry.dofmap
 ``mesh.geometry.dim``, ``mesh.topology.dim``, ``mesh.topology.index_map(d).size_local``,
 ``V.mesh``, ``V.dofmap.list``, ``V.dofmap.bs``, ``V.dofmap.index_map``, ``V.dofmap.index_map_bs``,
 ``V.element.interpolation_points`` ...  ``create_interpolation_matrix`` only uses these attributes,
-so real dolfinx objects work unchanged where dolfinx is installed (see ``adapters.py``).
+so real dolfinx objects work unchanged where dolfinx is installed.
 """
 
 from __future__ import annotations
@@ -109,6 +109,7 @@ class FunctionSpace:
 
     @property
     def num_dofs(self) -> int:
+        """Scalar dof count times the block size."""
         return self.dofmap.index_map.size_local * self.dofmap.index_map_bs
 
 
@@ -130,13 +131,19 @@ def _tet_p2_dofmap(cells: np.ndarray, n_nodes: int) -> tuple[np.ndarray, int]:
     return dof_list, n_nodes + uniq.shape[0]
 
 
-def functionspace(mesh: Mesh, element: tuple[str, int], dof_list: np.ndarray | None = None,
-                  n_dofs: int | None = None) -> FunctionSpace:
+def functionspace(mesh: Mesh, element, dof_list: np.ndarray | None = None, n_dofs: int | None = None) -> FunctionSpace:
     """``dolfinx.fem.functionspace`` for the element families the hot path supports.
 
     3D (tetrahedra): ("Lagrange", 1|2).  1D (intervals): ("Quadrature", q) — the ``(q+2)//2``
     Gauss points per cell, cell-local dofs; ("DG", k) k=0,1,2; ("Lagrange", 1|2).
     A precomputed ``dof_list`` (e.g. the closed-form P2 numbering of a structured mesh) may be given."""
+    bs = 1
+    if len(element) == 3:  # ("Lagrange", 1, (3,)): blocked (vector) space, dolfinx style
+        family, degree, shape = element
+        bs = int(np.prod(shape))
+        V = functionspace(mesh, (family, degree), dof_list, n_dofs)
+        V.dofmap.bs = V.dofmap.index_map_bs = bs
+        return V
     family, degree = element
     family = {"P": "Lagrange", "CG": "Lagrange", "Discontinuous Lagrange": "DG"}.get(family, family)
     cells = mesh.geometry.dofmap

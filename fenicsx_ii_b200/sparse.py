@@ -119,6 +119,12 @@ class DeviceCSR:
         c = DeviceCSR(out.value)
         return (c, ip.value) if return_ip else c
 
+    def expand_blocks(self, bs: int) -> "DeviceCSR":
+        """Π of blocked spaces from the scalar Π: bs x bs blocks, value on the diagonal, explicit zeros elsewhere."""
+        out = C.c_void_p()
+        _lib.check(_lib.load().fxii_csr_expand_blocks(self._h, int(bs), _lib.current_stream(), C.byref(out)))
+        return DeviceCSR(out.value)
+
     def scale_rows(self, d) -> "DeviceCSR":
         d = np.ascontiguousarray(d, dtype=np.float64)
         assert d.shape == (self.shape[0],)

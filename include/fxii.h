@@ -149,6 +149,9 @@ int fxii_csr_transpose_window(const fxii_csr* a, int64_t col_begin, int64_t col_
  * pass 0, -1 for all rows. */
 int fxii_spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row_end,
                 void* stream, fxii_csr** out, int64_t* ip);
+/* blocked spaces (K.bs == V.bs == bs): every scalar entry becomes a bs x bs block with the value on its
+ * diagonal and explicit zeros elsewhere (interpolation.py:214-248 + utils.unroll_dofmap, utils.py:36-47) */
+int fxii_csr_expand_blocks(const fxii_csr* a, int32_t bs, void* stream, fxii_csr** out);
 /* rows scaled by a diagonal: (diag(d)·A); d host [n_rows] — M_Γ·Π for a quadrature-element mass */
 int fxii_csr_scale_rows(fxii_csr* a, const double* d, void* stream);
 /* y = A·u (assembly.py:67); u host [n_cols], y host [n_rows] */

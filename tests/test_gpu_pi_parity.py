@@ -236,3 +236,38 @@ def test_circle_leaving_the_domain_raises(cuda):
         create_interpolation_matrix(V, K, Circle(gamma, 0.2, degree=9))
     except AssertionError as e:  # PointsNotFound is an AssertionError, like the reference's assert
         assert "points lie in no cell" in str(e)
+
+
+def test_blocked_spaces_and_cache(cuda):
+    """tests/test_interpolation_matrix.py:254-301 (vector spaces, bs=3): Π_blocked = Π ⊗ I_3 with the
+    reference's full 3x3 blocks (explicit zeros off the diagonal); plus the Π cache."""
+    import scipy.sparse as sp
+
+    from fenicsx_ii_b200 import Circle, clear_interpolation_cache
+
+    mesh, _ = small_cfg(6, 6, 6)
+    gamma = sy.polyline_network(50, 1 / 6, n_lines=2, lo=0.3, hi=0.7)
+    V = functionspace(mesh, ("Lagrange", 1))
+    K = functionspace(gamma, ("DG", 1))
+    V3 = functionspace(mesh, ("Lagrange", 1, (3,)))
+    K3 = functionspace(gamma, ("DG", 1, (3,)))
+    op = Circle(gamma, 0.05, degree=7)
+    A, _, _ = create_interpolation_matrix(V, K, op)
+    A3, _, _ = create_interpolation_matrix(V3, K3, op)
+    assert A3.shape == (3 * K.num_dofs, 3 * V.num_dofs) == (K3.num_dofs, V3.num_dofs)
+    S, S3 = A.to_scipy(), A3.to_scipy()
+    np.testing.assert_array_equal(S3.toarray(), sp.kron(S, sp.identity(3)).toarray())
+    assert S3.nnz == 9 * S.nnz  # full blocks, zeros kept
+    # Π u for a vector field interpolates component-wise
+    u = np.stack([mesh.geometry.x[:, 2], 2 * mesh.geometry.x[:, 2] + 1, np.ones(V.num_dofs)], axis=1).reshape(-1)
+    r = A3.mult(u).reshape(-1, 3)
+    np.testing.assert_allclose(r[:, 1], 2 * r[:, 0] + 1, rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(r[:, 2], 1.0, rtol=1e-12)
+    # cache: same objects -> same matrix object; different operator -> rebuilt
+    clear_interpolation_cache()
+    B1, _, _ = create_interpolation_matrix(V, K, op, cache=True)
+    B2, _, _ = create_interpolation_matrix(V, K, op, cache=True)
+    B3, _, _ = create_interpolation_matrix(V, K, Circle(gamma, 0.05, degree=7), cache=True)
+    assert B1 is B2 and B3 is not B1
+    np.testing.assert_array_equal(B3.indices, B1.indices)
+    clear_interpolation_cache()
