@@ -52,8 +52,8 @@ struct Block {
   cudaStream_t last;
 };
 std::mutex g_mem_mutex;
-std::map<size_t, std::vector<Block>> g_free;      // size class -> free blocks
-std::unordered_map<void*, size_t> g_live;          // live block -> size class
+std::map<std::pair<int, size_t>, std::vector<Block>> g_free;  // (device, size class) -> free blocks
+std::unordered_map<void*, std::pair<int, size_t>> g_live;       // live block -> (device, size class)
 size_t g_cached_bytes = 0;
 
 size_t size_class(size_t bytes) {
@@ -67,14 +67,17 @@ size_t size_class(size_t bytes) {
 
 void* cached_alloc(size_t bytes, cudaStream_t s) {
   const size_t cls = size_class(bytes);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const std::pair<int, size_t> key{dev, cls};
   {
     std::lock_guard<std::mutex> lock(g_mem_mutex);
-    auto it = g_free.find(cls);
+    auto it = g_free.find(key);
     if (it != g_free.end() && !it->second.empty()) {
       Block b = it->second.back();
       it->second.pop_back();
       g_cached_bytes -= cls;
-      g_live[b.p] = cls;
+      g_live[b.p] = key;
       if (b.last != s) cudaStreamSynchronize(b.last);  // cross-stream reuse: wait for the old stream
       return b.p;
     }
@@ -89,7 +92,7 @@ void* cached_alloc(size_t bytes, cudaStream_t s) {
   if (e != cudaSuccess)
     throw Error(FXII_E_CUDA, std::string("cudaMalloc of ") + std::to_string(cls) + " bytes: " + cudaGetErrorString(e));
   std::lock_guard<std::mutex> lock(g_mem_mutex);
-  g_live[p] = cls;
+  g_live[p] = key;
   return p;
 }
 
@@ -97,17 +100,22 @@ void cached_free(void* p, cudaStream_t s) {
   std::lock_guard<std::mutex> lock(g_mem_mutex);
   auto it = g_live.find(p);
   if (it == g_live.end()) return;
-  const size_t cls = it->second;
+  const std::pair<int, size_t> key = it->second;
   g_live.erase(it);
-  g_free[cls].push_back(Block{p, s});
-  g_cached_bytes += cls;
+  g_free[key].push_back(Block{p, s});
+  g_cached_bytes += key.second;
 }
 
 void cache_trim() {
   std::lock_guard<std::mutex> lock(g_mem_mutex);
-  cudaDeviceSynchronize();
-  for (auto& kv : g_free)
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (auto& kv : g_free) {
+    cudaSetDevice(kv.first.first);
+    cudaDeviceSynchronize();
     for (auto& b : kv.second) cudaFree(b.p);
+  }
+  cudaSetDevice(cur);
   g_free.clear();
   g_cached_bytes = 0;
 }
