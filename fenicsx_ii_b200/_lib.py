@@ -78,6 +78,8 @@ SIGNATURES = {
     "fxii_rows_destroy": (C.c_int, [_vp]),
     "fxii_rows_keep_points": (C.c_int, [_vp, _i32]),
     "fxii_rows_set_mode": (C.c_int, [_vp, _i32]),
+    "fxii_rows_set_nnz_hint": (C.c_int, [_vp, _i64]),
+    "fxii_rows_get_nnz_hint": (C.c_int64, [_vp]),
     "fxii_pi_assemble": (C.c_int, [_vp, _vp, _vp, C.POINTER(_vp), C.POINTER(PiStats)]),
     "fxii_rows_download_diag": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "fxii_rows_download_coo": (C.c_int, [_vp, _vp, _vp, _vp]),
@@ -144,7 +146,8 @@ def current_stream() -> int:
     """cudaStream_t of torch's current stream, so torch CUDA events bracket our kernels."""
     import torch
 
-    return int(torch.cuda.current_stream().cuda_stream)
+    # torch.cuda.current_stream() costs ~15 us of Python; the raw query is ~1 us
+    return int(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
 def require_cuda():

@@ -308,6 +308,15 @@ int fxii_rows_set_mode(fxii_rows* r, int32_t mode) {
   });
 }
 
+int fxii_rows_set_nnz_hint(fxii_rows* r, int64_t nnz) {
+  return guarded([&] {
+    FXII_CHECK(r && nnz >= 0, "bad argument");
+    r->nnz_hint = nnz;
+  });
+}
+
+int64_t fxii_rows_get_nnz_hint(const fxii_rows* r) { return r ? r->nnz_hint : 0; }
+
 int fxii_pi_assemble(const fxii_space* space, fxii_rows* rows, void* stream, fxii_csr** out, fxii_pi_stats* stats) {
   fxii_csr* c = nullptr;
   int rc = guarded([&] {

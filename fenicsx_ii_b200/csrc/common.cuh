@@ -194,7 +194,8 @@ struct fxii_rows {
   bool keep_points = false;  // also write the generated 3D points (diagnostics only)
   int mode = 0;              // 0: fused row reduction when possible; 1: always materialise the COO
   bool last_fused = false;
-  int64_t nnz_hint = 0;          // nnz of the previous fused build on this handle (0: unknown)
+  int64_t nnz_hint = 0;          // expected nnz: the previous fused build on this handle, or set by the caller (0: unknown)
+  int n_builds = 0;              // fused builds completed on this handle
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // stage timers, created on first use
   // fused path: workspace and, for graph replay, handle-owned CSR buffers + the captured graph
   fxii::DevBuf<uint8_t> ws, scan_tmp;

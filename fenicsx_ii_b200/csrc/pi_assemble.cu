@@ -1298,7 +1298,8 @@ static bool pi_assemble_fused(const fxii_space* sp, fxii_rows* rows, cudaStream_
     *ms_csr = elapsed_ms(ev[2], ev[3]);
   };
   // ---- graph replay -------------------------------------------------------------------------------
-  if (hint > 0 && graphs_enabled() && E <= ((int64_t)1 << 26)) {
+  // (a graph only pays off when the handle is reused: capture + instantiation cost ~0.2 ms)
+  if (hint > 0 && rows->n_builds >= 1 && graphs_enabled() && E <= ((int64_t)1 << 26)) {
     moved |= rows->g_indptr.ensure(n_rows + 1, s);
     moved |= rows->g_indices.ensure(hint, s);
     moved |= rows->g_values.ensure(hint, s);
@@ -1348,6 +1349,7 @@ static bool pi_assemble_fused(const fxii_space* sp, fxii_rows* rows, cudaStream_
         }
         *h_counters = hr->counters;
         rows->nnz_hint = hr->nnz;
+        rows->n_builds += 1;
         rows->last_graph = true;
         times();
         return true;
@@ -1375,6 +1377,7 @@ static bool pi_assemble_fused(const fxii_space* sp, fxii_rows* rows, cudaStream_
     FXII_CUDA(cudaStreamSynchronize(s));
   }
   rows->nnz_hint = hr->nnz;
+  rows->n_builds += 1;
   times();
   return true;
 }

@@ -149,6 +149,13 @@ class DeviceRows:
     def keep_points(self, flag: bool = True):
         _lib.check(_lib.load().fxii_rows_keep_points(self._h, 1 if flag else 0))
 
+    def set_nnz_hint(self, nnz: int):
+        """Expected nnz (from an earlier build of the same Γ/operator): one host sync instead of two."""
+        _lib.check(_lib.load().fxii_rows_set_nnz_hint(self._h, int(nnz)))
+
+    def nnz_hint(self) -> int:
+        return int(_lib.load().fxii_rows_get_nnz_hint(self._h))
+
     def set_mode(self, mode: int):
         """0: fused row reduction when possible (default); 1: always materialise the COO."""
         _lib.check(_lib.load().fxii_rows_set_mode(self._h, int(mode)))
@@ -306,7 +313,13 @@ def create_interpolation_matrix(V, K, red_op, tol: float = 1.0e-8, use_petsc: bo
     rows = device_rows(K, red_op, cells_K)
     if materialize_coo:
         rows.set_mode(1)
+    # nnz of the previous build with the same (K, operator, cells_K): lets the build allocate up front
+    hints = red_op.__dict__.setdefault("_fxii_nnz_hints", {}) if hasattr(red_op, "__dict__") else {}
+    hkey = (id(K), id(V), None if cells_K is None else len(cells_K))
+    if hkey in hints:
+        rows.set_nnz_hint(hints[hkey])
     csr, stats = rows.assemble(dspace)
+    hints[hkey] = csr.nnz
     if bs > 1:
         csr = csr.expand_blocks(bs)  # device kernel: bs x bs blocks, explicit zeros off the diagonal
     A = MatrixCSR(csr, stats=stats, rows=rows)

@@ -100,6 +100,11 @@ int fxii_rows_keep_points(fxii_rows* r, int32_t flag);
  * (cell-local K), falling back to the COO path otherwise; mode 1: always materialise the COO
  * (needed by fxii_rows_download_coo). */
 int fxii_rows_set_mode(fxii_rows* r, int32_t mode);
+/* Expected nnz of the matrix this handle will build (e.g. the nnz of the previous build of the same Γ and
+ * operator): the CSR arrays are then allocated before the kernels run and the build synchronises with the
+ * host once.  A wrong hint only costs a repeated compaction.  get returns the nnz of the last build. */
+int fxii_rows_set_nnz_hint(fxii_rows* r, int64_t nnz);
+int64_t fxii_rows_get_nnz_hint(const fxii_rows* r);
 
 /* ---- Π assembly -------------------------------------------------------------------------- */
 typedef struct {
