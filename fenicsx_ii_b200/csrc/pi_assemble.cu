@@ -282,7 +282,7 @@ __device__ __forceinline__ LocateResult finish_locate(const LocateState& st, dou
 struct QPoint {
   uint32_t x2, y2, z2;  // coordinate | 0x8000 in both halfwords
 };
-__device__ __forceinline__ QPoint quantise_point(const SceneGrid& g, const double* p, bool active) {
+__device__ __forceinline__ QPoint quantise_point(const SceneGrid& g, const double* p) {
   QPoint q;
   uint32_t v[3];
 #pragma unroll
@@ -290,7 +290,6 @@ __device__ __forceinline__ QPoint quantise_point(const SceneGrid& g, const doubl
   q.x2 = (v[0] | (v[0] << 16)) | 0x80008000u;
   q.y2 = (v[1] | (v[1] << 16)) | 0x80008000u;
   q.z2 = (v[2] | (v[2] << 16)) | 0x80008000u;
-  (void)active;
   return q;
 }
 
@@ -323,7 +322,7 @@ __device__ __forceinline__ void prefetch_l1(const void* ptr) { asm volatile("pre
 __device__ LocateResult locate_point(const WideNode* __restrict__ nodes, const SceneGrid& grid,
                                      const double* __restrict__ cellgeo, const double* __restrict__ x,
                                      const int4* __restrict__ cell_nodes, double padding, const double* p) {
-  const QPoint q = quantise_point(grid, p, true);
+  const QPoint q = quantise_point(grid, p);
   // 1.001: cells within 0.05% of the threshold still take the exact path
   const double tau2 = fmax(kCollisionD2, padding * padding) * 1.001;
   int stack[kStack];
@@ -375,7 +374,7 @@ __device__ LocateResult locate_point(const WideNode* __restrict__ nodes, const S
 __device__ LocateResult locate_packet(const WideNode* __restrict__ nodes, const SceneGrid& grid,
                                       const double* __restrict__ cellgeo, const double* __restrict__ x,
                                       const int4* __restrict__ cell_nodes, double padding, const double* p, bool active) {
-  const QPoint q = quantise_point(grid, p, active);
+  const QPoint q = quantise_point(grid, p);
   const double tau2 = fmax(kCollisionD2, padding * padding) * 1.001;
   int stack[kStack];  // warp-uniform contents
   int sp = 0;

@@ -271,3 +271,28 @@ def test_blocked_spaces_and_cache(cuda):
     assert B1 is B2 and B3 is not B1
     np.testing.assert_array_equal(B3.indices, B1.indices)
     clear_interpolation_cache()
+
+
+@pytest.mark.parametrize("degree", [1, 2])
+def test_unstructured_delaunay_mesh(cuda, degree):
+    """Irregular Ω (Delaunay tetrahedra of random points, incl. badly shaped cells): the LBVH, the
+    quantised boxes and the collision tests must not depend on mesh structure."""
+    from scipy.spatial import Delaunay
+
+    from fenicsx_ii_b200.mesh import Mesh
+
+    rng = np.random.default_rng(7)
+    pts = rng.uniform(0, 1, size=(1500, 3))
+    corners = np.array([[i, j, k] for i in (0, 1) for j in (0, 1) for k in (0, 1)], dtype=float)
+    pts = np.vstack([corners, pts])
+    tets = Delaunay(pts).simplices.astype(np.int32)
+    vol = np.abs(np.linalg.det(pts[tets[:, 1:]] - pts[tets[:, :1]])) / 6
+    tets = tets[vol > 1e-9]  # drop exactly degenerate slivers (a FEM mesh has none)
+    mesh = Mesh(pts, tets, tdim=3)
+    V = functionspace(mesh, ("Lagrange", degree))
+    gamma = sy.polyline_network(120, 0.04, n_lines=4, lo=0.2, hi=0.8)
+    K = functionspace(gamma, ("Quadrature", 6))
+    A, ref = run_case(V, K, gamma, "trace", expect_fused=True)
+    np.testing.assert_allclose(np.asarray(A.to_scipy().sum(axis=1)).ravel(), 1.0, atol=1e-9)
+    run_case(V, K, gamma, "circle", 0.07, 15, expect_fused=True)
+    run_case(V, K, gamma, "disk", 0.05, 4, expect_fused=True)
