@@ -204,7 +204,8 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
                                    const double* __restrict__ a_val, const int64_t* __restrict__ b_ptr,
                                    const int32_t* __restrict__ b_idx, const double* __restrict__ b_val,
                                    int64_t row_begin, const int32_t* __restrict__ row_list, int64_t n_list, uint32_t cap,
-                                   int overflow_limit, int* __restrict__ overflow_flag, int32_t* __restrict__ g_keys,
+                                   int overflow_limit, int flatten, int* __restrict__ overflow_flag,
+                                   int32_t* __restrict__ g_keys,
                                    double* __restrict__ g_vals, uint64_t* __restrict__ g_sort,
                                    const int64_t* __restrict__ g_off,
                                    int64_t* __restrict__ row_size, const int64_t* __restrict__ c_ptr,
@@ -251,6 +252,56 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
     group_sync<BLOCK>();
     const int64_t a0 = a_ptr[row_begin + i], a1 = a_ptr[row_begin + i + 1];
     bool overflow = false;
+    if (!NUMERIC && flatten) {
+      // Symbolic phase: insertion order is irrelevant, so the (k, entry of B_k) pairs of 32 consecutive
+      // k are flattened per warp — one lane per intermediate product instead of one warp pass per
+      // (short) row of B.  Prefix sums and the k lookup run on shuffles.
+      const int lane = threadIdx.x & 31;
+      const int wig = BLOCK ? (threadIdx.x >> 5) : 0;        // warp in group
+      const int nwarps = BLOCK ? (blockDim.x >> 5) : 1;
+      for (int64_t c0 = a0 + 32 * (int64_t)wig; c0 < a1; c0 += 32 * (int64_t)nwarps) {
+        if (overflow_limit > 0 && *(volatile int*)&s_new[gid] > overflow_limit) break;  // warp-uniform
+        const int64_t ka = c0 + lane;
+        int64_t b0 = 0;
+        int len = 0;
+        if (ka < a1) {
+          const int k = __ldg(&a_idx[ka]);
+          b0 = __ldg(&b_ptr[k]);
+          len = (int)(__ldg(&b_ptr[k + 1]) - b0);
+        }
+        int incl = len;  // inclusive prefix sum of the row lengths over the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        for (int t0 = 0; t0 < total; t0 += 32) {
+          if (overflow_limit > 0 && *(volatile int*)&s_new[gid] > overflow_limit) break;  // warp-uniform
+          const int t = t0 + lane;
+          // owner lane j: smallest j with incl[j] > t (binary search over the warp's prefix sums)
+          int lo = 0, hi = 31;
+#pragma unroll
+          for (int step = 0; step < 5; ++step) {
+            const int mid = (lo + hi) >> 1;
+            const int pm = __shfl_sync(0xffffffffu, incl, mid);
+            if (pm > t) hi = mid;
+            else lo = mid + 1;
+          }
+          const int j = lo;
+          const int incl_j = __shfl_sync(0xffffffffu, incl, j);
+          const int len_j = __shfl_sync(0xffffffffu, len, j);
+          const int64_t b0_j = __shfl_sync(0xffffffffu, b0, j);
+          if (t < total) {
+            bool is_new;
+            const uint32_t slot = hash_insert(keys, tcap, __ldg(&b_idx[b0_j + (t - (incl_j - len_j))]), is_new);
+            if (overflow_limit > 0 && is_new) atomicAdd(&s_new[gid], 1);
+            if (slot == 0xffffffffu) atomicAdd(&s_new[gid], (int)tcap);  // full: force the retry
+          }
+        }
+        if (overflow_limit > 0) __syncwarp();
+      }
+    } else
     for (int64_t ka = a0; ka < a1; ++ka) {
       const int k = a_idx[ka];
       const double av = NUMERIC ? a_val[ka] : 0.0;
@@ -399,6 +450,15 @@ static void bin_rows(const int64_t* size, int64_t m, int n_exact_bins, cudaStrea
   }
 }
 
+// FXII_SYMFLAT: 0 = k-sequential symbolic loop, 1 = flattened for exact tables only, 2 (default) = everywhere
+static int flatten_mode(int overflow_limit) {
+  static const int mode = [] {
+    const char* e = getenv("FXII_SYMFLAT");
+    return e ? atoi(e) : 2;
+  }();
+  return mode == 2 || (mode == 1 && overflow_limit == 0) ? 1 : 0;
+}
+
 void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row_end, cudaStream_t s, fxii_csr* out,
             int64_t* ip_out) {
   FXII_CHECK(a->n_cols == b->n_rows, "spgemm: inner dimensions differ");
@@ -471,7 +531,7 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
                                      (int)smem));                                                                     \
     spgemm_rows_kernel<BLK, NUM><<<grid, threads, smem, s>>>(                                                         \
         a->indptr.p, a->indices.p, a->values.p, b->indptr.p, b->indices.p, b->values.p, row_begin, list, nl, cap,     \
-        overflow_limit, overflow.p, global ? g_keys.p : nullptr, global ? g_vals.p : nullptr,                         \
+        overflow_limit, flatten_mode(overflow_limit), overflow.p, global ? g_keys.p : nullptr, global ? g_vals.p : nullptr,                         \
         global ? g_sort.p : nullptr, global ? g_off.p : nullptr, row_nnz.p, out->indptr.p, c_idx, c_val);                                          \
     FXII_CUDA(cudaGetLastError());                                                                                    \
     FXII_LAUNCHED(1);                                                                                                 \
