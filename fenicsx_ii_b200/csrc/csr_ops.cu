@@ -252,7 +252,7 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
     group_sync<BLOCK>();
     const int64_t a0 = a_ptr[row_begin + i], a1 = a_ptr[row_begin + i + 1];
     bool overflow = false;
-    if (!NUMERIC && flatten) {
+    if (!NUMERIC && (flatten & 1)) {
       // Symbolic phase: insertion order is irrelevant, so the (k, entry of B_k) pairs of 32 consecutive
       // k are flattened per warp — one lane per intermediate product instead of one warp pass per
       // (short) row of B.  Prefix sums and the k lookup run on shuffles.
@@ -300,6 +300,67 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
           }
         }
         if (overflow_limit > 0) __syncwarp();
+      }
+    } else if (NUMERIC && !BLOCK && (flatten & 2)) {
+      // Numeric phase, one warp per row: the same flattening, which batches the dependent loads
+      // (A column -> B row pointer -> B entries) 32 products at a time.  The sum order stays the
+      // sequential one (ascending k for every output column): batches run in order, and inside a
+      // batch the lanes that hit the same column (different k, ascending with the lane) add one
+      // after the other, ranked by __match_any_sync.
+      const int lane = threadIdx.x & 31;
+      for (int64_t c0 = a0; c0 < a1; c0 += 32) {
+        const int64_t ka = c0 + lane;
+        int64_t b0 = 0;
+        int len = 0;
+        double av = 0.0;
+        if (ka < a1) {
+          const int k = __ldg(&a_idx[ka]);
+          av = __ldg(&a_val[ka]);
+          b0 = __ldg(&b_ptr[k]);
+          len = (int)(__ldg(&b_ptr[k + 1]) - b0);
+        }
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        for (int t0 = 0; t0 < total; t0 += 32) {
+          const int t = t0 + lane;
+          int lo = 0, hi = 31;
+#pragma unroll
+          for (int step = 0; step < 5; ++step) {
+            const int mid = (lo + hi) >> 1;
+            const int pm = __shfl_sync(0xffffffffu, incl, mid);
+            if (pm > t) hi = mid;
+            else lo = mid + 1;
+          }
+          const int j = lo;
+          const int incl_j = __shfl_sync(0xffffffffu, incl, j);
+          const int len_j = __shfl_sync(0xffffffffu, len, j);
+          const int64_t b0_j = __shfl_sync(0xffffffffu, b0, j);
+          const double av_j = __shfl_sync(0xffffffffu, av, j);
+          const bool active = t < total;
+          int32_t col = -2 - lane;  // inactive lanes: distinct keys that match nothing
+          double prod = 0.0;
+          uint32_t slot = 0;
+          if (active) {
+            const int64_t kb = b0_j + (t - (incl_j - len_j));
+            col = __ldg(&b_idx[kb]);
+            prod = av_j * __ldg(&b_val[kb]);
+            bool is_new;
+            slot = hash_insert(keys, tcap, col, is_new);
+          }
+          const unsigned same = __match_any_sync(0xffffffffu, col);
+          const int rank = __popc(same & ((1u << lane) - 1));
+          unsigned pending = __ballot_sync(0xffffffffu, active);
+          for (int r = 0; pending; ++r) {
+            if (active && rank == r) vals[slot] += prod;
+            __syncwarp();
+            pending = __ballot_sync(0xffffffffu, active && rank > r);
+          }
+        }
       }
     } else
     for (int64_t ka = a0; ka < a1; ++ka) {
@@ -450,13 +511,18 @@ static void bin_rows(const int64_t* size, int64_t m, int n_exact_bins, cudaStrea
   }
 }
 
-// FXII_SYMFLAT: 0 = k-sequential symbolic loop, 1 = flattened for exact tables only, 2 (default) = everywhere
-static int flatten_mode(int overflow_limit) {
-  static const int mode = [] {
-    const char* e = getenv("FXII_SYMFLAT");
-    return e ? atoi(e) : 2;
+// bit 0: flattened symbolic loop, bit 1: flattened numeric loop (warp-per-row bins).  The numeric
+// flattening pays while B's rows are short (it batches the dependent loads of ~32 rows of B; 36 -> 27 ms
+// on the 1M-segment tree with 32-entry rows) and costs a few percent once a single row of B fills
+// several warp passes on its own (256-entry rows), so it is chosen from B's mean row length.
+// FXII_SPGEMM_FLAT overrides (0 restores the k-sequential loops).
+static int flatten_mode(const fxii_csr* b) {
+  static const int forced = [] {
+    const char* e = getenv("FXII_SPGEMM_FLAT");
+    return e ? atoi(e) : -1;
   }();
-  return mode == 2 || (mode == 1 && overflow_limit == 0) ? 1 : 0;
+  if (forced >= 0) return forced;
+  return b->nnz <= 64 * std::max<int64_t>(b->n_rows, 1) ? 3 : 1;
 }
 
 void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row_end, cudaStream_t s, fxii_csr* out,
@@ -531,7 +597,7 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
                                      (int)smem));                                                                     \
     spgemm_rows_kernel<BLK, NUM><<<grid, threads, smem, s>>>(                                                         \
         a->indptr.p, a->indices.p, a->values.p, b->indptr.p, b->indices.p, b->values.p, row_begin, list, nl, cap,     \
-        overflow_limit, flatten_mode(overflow_limit), overflow.p, global ? g_keys.p : nullptr, global ? g_vals.p : nullptr,                         \
+        overflow_limit, flatten_mode(b), overflow.p, global ? g_keys.p : nullptr, global ? g_vals.p : nullptr,                         \
         global ? g_sort.p : nullptr, global ? g_off.p : nullptr, row_nnz.p, out->indptr.p, c_idx, c_val);                                          \
     FXII_CUDA(cudaGetLastError());                                                                                    \
     FXII_LAUNCHED(1);                                                                                                 \
@@ -618,6 +684,11 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
     else if (bin == 5) launch(true, list, num.count[bin], cap, false, 64, 0, row_nnz.p, out->indices.p, out->values.p);   // 2048
     else if (bin == 6) launch(true, list, num.count[bin], cap, true, 128, 0, row_nnz.p, out->indices.p, out->values.p);   // 4096
     else launch(true, list, num.count[bin], cap, true, 256, 0, row_nnz.p, out->indices.p, out->values.p);                 // 8192, global
+    if (tr.on && num.count[bin] > 0) {
+      char label[64];
+      snprintf(label, sizeof label, "numeric bin %d (%lld rows)", bin, (long long)num.count[bin]);
+      tr.mark(label);
+    }
   }
   tr.mark("numeric");
 }
