@@ -293,6 +293,8 @@ def run_ours(args):
     peak, peak_src = measured_peak_gbs()
     nd = dspace.nd
     k_loc = stage["ms_locate"] / args.steps
+    if st.get("fused", 0) == 3:  # single cooperative launch: ms_locate + ms_csr apportion ONE kernel's event time
+        k_loc += stage["ms_csr"] / args.steps
     k_cnt = stage["ms_csr_count"] / args.steps
     k_fill = stage["ms_csr_fill"] / args.steps
     fused = bool(st.get("fused", 0))

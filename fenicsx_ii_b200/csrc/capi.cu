@@ -303,7 +303,7 @@ int fxii_rows_keep_points(fxii_rows* r, int32_t flag) {
 
 int fxii_rows_set_mode(fxii_rows* r, int32_t mode) {
   return guarded([&] {
-    FXII_CHECK(r && (mode == 0 || mode == 1), "bad mode");
+    FXII_CHECK(r && mode >= 0 && mode <= 2, "bad mode");
     r->mode = mode;
   });
 }

@@ -209,7 +209,7 @@ struct fxii_rows {
   cudaStream_t capture_stream = nullptr;
   int64_t graph_cap = 0;
   int graph_kernels = 0;
-  bool buffers_moved = false, last_graph = false;
+  bool buffers_moved = false, last_graph = false, last_coop = false;
   ~fxii_rows() {
     for (auto& e : ev)
       if (e) cudaEventDestroy(e);

@@ -14,6 +14,7 @@
 // This translation unit is compiled with -fmad=false so the fp64 geometry follows the same
 // operation order as the CPU oracle (no FMA contraction).
 #include <cub/cub.cuh>
+#include <vector>
 
 #include "common.cuh"
 
@@ -26,78 +27,89 @@ constexpr double kCollisionD2 = 10.0 * 2.220446049250313e-16;  // dolfinx: d^2 <
 //  [0..2] x0, [3] R, [4..12] Rot row-major, [13] weight multiplier, [14] scale, [15] unused
 constexpr int kFrame = 16;
 
+// Frame of point row r: the K interpolation point on its Γ segment and, for the averaging operators,
+// the rotation taking the reference circle/disk into the plane normal to the segment.
+__device__ __forceinline__ void compute_frame(const double* __restrict__ gx, const int32_t* __restrict__ gcells,
+                                              const int32_t* __restrict__ cells_k, const double* __restrict__ xref, int nip,
+                                              const double* __restrict__ radius, int radius_per_row, int kind, int64_t r,
+                                              double* f) {
+  const double PI = 3.141592653589793;
+  const int64_t i = r / nip;
+  const int j = (int)(r - i * nip);
+  const int c = cells_k[i];
+  const int g0 = gcells[2 * (int64_t)c], g1 = gcells[2 * (int64_t)c + 1];
+  double v0[3], v1[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    v0[d] = gx[3 * (int64_t)g0 + d];
+    v1[d] = gx[3 * (int64_t)g1 + d];
+  }
+  const double X = xref[j];
+  const double omx = 1.0 - X;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) f[d] = v0[d] * omx + v1[d] * X;  // utils.py:18-20
+  if (kind == FXII_OP_TRACE) {
+    f[3] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) f[4 + k] = 0.0;
+    f[13] = 1.0;
+    f[14] = 1.0;
+    f[15] = 0.0;
+    return;
+  }
+  // tangent (utils.py:31-32) then the normalisation of rotation_matrix (quadrature.py:43)
+  double t[3] = {v0[0] - v1[0], v0[1] - v1[1], v0[2] - v1[2]};
+  double nrm = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) t[d] = t[d] / nrm;
+  nrm = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+  double n[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) n[d] = t[d] / nrm;
+  // axis = ez x n ; ez when the cross product vanishes (np.isclose(.,0): <= 1e-8)
+  double a[3] = {-n[1], n[0], 0.0};
+  double an = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+  if (an <= 1.0e-8) {
+    a[0] = 0.0;
+    a[1] = 0.0;
+    a[2] = 1.0;
+  }
+  an = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) a[d] = a[d] / an;
+  const double ct = n[2];
+  const double st = sqrt(1.0 - ct * ct);
+  const double omc = 1.0 - ct;
+  const double sm[9] = {0.0, -a[2], a[1], a[2], 0.0, -a[0], -a[1], a[0], 0.0};
+#pragma unroll
+  for (int p = 0; p < 3; ++p)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const double diag = (p == q) ? ct : 0.0;
+      f[4 + 3 * p + q] = (diag + sm[3 * p + q] * st) + (a[p] * a[q]) * omc;
+    }
+  const double R = radius_per_row ? radius[r] : radius[0];
+  f[3] = R;
+  if (kind == FXII_OP_CIRCLE) {
+    const double scale = 2.0 * R * PI;  // restriction_operators.py:203
+    f[13] = scale;
+    f[14] = scale;
+  } else {  // DISK
+    f[13] = R * R;         // :312
+    f[14] = PI * (R * R);  // :311
+  }
+  f[15] = 0.0;
+}
+
 __global__ void __launch_bounds__(128)
 row_frames_kernel(const double* __restrict__ gx, const int32_t* __restrict__ gcells, const int32_t* __restrict__ cells_k,
                   const double* __restrict__ xref, int nip, const double* __restrict__ radius, int radius_per_row,
                   int kind, int64_t n_point_rows, double* __restrict__ frames) {
-  const double PI = 3.141592653589793;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_point_rows; r += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = r / nip;
-    const int j = (int)(r - i * nip);
-    const int c = cells_k[i];
-    const int g0 = gcells[2 * (int64_t)c], g1 = gcells[2 * (int64_t)c + 1];
-    double v0[3], v1[3];
+    double f[kFrame];
+    compute_frame(gx, gcells, cells_k, xref, nip, radius, radius_per_row, kind, r, f);
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      v0[d] = gx[3 * (int64_t)g0 + d];
-      v1[d] = gx[3 * (int64_t)g1 + d];
-    }
-    const double X = xref[j];
-    double* f = frames + kFrame * r;
-    const double omx = 1.0 - X;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) f[d] = v0[d] * omx + v1[d] * X;  // utils.py:18-20
-    if (kind == FXII_OP_TRACE) {
-      f[3] = 0.0;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) f[4 + k] = 0.0;
-      f[13] = 1.0;
-      f[14] = 1.0;
-      f[15] = 0.0;
-      continue;
-    }
-    // tangent (utils.py:31-32) then the normalisation of rotation_matrix (quadrature.py:43)
-    double t[3] = {v0[0] - v1[0], v0[1] - v1[1], v0[2] - v1[2]};
-    double nrm = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
-#pragma unroll
-    for (int d = 0; d < 3; ++d) t[d] = t[d] / nrm;
-    nrm = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
-    double n[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) n[d] = t[d] / nrm;
-    // axis = ez x n ; ez when the cross product vanishes (np.isclose(.,0): <= 1e-8)
-    double a[3] = {-n[1], n[0], 0.0};
-    double an = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
-    if (an <= 1.0e-8) {
-      a[0] = 0.0;
-      a[1] = 0.0;
-      a[2] = 1.0;
-    }
-    an = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
-#pragma unroll
-    for (int d = 0; d < 3; ++d) a[d] = a[d] / an;
-    const double ct = n[2];
-    const double st = sqrt(1.0 - ct * ct);
-    const double omc = 1.0 - ct;
-    const double sm[9] = {0.0, -a[2], a[1], a[2], 0.0, -a[0], -a[1], a[0], 0.0};
-#pragma unroll
-    for (int p = 0; p < 3; ++p)
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const double diag = (p == q) ? ct : 0.0;
-        f[4 + 3 * p + q] = (diag + sm[3 * p + q] * st) + (a[p] * a[q]) * omc;
-      }
-    const double R = radius_per_row ? radius[r] : radius[0];
-    f[3] = R;
-    if (kind == FXII_OP_CIRCLE) {
-      const double scale = 2.0 * R * PI;  // restriction_operators.py:203
-      f[13] = scale;
-      f[14] = scale;
-    } else {  // DISK
-      f[13] = R * R;         // :312
-      f[14] = PI * (R * R);  // :311
-    }
-    f[15] = 0.0;
+    for (int k = 0; k < kFrame; ++k) frames[kFrame * r + k] = f[k];
   }
 }
 
@@ -422,7 +434,7 @@ __device__ __forceinline__ void make_point(int kind, const double* __restrict__ 
     S = s_in[r];
     return;
   }
-  const double* f = frames + kFrame * r;
+  const double* f = frames;  // the frame of point row r
   if (kind == FXII_OP_TRACE) {
     p[0] = f[0]; p[1] = f[1]; p[2] = f[2];
     W = 1.0;
@@ -510,7 +522,7 @@ pi_locate_tabulate_kernel(const WideNode* __restrict__ nodes, const SceneGrid gr
     const int64_t r = active ? pidx / nq : 0;
     const int l = active ? (int)(pidx - r * nq) : 0;
     double p[3] = {0.0, 0.0, 0.0}, W = 1.0, S = 1.0;
-    if (active) make_point(kind, frames, s_tab, pts_in, w_in, s_in, r, l, pidx, p, W, S);
+    if (active) make_point(kind, frames + kFrame * r, s_tab, pts_in, w_in, s_in, r, l, pidx, p, W, S);
     const LocateResult res = packet ? locate_packet(nodes, grid, cellgeo, x, cell_nodes, padding, p, active)
                                     : (active ? locate_point(nodes, grid, cellgeo, x, cell_nodes, padding, p) : LocateResult{-1, 0, false});
     if (!active) continue;
@@ -911,10 +923,87 @@ __device__ __forceinline__ int team_prefix(bool flag, int team, int team_id, int
   return before + __popc(ball & ((1u << lane) - 1u));
 }
 
+// what a build reports back to the host (one device-to-host copy)
+struct FusedResult {
+  int64_t nnz;
+  PiCounters counters;
+  int conflict;
+  int pad;
+  unsigned long long ns_rows, ns_csr;  // single-kernel path: device time of the two phases (%globaltimer)
+};
+
+// Extra arguments of the single-kernel (cooperative) variant: the inputs of the row frames, which it
+// computes itself, and the outputs of the scan + compaction phase that follows a grid-wide barrier.
+struct CoopArgs {
+  const double* gx;
+  const int32_t* gcells;
+  const int32_t* cells_k;
+  const double* xref;
+  const double* radius;
+  int nip, radius_per_row;
+  unsigned int* barrier;  // arrival counter, zeroed with the workspace
+  unsigned long long* ticket;  // next unit of point rows, zeroed with the workspace
+  int64_t* cta_sum;       // [gridDim.x]
+  int64_t* indptr;
+  int32_t* indices;
+  double* values;
+  int64_t capacity;       // entries indices/values can hold; 0: count only
+  FusedResult* result;
+};
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Barrier over all CTAs of a cooperative launch (co-residency guaranteed by the launch API).
+// `target` = gridDim.x * (number of barriers passed so far + 1); the counter only grows.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v < target) __nanosleep(40);
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// sum over the block (every thread gets it); s_red: 32 slots
+__device__ __forceinline__ int64_t block_sum_i64(int64_t v, int64_t* s_red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int64_t t = 0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[w];
+  __syncthreads();
+  return t;
+}
+
+// frame + point in one out-of-line call: its ~30 live doubles stay out of the traversal's register budget
+__device__ __noinline__ void make_point_with_frame(const CoopArgs& ca, int kind, const double* s_tab,
+                                                   const double* __restrict__ pts_in, const double* __restrict__ w_in,
+                                                   const double* __restrict__ s_in, int64_t r, int l, int64_t pidx, double* p,
+                                                   double& W, double& S) {
+  double fr[kFrame];
+  if (kind != FXII_OP_POINTS)
+    compute_frame(ca.gx, ca.gcells, ca.cells_k, ca.xref, ca.nip, ca.radius, ca.radius_per_row, kind, r, fr);
+  make_point(kind, fr, s_tab, pts_in, w_in, s_in, r, l, pidx, p, W, S);
+}
+
 #ifndef FXII_FUSED_MINBLOCKS
 #define FXII_FUSED_MINBLOCKS 4
 #endif
-template <int ND>
+// COOP: launched cooperatively with one wave of CTAs.  The kernel then also computes the row frames
+// (every lane of a team recomputes its row's frame in registers: SIMT makes that as cheap as one lane
+// doing it) and, after a grid-wide barrier, scans the row lengths and copies the staged rows into the
+// CSR — memset + ONE kernel per build instead of memset + frames + rows + 2 scan kernels + compaction.
+template <int ND, int MODE>  // 0: rows only (frames, scan and compaction are separate kernels); 2: cooperative single kernel
 __global__ void __launch_bounds__(256, FXII_FUSED_MINBLOCKS)
 pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const double* __restrict__ cellgeo,
                 const double* __restrict__ x,
@@ -925,7 +1014,11 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
                 const int32_t* __restrict__ row_dofs,
                 int32_t* __restrict__ out_cell, uint8_t* __restrict__ out_ncoll, double* __restrict__ out_points,
                 int32_t* __restrict__ stage_col, double* __restrict__ stage_val, int64_t* __restrict__ row_cnt,
-                int32_t* __restrict__ src_row, int* __restrict__ conflict, PiCounters* counters) {
+                int32_t* __restrict__ src_row, int* __restrict__ conflict, PiCounters* counters, const CoopArgs ca) {
+  constexpr bool COOP = MODE == 2;
+  constexpr bool FRAMES = MODE >= 1;
+  unsigned long long t_begin = 0;
+  if (COOP && blockIdx.x == 0 && threadIdx.x == 0) t_begin = global_timer_ns();
   extern __shared__ __align__(16) unsigned char s_raw[];
   const int B = blockDim.x;
   const int rpb = B / team;  // point rows per block
@@ -955,8 +1048,31 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
   const int seg = nq * ND;
   const bool in_team = team_id < rpb;      // threads beyond the last whole team idle (B % team != 0 never happens)
   const int64_t n_groups = (n_point_rows + rpb - 1) / rpb;
-  for (int64_t rb = blockIdx.x; rb < n_groups; rb += gridDim.x) {
-    const int64_t r = rb * rpb + team_id;
+  // COOP: rows are handed out dynamically, one ticket per warp (sub-warp teams: 32/team rows) or per
+  // multi-warp team — the single wave of CTAs has no block scheduler behind it to even out slow rows
+  __shared__ long long s_ticket[8];
+  const int unit_rows = team >= 32 ? 1 : 32 / team;
+  const int team_in_unit = team >= 32 ? 0 : (tid & 31) / team;
+  int64_t rb = blockIdx.x;
+  while (true) {
+    int64_t r;
+    if (COOP) {
+      long long tk = 0;
+      if (team <= 32) {
+        if ((tid & 31) == 0) tk = (long long)atomicAdd(ca.ticket, 1ULL);
+        tk = __shfl_sync(0xffffffffu, tk, 0);
+      } else {
+        if (l == 0) s_ticket[team_id & 7] = (long long)atomicAdd(ca.ticket, 1ULL);
+        team_sync(team, team_id);
+        tk = s_ticket[team_id & 7];
+      }
+      if (tk * unit_rows >= n_point_rows) break;
+      r = tk * unit_rows + team_in_unit;
+    } else {
+      if (rb >= n_groups) break;
+      r = rb * rpb + team_id;
+      rb += gridDim.x;
+    }
     const bool active = in_team && r < n_point_rows && l < nq;
     // ---- A: locate + tabulate ------------------------------------------------------------------
     int cell = -1;
@@ -966,7 +1082,13 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
     {
       const int64_t pidx = active ? r * nq + l : 0;
       double p[3] = {0.0, 0.0, 0.0}, W = 1.0, S = 1.0;
-      if (active) make_point(kind, frames, s_tab, pts_in, w_in, s_in, r, l, pidx, p, W, S);
+      if (active) {
+        if (FRAMES) {
+          make_point_with_frame(ca, kind, s_tab, pts_in, w_in, s_in, r, l, pidx, p, W, S);
+        } else {
+          make_point(kind, frames + kFrame * r, s_tab, pts_in, w_in, s_in, r, l, pidx, p, W, S);
+        }
+      }
       const LocateResult res = packet ? locate_packet(nodes, grid, cellgeo, x, cell_nodes, padding, p, active)
                                       : (active ? locate_point(nodes, grid, cellgeo, x, cell_nodes, padding, p) : LocateResult{-1, 0, false});
       if (active) {
@@ -1102,6 +1224,114 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
     }
     team_sync(team, team_id);  // s_cell / s_val / ekey are rewritten by the next row group
   }
+  if (!COOP) return;
+  // ================= scan + compaction (cooperative launch only) ==================================
+  grid_barrier(ca.barrier, gridDim.x);
+  unsigned long long t_rows = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) t_rows = global_timer_ns();
+  const int conf = __ldcg(conflict);
+  if (conf != 0) {  // K dofs shared between point rows: the host reruns the general path
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      ca.result->conflict = conf;
+      ca.result->counters.not_found = __ldcg(&counters->not_found);
+      ca.result->counters.ties = __ldcg(&counters->ties);
+      ca.result->counters.fallback = __ldcg(&counters->fallback);
+    }
+    return;
+  }
+  // shared memory is reused: s_red i64[32] | s_rel i32[B] | s_src i32[B] | s_w i32[32]
+  int64_t* s_red = reinterpret_cast<int64_t*>(s_raw);
+  int32_t* s_rel = reinterpret_cast<int32_t*>(s_red + 32);
+  int32_t* s_src = s_rel + B;
+  int32_t* s_w = s_src + B;
+  const int lane = tid & 31, warp = tid >> 5, n_warps = B >> 5;
+  int32_t* __restrict__ out_idx = ca.indices;
+  double* __restrict__ out_val = ca.values;
+  // contiguous slice of matrix rows per CTA
+  const int64_t per = (n_rows_total + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = min(n_rows_total, (int64_t)blockIdx.x * per), r1 = min(n_rows_total, r0 + per);
+  int64_t local = 0;
+  for (int64_t rho = r0 + tid; rho < r1; rho += B) local += __ldcg(&row_cnt[rho]);
+  local = block_sum_i64(local, s_red);
+  if (tid == 0) ca.cta_sum[blockIdx.x] = local;
+  grid_barrier(ca.barrier, 2u * gridDim.x);
+  int64_t before = 0, total = 0;
+  for (int i = tid; i < (int)gridDim.x; i += B) {
+    const int64_t v = __ldcg(&ca.cta_sum[i]);
+    total += v;
+    if (i < (int)blockIdx.x) before += v;
+  }
+  before = block_sum_i64(before, s_red);
+  total = block_sum_i64(total, s_red);
+  const bool fits = total <= ca.capacity;  // otherwise the host compacts into exact-size arrays
+  int64_t run = before;
+  for (int64_t tile0 = r0; tile0 < r1; tile0 += B) {
+    const int64_t rho = tile0 + tid;
+    const int c = rho < r1 ? (int)__ldcg(&row_cnt[rho]) : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    int wbefore = 0, tile_total = 0;
+    for (int w = 0; w < n_warps; ++w) {
+      const int v = s_w[w];
+      if (w < warp) wbefore += v;
+      tile_total += v;
+    }
+    const int rel = wbefore + incl - c;  // offset of this row inside the tile's output range
+    if (rho < r1) ca.indptr[rho] = run + rel;
+    s_rel[tid] = rel;
+    s_src[tid] = rho < r1 ? __ldcg(&src_row[rho]) - 1 : -1;
+    __syncthreads();
+    if (fits) {
+      // the tile's entries are copied flat: consecutive threads write consecutive CSR slots; the source
+      // row is the last one whose offset is <= the slot (empty rows share the offset of their successor).
+      // Four independent entries per thread keep enough loads in flight.
+      for (int e0 = tid; e0 < tile_total; e0 += 4 * B) {
+        int32_t cv[4];
+        double vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * B;
+          if (e < tile_total) {
+            int lo = 0, hi = B - 1;
+            while (lo < hi) {
+              const int mid = (lo + hi + 1) >> 1;
+              if (s_rel[mid] <= e) lo = mid;
+              else hi = mid - 1;
+            }
+            const int64_t src = (int64_t)s_src[lo] * seg + (e - s_rel[lo]);
+            cv[u] = __ldcg(&stage_col[src]);
+            vv[u] = __ldcg(&stage_val[src]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * B;
+          if (e < tile_total) {
+            out_idx[run + e] = cv[u];
+            out_val[run + e] = vv[u];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    run += tile_total;
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    ca.indptr[n_rows_total] = total;
+    ca.result->nnz = total;
+    ca.result->conflict = 0;
+    ca.result->counters.not_found = __ldcg(&counters->not_found);
+    ca.result->counters.ties = __ldcg(&counters->ties);
+    ca.result->counters.fallback = __ldcg(&counters->fallback);
+    ca.result->ns_rows = t_rows - t_begin;
+    ca.result->ns_csr = global_timer_ns() - t_rows;
+  }
 }
 
 // staging -> CSR: a group of G lanes copies one matrix row.  Nothing is written when the matrix does
@@ -1133,14 +1363,9 @@ struct FusedPlan {
   uint32_t scap;
   size_t smem;
   size_t off_counters, off_conflict, off_src, ws_bytes;  // workspace layout
+  size_t off_barrier, off_result, off_cta;               // single-kernel path
+  int max_grid;
   size_t scan_tmp_bytes;
-};
-
-// what a build reports back to the host, written by three small device-to-host copies
-struct FusedResult {
-  int64_t nnz;
-  PiCounters counters;
-  int conflict;
 };
 
 // false: the fused path does not apply (nq > 256, too much shared memory, empty)
@@ -1173,6 +1398,12 @@ static bool make_fused_plan(const fxii_space* sp, const fxii_rows* rows, FusedPl
   p.off_conflict = p.off_counters + sizeof(PiCounters);
   p.off_src = p.off_conflict + 8;
   p.ws_bytes = p.off_src + sizeof(int32_t) * (size_t)n_rows;
+  // single-kernel path: barrier counter | result | per-CTA sums (one wave: at most 16 CTAs of 128 threads per SM)
+  p.max_grid = num_sms() * 16;
+  p.off_barrier = (p.ws_bytes + 15) & ~(size_t)15;
+  p.off_result = p.off_barrier + 16;
+  p.off_cta = p.off_result + ((sizeof(FusedResult) + 15) & ~(size_t)15);
+  p.ws_bytes = p.off_cta + sizeof(int64_t) * (size_t)p.max_grid;
   p.scan_tmp_bytes = 0;
   FXII_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, p.scan_tmp_bytes, (const long long*)nullptr, (long long*)nullptr,
                                           (int64_t)(n_rows + 1), (cudaStream_t)0));
@@ -1226,12 +1457,12 @@ static void enqueue_fused(const fxii_space* sp, fxii_rows* rows, const FusedPlan
                                        rows->table.p, rows->w.p, rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, rows->nq,
                                        (rows->kind != FXII_OP_POINTS) ? packet_mode() : 0, p.team, p.scap, rows->n_point_rows,
                                        n_rows, rows->row_dofs.p, rows->cell.p, rows->ncoll.p, rows->points.p, rows->coo_cols.p,
-                                       rows->coo_vals.p, row_cnt, src_row, conflict, counters_dev);
+                                       rows->coo_vals.p, row_cnt, src_row, conflict, counters_dev, CoopArgs{});
     FXII_LAUNCHED(1);
     FXII_CUDA(cudaGetLastError());
   };
-  if (sp->nd == 4) launch(pi_fused_kernel<4>);
-  else launch(pi_fused_kernel<10>);
+  if (sp->nd == 4) launch(pi_fused_kernel<4, 0>);
+  else launch(pi_fused_kernel<10, 0>);
   FXII_CUDA(cudaEventRecordWithFlags(ev[2], s, ev_flags));
   size_t tb = p.scan_tmp_bytes;
   FXII_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, tb, (const long long*)row_cnt, (long long*)indptr, (int64_t)(n_rows + 1), s));
@@ -1250,8 +1481,152 @@ static void set_fused_attributes(const fxii_space* sp, const FusedPlan& p) {
     if (carve > 100) carve = 100;
     FXII_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
   };
-  if (sp->nd == 4) set(pi_fused_kernel<4>);
-  else set(pi_fused_kernel<10>);
+  if (sp->nd == 4) {
+    set(pi_fused_kernel<4, 0>);
+    set(pi_fused_kernel<4, 2>);
+  } else {
+    set(pi_fused_kernel<10, 0>);
+    set(pi_fused_kernel<10, 2>);
+  }
+}
+
+// The single cooperative kernel wins while a build is launch-bound (config 2: 0.096 ms against 0.13-0.18 ms
+// for memset + 5 kernels, graph-replayed) and loses once the row phase runs for milliseconds: computing
+// the frames per team costs ~7 % there (13.7 against 12.2 + 0.6 ms on the 1M-segment tree) and the
+// per-CTA scan + copy runs at half the rate of the dedicated kernels.  Measured break-even: ~8 M COO
+// entries; the default switch-over is 4 M.  FXII_COOP=0 disables it, FXII_COOP_MAX_ENTRIES moves it.
+static bool coop_enabled(int64_t E) {
+  static const int64_t max_entries = [] {
+    const char* e = getenv("FXII_COOP");
+    if (e && e[0] == '0') return (int64_t)-1;
+    const char* m = getenv("FXII_COOP_MAX_ENTRIES");
+    return m ? (int64_t)atoll(m) : ((int64_t)1 << 22);
+  }();
+  return E <= max_entries;
+}
+
+// CTAs of the fused kernel that fit one SM (cached per kernel variant and launch shape)
+template <typename K>
+static int fused_blocks_per_sm(K kernel, int B, size_t smem) {
+  struct Key { const void* k; int B; size_t smem; int dev; int n; };
+  static std::vector<Key> cache;
+  int dev = 0;
+  FXII_CUDA(cudaGetDevice(&dev));
+  for (const auto& c : cache)
+    if (c.k == (const void*)kernel && c.B == B && c.smem == smem && c.dev == dev) return c.n;
+  int n = 0;
+  FXII_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, B, smem));
+  cache.push_back({(const void*)kernel, B, smem, dev, n});
+  return n;
+}
+
+// Single-kernel build: workspace memset + ONE cooperative launch (frames, locate, row reduction, scan,
+// compaction), one 56-byte result copy, one host synchronisation.  Without an nnz hint (first build on
+// a handle) the kernel only counts and the compaction runs as a second launch into exact-size arrays.
+// Returns false when K is not cell-local (the caller falls back to the COO path).
+static bool pi_assemble_coop(const fxii_space* sp, fxii_rows* rows, const FusedPlan& p, cudaStream_t s, fxii_csr* out,
+                             PiCounters* h_counters, float* ms_frames, float* ms_locate, float* ms_csr, bool* launched) {
+  *launched = false;
+  const fxii_mesh* m = sp->mesh;
+  const int64_t n_rows = rows->n_rows_total;
+  FusedResult* hr = static_cast<FusedResult*>(rows->host_result);
+  cudaEvent_t* ev = rows->ev;
+  const int64_t n_groups = (rows->n_point_rows + p.rpb - 1) / p.rpb;
+  const int per_sm = sp->nd == 4 ? fused_blocks_per_sm(pi_fused_kernel<4, 2>, p.B, p.smem)
+                                 : fused_blocks_per_sm(pi_fused_kernel<10, 2>, p.B, p.smem);
+  if (per_sm <= 0) return false;
+  const int grid = (int)std::min<int64_t>(std::min<int64_t>(n_groups, (int64_t)per_sm * num_sms()), p.max_grid);
+  const int64_t hint = rows->nnz_hint;
+  out->n_rows = n_rows;
+  out->n_cols = sp->n_dofs;
+  out->indptr.alloc(n_rows + 1, s);
+  if (hint > 0) {
+    out->indices.alloc(hint, s);
+    out->values.alloc(hint, s);
+  }
+  uint8_t* ws = rows->ws.p;
+  CoopArgs ca;
+  ca.gx = rows->gx.p;
+  ca.gcells = rows->gcells.p;
+  ca.cells_k = rows->cells_k.p;
+  ca.xref = rows->xref.p;
+  ca.radius = rows->radius.p;
+  ca.nip = rows->nip;
+  ca.radius_per_row = rows->radius_per_row;
+  ca.barrier = reinterpret_cast<unsigned int*>(ws + p.off_barrier);
+  ca.ticket = reinterpret_cast<unsigned long long*>(ws + p.off_barrier + 8);
+  ca.cta_sum = reinterpret_cast<int64_t*>(ws + p.off_cta);
+  ca.indptr = out->indptr.p;
+  ca.indices = hint > 0 ? out->indices.p : nullptr;
+  ca.values = hint > 0 ? out->values.p : nullptr;
+  ca.capacity = hint > 0 ? hint : 0;
+  ca.result = reinterpret_cast<FusedResult*>(ws + p.off_result);
+  // kernel arguments (by address, cudaLaunchCooperativeKernel)
+  const WideNode* a_nodes = m->wnodes.p;
+  SceneGrid a_grid = m->grid;
+  const double* a_cellgeo = m->cellgeo.p;
+  const double* a_x = m->x.p;
+  const int4* a_cn = reinterpret_cast<const int4*>(m->cell_nodes.p);
+  double a_pad = m->padding;
+  const int32_t* a_dofmap = sp->dofmap.p;
+  const double* a_frames = nullptr;
+  const double* a_table = rows->table.p;
+  const double* a_wq = rows->w.p;
+  const double* a_pts = rows->pts_in.p;
+  const double* a_win = rows->w_in.p;
+  const double* a_sin = rows->s_in.p;
+  int a_kind = rows->kind, a_nq = rows->nq, a_packet = (rows->kind != FXII_OP_POINTS) ? packet_mode() : 0, a_team = p.team;
+  uint32_t a_scap = p.scap;
+  int64_t a_npr = rows->n_point_rows, a_nrows = n_rows;
+  const int32_t* a_rowdofs = rows->row_dofs.p;
+  int32_t* a_cell = rows->cell.p;
+  uint8_t* a_ncoll = rows->ncoll.p;
+  double* a_points = rows->points.p;
+  int32_t* a_scol = rows->coo_cols.p;
+  double* a_sval = rows->coo_vals.p;
+  int64_t* a_rowcnt = reinterpret_cast<int64_t*>(ws);
+  int32_t* a_src = reinterpret_cast<int32_t*>(ws + p.off_src);
+  int* a_conf = reinterpret_cast<int*>(ws + p.off_conflict);
+  PiCounters* a_counters = reinterpret_cast<PiCounters*>(ws + p.off_counters);
+  void* args[] = {&a_nodes, &a_grid, &a_cellgeo, &a_x, &a_cn, &a_pad, &a_dofmap, &a_frames, &a_table, &a_wq, &a_pts, &a_win,
+                  &a_sin, &a_kind, &a_nq, &a_packet, &a_team, &a_scap, &a_npr, &a_nrows, &a_rowdofs, &a_cell, &a_ncoll,
+                  &a_points, &a_scol, &a_sval, &a_rowcnt, &a_src, &a_conf, &a_counters, &ca};
+  FXII_CUDA(cudaMemsetAsync(ws, 0, p.ws_bytes, s));
+  FXII_CUDA(cudaEventRecord(ev[1], s));
+  const void* fn = sp->nd == 4 ? (const void*)pi_fused_kernel<4, 2> : (const void*)pi_fused_kernel<10, 2>;
+  const cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(p.B), args, p.smem, s);
+  if (le != cudaSuccess) {  // e.g. a shared device that cannot hold the wave: use the multi-kernel path
+    cudaGetLastError();
+    return false;
+  }
+  *launched = true;
+  FXII_LAUNCHED(1);
+  FXII_CUDA(cudaEventRecord(ev[2], s));
+  FXII_CUDA(cudaMemcpyAsync(hr, ca.result, sizeof(FusedResult), cudaMemcpyDeviceToHost, s));
+  FXII_CUDA(cudaStreamSynchronize(s));
+  *h_counters = hr->counters;
+  if (hr->conflict) return false;
+  out->nnz = hr->nnz;
+  float ms_extra = 0.f;
+  if (hint <= 0 || hr->nnz > hint) {
+    out->indices.alloc(hr->nnz, s);
+    out->values.alloc(hr->nnz, s);
+    FXII_CUDA(cudaEventRecord(ev[0], s));
+    launch_compact(sp, rows, ws, p, out->indptr.p, hr->nnz, out->indices.p, out->values.p, s);
+    FXII_CUDA(cudaEventRecord(ev[3], s));
+    FXII_CUDA(cudaStreamSynchronize(s));
+    ms_extra = elapsed_ms(ev[0], ev[3]);
+  }
+  rows->nnz_hint = hr->nnz;
+  rows->n_builds += 1;
+  // stage split of the single launch: event duration, apportioned by the in-kernel timers
+  const float ms_kernel = elapsed_ms(ev[1], ev[2]);
+  const double ns_all = (double)hr->ns_rows + (double)hr->ns_csr;
+  const float frac_csr = ns_all > 0 ? (float)((double)hr->ns_csr / ns_all) : 0.f;
+  *ms_frames = 0.f;
+  *ms_csr = ms_kernel * frac_csr + ms_extra;
+  *ms_locate = ms_kernel - ms_kernel * frac_csr;
+  return true;
 }
 
 static void destroy_graph(fxii_rows* rows) {
@@ -1291,6 +1666,17 @@ static bool pi_assemble_fused(const fxii_space* sp, fxii_rows* rows, cudaStream_
   out->n_rows = n_rows;
   out->n_cols = sp->n_dofs;
   const int64_t hint = rows->nnz_hint;
+  rows->last_coop = false;
+  if (coop_enabled(E) && rows->mode != 2) {
+    bool launched = false;
+    rows->last_graph = false;
+    const bool ok = pi_assemble_coop(sp, rows, p, s, out, h_counters, ms_frames, ms_locate, ms_csr, &launched);
+    if (ok) {
+      rows->last_coop = true;
+      return true;
+    }
+    if (launched) return false;  // not cell-local: the COO path takes over
+  }
   auto times = [&] {
     *ms_frames = elapsed_ms(ev[0], ev[1]);
     *ms_locate = elapsed_ms(ev[1], ev[2]);
@@ -1456,7 +1842,7 @@ void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr
     stats->ms_csr = fused ? ms_csr_f : elapsed_ms(ev[2], ev[3]);
     stats->ms_csr_count = ms_count;
     stats->ms_csr_fill = ms_fill;
-    stats->fused = fused ? (rows->last_graph ? 2 : 1) : 0;
+    stats->fused = fused ? (rows->last_coop ? 3 : (rows->last_graph ? 2 : 1)) : 0;
   }
   for (auto& e : ev) cudaEventDestroy(e);
   if (h.not_found > 0)

@@ -157,7 +157,8 @@ class DeviceRows:
         return int(_lib.load().fxii_rows_get_nnz_hint(self._h))
 
     def set_mode(self, mode: int):
-        """0: fused row reduction when possible (default); 1: always materialise the COO."""
+        """0: fused row reduction when possible (default); 1: always materialise the COO;
+        2: fused, as separate kernels + CUDA-graph replay instead of the single cooperative launch."""
         _lib.check(_lib.load().fxii_rows_set_mode(self._h, int(mode)))
 
     def assemble(self, space: DeviceSpace, stream=None, allow_not_found: bool = False):

@@ -98,7 +98,8 @@ int fxii_rows_destroy(fxii_rows* r);
 int fxii_rows_keep_points(fxii_rows* r, int32_t flag);
 /* mode 0 (default): reduce rows inside the locate kernel when every matrix row comes from one point row
  * (cell-local K), falling back to the COO path otherwise; mode 1: always materialise the COO
- * (needed by fxii_rows_download_coo). */
+ * (needed by fxii_rows_download_coo); mode 2: fused, but as separate kernels (frames, rows, scan,
+ * compaction; CUDA-graph replay on reused handles) instead of the single cooperative launch. */
 int fxii_rows_set_mode(fxii_rows* r, int32_t mode);
 /* Expected nnz of the matrix this handle will build (e.g. the nnz of the previous build of the same Γ and
  * operator): the CSR arrays are then allocated before the kernels run and the build synchronises with the
@@ -116,7 +117,10 @@ typedef struct {
   float ms_frames, ms_locate, ms_csr; /* device time of the three stages (CUDA events) */
   float ms_csr_count, ms_csr_fill;    /* the two row kernels inside ms_csr (COO path) */
   int32_t fused;                      /* 1: rows were reduced inside the locate kernel (no COO in HBM);
-                                         2: same, replayed as one CUDA graph launch */
+                                         2: same, replayed as one CUDA graph launch;
+                                         3: same, as ONE cooperative kernel that also computes the row frames,
+                                            scans the row lengths and writes the CSR (ms_frames = 0, ms_locate and
+                                            ms_csr apportion the launch by its in-kernel timers) */
 } fxii_pi_stats;
 
 /* Builds Π (n_rows_total x n_dofs).  Leaves per-point diagnostics on `rows`

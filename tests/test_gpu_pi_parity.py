@@ -159,10 +159,12 @@ def test_fused_p2_disk_many_points(cuda):
     run_case(V, K, gamma, "disk", 0.12, 17, expect_fused=False)  # 289 points per row: COO path
 
 
+@pytest.mark.parametrize("mode", [0, 2])
 @pytest.mark.parametrize("op_name,radius,degree,p", [("trace", None, None, 1), ("circle", 0.05, 15, 1), ("disk", 0.06, 5, 2)])
-def test_repeated_builds_on_one_handle(cuda, op_name, radius, degree, p):
-    """Build 1 reads the nnz back before allocating; build 2+ know it (one host sync) and are
-    replayed as one CUDA graph launch.  All builds must be bitwise identical."""
+def test_repeated_builds_on_one_handle(cuda, op_name, radius, degree, p, mode):
+    """Build 1 reads the nnz back before allocating; build 2+ know it (one host sync).
+    mode 0: every build is ONE cooperative kernel (stats.fused == 3).  mode 2: separate kernels,
+    builds 2+ replayed as one CUDA graph launch.  All builds must be bitwise identical."""
     from fenicsx_ii_b200.interpolation import device_rows, device_space
 
     mesh, V = small_cfg(8, 8, 8, degree=p)
@@ -171,18 +173,43 @@ def test_repeated_builds_on_one_handle(cuda, op_name, radius, degree, p):
     op = make_operator(op_name, gamma, radius, degree)
     ds = device_space(V)
     rows = device_rows(K, op)
+    rows.set_mode(mode)
     results, modes = [], []
     for _ in range(4):
         csr, st = rows.assemble(ds)
         results.append(csr.to_host())
         modes.append(st["fused"])
-    assert modes[0] == 1 and modes[1:] == [2, 2, 2]
+    assert modes == ([3, 3, 3, 3] if mode == 0 else [1, 2, 2, 2])
     for r in results[1:]:
         np.testing.assert_array_equal(r[0], results[0][0])
         np.testing.assert_array_equal(r[1], results[0][1])
         assert r[2].tobytes() == results[0][2].tobytes()
     ref = oracle_pi(V, K, gamma, op_name, radius, degree)
     assert_csr_parity(results[-1], ref)
+
+
+def test_cooperative_and_multi_kernel_paths_agree(cuda):
+    """The single cooperative launch and the multi-kernel fused path must give the same bytes
+    (P2 space, subset of Γ cells so that matrix rows have gaps, per-segment radius)."""
+    from fenicsx_ii_b200.interpolation import device_rows, device_space
+
+    mesh, V = small_cfg(6, 6, 6, degree=2)
+    gamma = sy.polyline_network(150, 1 / 6, n_lines=3, lo=0.3, hi=0.7)
+    K = functionspace(gamma, ("DG", 1))
+    op = make_operator("circle", gamma, 0.07, 9)
+    cells_K = np.arange(5, 140, 3, dtype=np.int32)
+    ds = device_space(V)
+    out = {}
+    for mode in (0, 2):
+        rows = device_rows(K, op, cells_K)
+        rows.set_mode(mode)
+        rows.assemble(ds)
+        csr, st = rows.assemble(ds)  # second build: nnz hint known
+        assert st["fused"] == (3 if mode == 0 else 2)
+        out[mode] = csr.to_host()
+    np.testing.assert_array_equal(out[0][0], out[2][0])
+    np.testing.assert_array_equal(out[0][1], out[2][1])
+    assert out[0][2].tobytes() == out[2][2].tobytes()
 
 
 def test_single_tetrahedron_mesh(cuda):
