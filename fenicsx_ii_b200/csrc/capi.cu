@@ -7,6 +7,7 @@
 namespace fxii {
 void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* cell_nodes, int64_t n_cells,
                 double padding, cudaStream_t s);
+void device_iota(int32_t* a, int64_t n, cudaStream_t s);
 void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr* out, fxii_pi_stats* stats,
                  bool keep_points);
 void csr_transpose(const fxii_csr* a, int64_t c0, int64_t c1, cudaStream_t s, fxii_csr* out);
@@ -43,6 +44,61 @@ void Trace::mark(const char* label) {
   const double t = now();
   fprintf(stderr, "[fxii %s] %-28s %9.3f ms\n", what, label, t - t0);
   t0 = t;
+}
+
+// ---- pools: pinned result slots, timing events ---------------------------------------------------------
+namespace {
+std::mutex g_pool_mutex;
+std::vector<void*> g_free_slots;
+std::vector<std::pair<int, cudaEvent_t>> g_free_events;   // (device, event)
+std::vector<std::pair<cudaEvent_t, int>> g_event_device;  // every event ever created -> its device
+}  // namespace
+
+void* pinned_slot_acquire() {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  if (g_free_slots.empty()) {
+    unsigned char* page = nullptr;
+    FXII_CUDA(cudaMallocHost((void**)&page, 4096));  // never freed: slots live as long as the process
+    for (int i = 0; i < 64; ++i) g_free_slots.push_back(page + 64 * i);
+  }
+  void* p = g_free_slots.back();
+  g_free_slots.pop_back();
+  memset(p, 0, 64);
+  return p;
+}
+
+void pinned_slot_release(void* p) {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  g_free_slots.push_back(p);
+}
+
+// events belong to the device that was current when they were created: the pool is keyed by device
+cudaEvent_t event_acquire() {
+  int dev = 0;
+  FXII_CUDA(cudaGetDevice(&dev));
+  {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    for (size_t i = g_free_events.size(); i-- > 0;) {
+      if (g_free_events[i].first == dev) {
+        cudaEvent_t e = g_free_events[i].second;
+        g_free_events.erase(g_free_events.begin() + (long)i);
+        return e;
+      }
+    }
+  }
+  cudaEvent_t e = nullptr;
+  FXII_CUDA(cudaEventCreate(&e));
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  g_event_device.push_back({e, dev});
+  return e;
+}
+
+void event_release(cudaEvent_t e) {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  int dev = 0;
+  for (const auto& ed : g_event_device)
+    if (ed.first == e) dev = ed.second;
+  g_free_events.push_back({dev, e});
 }
 
 // ---- size-class caching allocator -----------------------------------------------------------------
@@ -230,12 +286,27 @@ int fxii_rows_create(const double* gx, int64_t n_gnodes, const int32_t* gcells, 
   return guarded([&] {
     FXII_CHECK(out && nip >= 1 && n_cells_k >= 0 && n_rows_total >= 0, "bad argument");
     FXII_CHECK(kind == FXII_OP_TRACE || kind == FXII_OP_CIRCLE || kind == FXII_OP_DISK, "bad operator kind");
-    FXII_CHECK(n_cells_k == 0 || (gx && gcells && cells_k && xref && row_dofs), "null argument");
+    FXII_CHECK(n_cells_k == 0 || (gx && gcells && xref), "null argument");
+    FXII_CHECK(cells_k || n_cells_k <= n_gcells, "cells_k == NULL means cells 0..n_cells_k-1: n_cells_k exceeds the cell count");
+    FXII_CHECK(row_dofs || n_cells_k * nip <= n_rows_total, "row_dofs == NULL means rows 0..n_cells_k*nip-1: more than n_rows_total");
     if (kind == FXII_OP_TRACE) nq = 1;
     else FXII_CHECK(nq >= 1 && table && w && radius, "circle/disk operators need table, w and radius");
-    for (int64_t i = 0; i < n_cells_k; ++i)
-      FXII_CHECK(cells_k[i] >= 0 && cells_k[i] < n_gcells, "cells_k out of range");
-    for (int64_t i = 0; i < 2 * n_gcells; ++i) FXII_CHECK(gcells[i] >= 0 && gcells[i] < n_gnodes, "gamma cell node out of range");
+    {  // range checks as min/max reductions (these loops vectorise; an early-exit loop does not)
+      int32_t lo = 0, hi = -1;
+      if (cells_k) {
+        for (int64_t i = 0; i < n_cells_k; ++i) {
+          lo = cells_k[i] < lo ? cells_k[i] : lo;
+          hi = cells_k[i] > hi ? cells_k[i] : hi;
+        }
+        FXII_CHECK(lo >= 0 && hi < n_gcells, "cells_k out of range");
+      }
+      lo = 0, hi = -1;
+      for (int64_t i = 0; i < 2 * n_gcells; ++i) {
+        lo = gcells[i] < lo ? gcells[i] : lo;
+        hi = gcells[i] > hi ? gcells[i] : hi;
+      }
+      FXII_CHECK(lo >= 0 && hi < n_gnodes, "gamma cell node out of range");
+    }
     auto* r = new fxii_rows();
     cudaStream_t s = S(stream);
     try {
@@ -247,9 +318,18 @@ int fxii_rows_create(const double* gx, int64_t n_gnodes, const int32_t* gcells, 
       r->radius_per_row = radius_per_row;
       r->gx.upload(gx, 3 * n_gnodes, s);
       r->gcells.upload(gcells, 2 * n_gcells, s);
-      r->cells_k.upload(cells_k, n_cells_k, s);
+      // NULL cells_k / row_dofs: the identity, generated on the device instead of uploaded
+      if (cells_k) r->cells_k.upload(cells_k, n_cells_k, s);
+      else {
+        r->cells_k.alloc(n_cells_k, s);
+        fxii::device_iota(r->cells_k.p, n_cells_k, s);
+      }
       r->xref.upload(xref, nip, s);
-      r->row_dofs.upload(row_dofs, n_cells_k * nip, s);
+      if (row_dofs) r->row_dofs.upload(row_dofs, n_cells_k * nip, s);
+      else {
+        r->row_dofs.alloc(n_cells_k * nip, s);
+        fxii::device_iota(r->row_dofs.p, n_cells_k * nip, s);
+      }
       if (kind != FXII_OP_TRACE) {
         r->table.upload(table, 3 * (int64_t)nq, s);
         r->w.upload(w, nq, s);

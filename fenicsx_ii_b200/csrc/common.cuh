@@ -55,6 +55,12 @@ inline int grid_for(int64_t work_items, int block, int blocks_per_sm) {
 // stream first synchronises the stream that last used it.
 void* cached_alloc(size_t bytes, cudaStream_t s);
 void cached_free(void* p, cudaStream_t s);
+// pools of small per-handle resources (creating a pinned allocation or an event per handle costs more than
+// a launch-bound build): 64-byte pinned host slots and timing events, recycled for the life of the process
+void* pinned_slot_acquire();
+void pinned_slot_release(void* p);
+cudaEvent_t event_acquire();
+void event_release(cudaEvent_t e);
 void cache_trim();  // return all cached blocks to the driver
 
 // stream-ordered device buffer
@@ -196,7 +202,8 @@ struct fxii_rows {
   bool last_fused = false;
   int64_t nnz_hint = 0;          // expected nnz: the previous fused build on this handle, or set by the caller (0: unknown)
   int n_builds = 0;              // fused builds completed on this handle
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // stage timers, created on first use
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};      // stage timers (fused paths), from the event pool
+  cudaEvent_t ev_coo[4] = {nullptr, nullptr, nullptr, nullptr};  // stage timers (COO path)
   // fused path: workspace and, for graph replay, handle-owned CSR buffers + the captured graph
   fxii::DevBuf<uint8_t> ws, scan_tmp;
   fxii::DevBuf<int64_t> g_indptr;
@@ -212,10 +219,12 @@ struct fxii_rows {
   bool buffers_moved = false, last_graph = false, last_coop = false;
   ~fxii_rows() {
     for (auto& e : ev)
-      if (e) cudaEventDestroy(e);
+      if (e) fxii::event_release(e);
+    for (auto& e : ev_coo)
+      if (e) fxii::event_release(e);
     if (graph_exec) cudaGraphExecDestroy(graph_exec);
     if (capture_stream) cudaStreamDestroy(capture_stream);
-    if (host_result) cudaFreeHost(host_result);
+    if (host_result) fxii::pinned_slot_release(host_result);
   }
   // Γ inputs
   fxii::DevBuf<double> gx;

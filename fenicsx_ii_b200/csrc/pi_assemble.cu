@@ -717,6 +717,12 @@ __global__ void __launch_bounds__(256) iota_kernel(int32_t* __restrict__ a, int6
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] = (int32_t)i;
 }
 
+void device_iota(int32_t* a, int64_t n, cudaStream_t s) {
+  if (n <= 0) return;
+  { iota_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(a, n); FXII_LAUNCHED(1); }
+  FXII_CUDA(cudaGetLastError());
+}
+
 __global__ void __launch_bounds__(256)
 max_u64_kernel(const unsigned long long* __restrict__ a, int64_t n, unsigned long long* __restrict__ out) {
   unsigned long long m = 0;
@@ -1474,6 +1480,13 @@ static void enqueue_fused(const fxii_space* sp, fxii_rows* rows, const FusedPlan
 }
 
 static void set_fused_attributes(const fxii_space* sp, const FusedPlan& p) {
+  // the attributes stick to the kernels: only set them again when the launch shape changes
+  static int last_nd = -1, last_B = -1, last_dev = -1;
+  static size_t last_smem = 0;
+  int dev = 0;
+  FXII_CUDA(cudaGetDevice(&dev));
+  if (last_nd == sp->nd && last_B == p.B && last_smem == p.smem && last_dev == dev) return;
+  last_nd = sp->nd, last_B = p.B, last_smem = p.smem, last_dev = dev;
   auto set = [&](auto kernel) {
     if (p.smem > 48 * 1024) FXII_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     // shared memory for all blocks the register file can hold (1024 threads at 64 registers), the rest stays L1
@@ -1655,9 +1668,10 @@ static bool pi_assemble_fused(const fxii_space* sp, fxii_rows* rows, cudaStream_
   const int64_t n_rows = rows->n_rows_total;
   const int64_t E = rows->n_point_rows * rows->nq * sp->nd;
   if (!rows->ev[0]) {
-    for (auto& e : rows->ev) FXII_CUDA(cudaEventCreate(&e));
+    for (auto& e : rows->ev) e = event_acquire();
   }
-  if (!rows->host_result) FXII_CUDA(cudaMallocHost((void**)&rows->host_result, sizeof(FusedResult)));
+  static_assert(sizeof(FusedResult) <= 64, "FusedResult must fit a pinned slot");
+  if (!rows->host_result) rows->host_result = pinned_slot_acquire();
   FusedResult* hr = static_cast<FusedResult*>(rows->host_result);
   cudaEvent_t* ev = rows->ev;
   set_fused_attributes(sp, p);
@@ -1777,8 +1791,8 @@ void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr
   const int64_t Np = Nr * nq;
   const int64_t E = Np * nd;
   rows->nd = nd;
-  cudaEvent_t ev[4];
-  for (auto& e : ev) FXII_CUDA(cudaEventCreate(&e));
+  // stage timers of the unfused path: created on first use, owned by the handle
+  cudaEvent_t* ev = rows->ev_coo;
   // per-build buffers keep their addresses while their sizes do not change (a captured graph refers to them)
   bool moved = false;
   if (rows->kind != FXII_OP_POINTS) moved |= rows->frames.ensure(kFrame * Nr, s);
@@ -1802,6 +1816,9 @@ void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr
   if (rows->mode != 1) fused = pi_assemble_fused(sp, rows, s, out, &h, &ms_fr_f, &ms_loc_f, &ms_csr_f);
   rows->last_fused = fused;
   if (!fused) {
+    if (!ev[0]) {
+      for (int i = 0; i < 4; ++i) ev[i] = event_acquire();
+    }
     counters.alloc(1, s);
     FXII_CUDA(cudaMemsetAsync(counters.p, 0, sizeof(PiCounters), s));
     FXII_CUDA(cudaEventRecord(ev[0], s));
@@ -1844,7 +1861,6 @@ void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr
     stats->ms_csr_fill = ms_fill;
     stats->fused = fused ? (rows->last_coop ? 3 : (rows->last_graph ? 2 : 1)) : 0;
   }
-  for (auto& e : ev) cudaEventDestroy(e);
   if (h.not_found > 0)
     throw Error(FXII_E_NOT_FOUND, std::to_string(h.not_found) + " of " + std::to_string(Np) +
                                       " points lie in no cell of the 3D mesh (interpolation.py:78)");

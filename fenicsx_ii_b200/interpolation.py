@@ -100,13 +100,20 @@ class DeviceRows:
 
     @classmethod
     def from_gamma(cls, gx, gcells, cells_k, xref, row_dofs, n_rows_total, desc: dict, stream=None) -> "DeviceRows":
+        """`cells_k` None: all cells of Γ in order; `row_dofs` None: rows 0..n_cells*nip-1 (the numbering of
+        Quadrature / DG spaces).  Neither is then uploaded — the library generates them on the device."""
         gx = np.ascontiguousarray(gx, dtype=np.float64)
         gcells = np.ascontiguousarray(gcells, dtype=np.int32)
-        cells_k = np.ascontiguousarray(cells_k, dtype=np.int32)
         xref = np.ascontiguousarray(np.asarray(xref, dtype=np.float64).reshape(-1))
-        row_dofs = np.ascontiguousarray(np.asarray(row_dofs, dtype=np.int32).reshape(-1))
         nip = xref.shape[0]
-        assert row_dofs.shape[0] == cells_k.shape[0] * nip
+        if cells_k is None:
+            n_cells_k = gcells.shape[0]
+        else:
+            cells_k = np.ascontiguousarray(cells_k, dtype=np.int32)
+            n_cells_k = cells_k.shape[0]
+        if row_dofs is not None:
+            row_dofs = np.ascontiguousarray(np.asarray(row_dofs, dtype=np.int32).reshape(-1))
+            assert row_dofs.shape[0] == n_cells_k * nip
         kind, nq = desc["kind"], int(desc["nq"])
         table = w = radius = None
         per_row = 0
@@ -114,20 +121,21 @@ class DeviceRows:
             table = np.ascontiguousarray(desc["table"], dtype=np.float64)
             w = np.ascontiguousarray(desc["w"], dtype=np.float64)
             if "cell_radius" in desc:
-                radius = np.ascontiguousarray(np.repeat(desc["cell_radius"][cells_k], nip), dtype=np.float64)
+                cr = desc["cell_radius"] if cells_k is None else desc["cell_radius"][cells_k]
+                radius = np.ascontiguousarray(np.repeat(cr, nip), dtype=np.float64)
                 per_row = 1
             else:
                 radius = np.ascontiguousarray(desc["radius"], dtype=np.float64)
                 per_row = 1 if desc.get("radius_per_row") else 0
                 if per_row:
-                    assert radius.shape[0] == cells_k.shape[0] * nip
+                    assert radius.shape[0] == n_cells_k * nip
         out = C.c_void_p()
         s = _lib.current_stream() if stream is None else stream
         _lib.check(_lib.load().fxii_rows_create(
-            _lib.ptr(gx), gx.shape[0], _lib.ptr(gcells), gcells.shape[0], _lib.ptr(cells_k), cells_k.shape[0],
+            _lib.ptr(gx), gx.shape[0], _lib.ptr(gcells), gcells.shape[0], _lib.ptr(cells_k), n_cells_k,
             _lib.ptr(xref), nip, _lib.ptr(row_dofs), int(n_rows_total), kind, nq, _lib.ptr(table), _lib.ptr(w),
             _lib.ptr(radius), per_row, s, C.byref(out)))
-        return cls(out, cells_k.shape[0] * nip, nq, int(n_rows_total))
+        return cls(out, n_cells_k * nip, nq, int(n_rows_total))
 
     @classmethod
     def from_points(cls, points, weights, scales, row_dofs, n_rows_total, stream=None) -> "DeviceRows":
@@ -238,27 +246,47 @@ def device_rows(K, red_op, cells_K=None) -> DeviceRows:
     """interpolation.py:41-64: interpolation points of K, cells_K, the operator's quadrature."""
     mesh_to = K.mesh
     ref_points = np.asarray(K.element.interpolation_points, dtype=np.float64)
-    if cells_K is None:
-        n = mesh_to.topology.index_map(mesh_to.topology.dim).size_local
-        cells_K = np.arange(n, dtype=np.int32)
-    cells_K = np.ascontiguousarray(cells_K, dtype=np.int32)
     assert K.element.interpolation_ident
     assert not K.element.needs_dof_transformations
     k_list = np.asarray(K.dofmap.list)
-    all_cells = cells_K.shape[0] == k_list.shape[0] and (cells_K.shape[0] == 0 or (cells_K[0] == 0 and cells_K[-1] == k_list.shape[0] - 1
-                                                                  and bool(np.all(np.diff(cells_K) == 1))))
-    row_dofs = k_list.reshape(-1) if all_cells else k_list[cells_K].reshape(-1)  # no copy for the default cells_K
+    n_cells = mesh_to.topology.index_map(mesh_to.topology.dim).size_local
+    if cells_K is not None:
+        cells_K = np.ascontiguousarray(cells_K, dtype=np.int32)
+        if cells_K.shape[0] == n_cells and (n_cells == 0 or (cells_K[0] == 0 and cells_K[-1] == n_cells - 1
+                                                             and bool(np.all(np.diff(cells_K) == 1)))):
+            cells_K = None  # all cells in order
+    all_cells = cells_K is None and k_list.shape[0] == n_cells
     n_rows_total = K.dofmap.index_map.size_local + K.dofmap.index_map.num_ghosts  # scalar rows; blocks are expanded later
     if k_list.shape[1] != ref_points.shape[0]:
         raise ValueError("K must have one dof per interpolation point")
+    # cell-local numbering (Quadrature / DG spaces): row r of the point rows IS matrix row r; checked once per K
+    identity = False
+    if all_cells:
+        identity = K.__dict__.get("_fxii_identity_dofs") if hasattr(K, "__dict__") else None
+        if identity is None:
+            flat = k_list.reshape(-1)
+            identity = bool(flat.shape[0] <= n_rows_total and np.array_equal(flat, np.arange(flat.shape[0], dtype=flat.dtype)))
+            if hasattr(K, "__dict__"):
+                K.__dict__["_fxii_identity_dofs"] = identity
+    if identity:
+        row_dofs = None
+    else:
+        row_dofs = k_list.reshape(-1) if cells_K is None else k_list[cells_K].reshape(-1)
+
+    def all_or(cells):
+        return np.arange(n_cells, dtype=np.int32) if cells is None else cells
+
     on_device = hasattr(red_op, "device_descriptor") and red_op._mesh is mesh_to and mesh_to.topology.dim == 1 \
         and np.asarray(mesh_to.geometry.dofmap).shape[1] == 2
     if on_device:
         from .restriction_operators import get_physical_points
 
-        desc = red_op.device_descriptor(lambda: get_physical_points(mesh_to, cells_K, ref_points))
-        return DeviceRows.from_gamma(np.asarray(mesh_to.geometry.x), np.asarray(mesh_to.geometry.dofmap), cells_K,
-                                     ref_points, row_dofs, n_rows_total, desc)
+        desc = red_op.device_descriptor(lambda: get_physical_points(mesh_to, all_or(cells_K), ref_points))
+        return DeviceRows.from_gamma(np.asarray(mesh_to.geometry.x), np.asarray(mesh_to.geometry.dofmap),
+                                     cells_K, ref_points, row_dofs, n_rows_total, desc)
+    cells_K = all_or(cells_K)
+    if row_dofs is None:
+        row_dofs = k_list.reshape(-1)
     q = red_op.compute_quadrature(cells_K, ref_points)
     return DeviceRows.from_points(q.points, q.weights, q.scales, row_dofs, n_rows_total)
 

@@ -80,7 +80,8 @@ int fxii_space_destroy(fxii_space* s);
 /* ---- Γ rows ------------------------------------------------------------------------------ */
 /* gx [n_gnodes,3], gcells [n_gcells,2]: Γ geometry.  cells_k [n_cells_k]: Γ cells processed
  * (cells_K of interpolation.py:47-51).  xref [nip]: reference interpolation points of K (:43).
- * row_dofs [n_cells_k*nip]: K.dofmap.list[cells_K] flattened.  table [nq,3], w [nq]: operator
+ * row_dofs [n_cells_k*nip]: K.dofmap.list[cells_K] flattened.  cells_k == NULL: cells 0..n_cells_k-1;
+ * row_dofs == NULL: rows 0..n_cells_k*nip-1 (both then need no upload).  table [nq,3], w [nq]: operator
  * tables (NULL for TRACE).  radius: [n_cells_k*nip] when radius_per_row != 0, else [1]. */
 int fxii_rows_create(const double* gx, int64_t n_gnodes, const int32_t* gcells, int64_t n_gcells,
                      const int32_t* cells_k, int64_t n_cells_k, const double* xref, int32_t nip,
