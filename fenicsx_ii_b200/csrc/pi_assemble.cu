@@ -949,7 +949,7 @@ struct CoopArgs {
   int nip, radius_per_row;
   unsigned int* barrier;  // arrival counter, zeroed with the workspace
   unsigned long long* ticket;  // next unit of point rows, zeroed with the workspace
-  int64_t* cta_sum;       // [gridDim.x]
+  int64_t* cta_sum;       // [gridDim.x] entries per slice of matrix rows, zeroed with the workspace
   int64_t* indptr;
   int32_t* indices;
   double* values;
@@ -1059,6 +1059,9 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
   __shared__ long long s_ticket[8];
   const int unit_rows = team >= 32 ? 1 : 32 / team;
   const int team_in_unit = team >= 32 ? 0 : (tid & 31) / team;
+  // COOP: matrix rows are cut into gridDim.x contiguous slices for the scan phase; the entry count of
+  // every slice is accumulated here, as rows finish, so that phase needs no second grid barrier
+  const int64_t slice_rows = COOP ? max((int64_t)1, (n_rows_total + gridDim.x - 1) / gridDim.x) : 1;
   int64_t rb = blockIdx.x;
   while (true) {
     int64_t r;
@@ -1141,7 +1144,10 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
         const int rho = row_dofs[r];
         if (rho < 0 || rho >= n_rows_total) *conflict = 2;
         else if (atomicCAS(&src_row[rho], 0, (int32_t)r + 1) != 0) *conflict = 1;
-        else row_cnt[rho] = nrow;
+        else {
+          row_cnt[rho] = nrow;
+          if (COOP && nrow) atomicAdd((unsigned long long*)&ca.cta_sum[rho / slice_rows], (unsigned long long)nrow);
+        }
       }
       continue;
     }
@@ -1226,7 +1232,10 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
       const int rho = row_dofs[r];
       if (rho < 0 || rho >= n_rows_total) *conflict = 2;  // bad row index: reported by the general path
       else if (atomicCAS(&src_row[rho], 0, (int32_t)r + 1) != 0) *conflict = 1;  // row produced twice: not cell-local
-      else row_cnt[rho] = base;
+      else {
+        row_cnt[rho] = base;
+        if (COOP && base) atomicAdd((unsigned long long*)&ca.cta_sum[rho / slice_rows], (unsigned long long)base);
+      }
     }
     team_sync(team, team_id);  // s_cell / s_val / ekey are rewritten by the next row group
   }
@@ -1253,14 +1262,8 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
   const int lane = tid & 31, warp = tid >> 5, n_warps = B >> 5;
   int32_t* __restrict__ out_idx = ca.indices;
   double* __restrict__ out_val = ca.values;
-  // contiguous slice of matrix rows per CTA
-  const int64_t per = (n_rows_total + gridDim.x - 1) / gridDim.x;
-  const int64_t r0 = min(n_rows_total, (int64_t)blockIdx.x * per), r1 = min(n_rows_total, r0 + per);
-  int64_t local = 0;
-  for (int64_t rho = r0 + tid; rho < r1; rho += B) local += __ldcg(&row_cnt[rho]);
-  local = block_sum_i64(local, s_red);
-  if (tid == 0) ca.cta_sum[blockIdx.x] = local;
-  grid_barrier(ca.barrier, 2u * gridDim.x);
+  // contiguous slice of matrix rows per CTA; its base offset = the slice totals before it
+  const int64_t r0 = min(n_rows_total, (int64_t)blockIdx.x * slice_rows), r1 = min(n_rows_total, r0 + slice_rows);
   int64_t before = 0, total = 0;
   for (int i = tid; i < (int)gridDim.x; i += B) {
     const int64_t v = __ldcg(&ca.cta_sum[i]);
