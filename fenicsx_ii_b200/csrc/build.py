@@ -47,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     for src in SOURCES:
         obj = HERE / (src[:-3] + ".o")
         cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-               *EXTRA.get(src, []), "-c", str(HERE / src), "-o", str(obj)]
+               *EXTRA.get(src, []), *os.environ.get("FXII_NVCC_FLAGS", "").split(), "-c", str(HERE / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -190,9 +190,12 @@ __device__ __forceinline__ void pull_back(const CellGeo& g, const double* p, dou
 
 // Slow path of the leaf test (some barycentric coordinate negative): exact fp64 padded-box test
 // (dolfinx point_in_bbox, slack 1e-14*extent) and exact point-tetrahedron distance.
-// Returns false when the cell is not a candidate; otherwise d2.
-__device__ __noinline__ bool cell_distance2(const double* __restrict__ x, const int4* __restrict__ cell_nodes, int cell,
-                               const double* p, double padding, double& d2) {
+// Returns -1 when the cell is not a candidate; otherwise d2 (>= 0).
+// (point by value, result by value: a pointer or reference here would pin the caller's point and search state
+// in local memory for the whole traversal)
+__device__ __noinline__ double cell_distance2(const double* __restrict__ x, const int4* __restrict__ cell_nodes, int cell,
+                                              double p0, double p1, double p2, double padding) {
+  const double p[3] = {p0, p1, p2};
   const int4 nd = __ldg(&cell_nodes[cell]);
   const int id[4] = {nd.x, nd.y, nd.z, nd.w};
   double v[4][3];
@@ -205,14 +208,13 @@ __device__ __noinline__ bool cell_distance2(const double* __restrict__ x, const 
     const double lo = fmin(fmin(v[0][d], v[1][d]), fmin(v[2][d], v[3][d])) - padding;
     const double hi = fmax(fmax(v[0][d], v[1][d]), fmax(v[2][d], v[3][d])) + padding;
     const double eps = 1e-14 * (hi - lo);
-    if (!(p[d] >= lo - eps && p[d] <= hi + eps)) return false;
+    if (!(p[d] >= lo - eps && p[d] <= hi + eps)) return -1.0;
   }
   double best = tri_dist2(p, v[1], v[2], v[3]);
   best = fmin(best, tri_dist2(p, v[0], v[2], v[3]));
   best = fmin(best, tri_dist2(p, v[0], v[1], v[3]));
   best = fmin(best, tri_dist2(p, v[0], v[1], v[2]));
-  d2 = best;
-  return true;
+  return best;
 }
 
 struct LocateResult {
@@ -261,8 +263,8 @@ __device__ __forceinline__ void test_cell(const double* __restrict__ cellgeo, co
   far = far || ((X[0] < 0) && (X[0] * X[0] > t1));
   far = far || ((X[1] < 0) && (X[1] * X[1] > t2));
   far = far || ((X[2] < 0) && (X[2] * X[2] > t3));
-  double d2;
-  if (!far && cell_distance2(x, cell_nodes, cell, p, padding, d2)) {
+  const double d2 = far ? -1.0 : cell_distance2(x, cell_nodes, cell, p[0], p[1], p[2], padding);
+  if (d2 >= 0.0) {
     if (d2 < kCollisionD2) {
       st.best = min(st.best, cell);
       ++st.ncoll;
@@ -523,8 +525,9 @@ pi_locate_tabulate_kernel(const WideNode* __restrict__ nodes, const SceneGrid gr
     const int l = active ? (int)(pidx - r * nq) : 0;
     double p[3] = {0.0, 0.0, 0.0}, W = 1.0, S = 1.0;
     if (active) make_point(kind, frames + kFrame * r, s_tab, pts_in, w_in, s_in, r, l, pidx, p, W, S);
-    const LocateResult res = packet ? locate_packet(nodes, grid, cellgeo, x, cell_nodes, padding, p, active)
-                                    : (active ? locate_point(nodes, grid, cellgeo, x, cell_nodes, padding, p) : LocateResult{-1, 0, false});
+    LocateResult res{-1, 0, false};
+    if (packet == 1) res = locate_packet(nodes, grid, cellgeo, x, cell_nodes, padding, p, active);
+    else if (active) res = locate_point(nodes, grid, cellgeo, x, cell_nodes, padding, p);
     if (!active) continue;
     out_cell[pidx] = res.cell;
     out_ncoll[pidx] = (uint8_t)min(res.ncoll, 255);
@@ -738,7 +741,8 @@ max_u64_kernel(const unsigned long long* __restrict__ a, int64_t n, unsigned lon
 static int packet_mode() {
   static const int mode = [] {
     const char* e = getenv("FXII_TRAVERSAL");
-    return (e && std::string(e) == "packet") ? 1 : 0;
+    if (e && std::string(e) == "packet") return 1;
+    return 0;
   }();
   return mode;
 }
@@ -1098,8 +1102,11 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
           make_point(kind, frames + kFrame * r, s_tab, pts_in, w_in, s_in, r, l, pidx, p, W, S);
         }
       }
-      const LocateResult res = packet ? locate_packet(nodes, grid, cellgeo, x, cell_nodes, padding, p, active)
-                                      : (active ? locate_point(nodes, grid, cellgeo, x, cell_nodes, padding, p) : LocateResult{-1, 0, false});
+      // (the packet traversal is only kept in the unfused kernel: a second inlined walk costs this kernel registers —
+      // 12.2 -> 11.0 ms on the 1M-segment tree together with passing the point by value to the slow-path distance.
+      // A batched walk that first collects candidate cells and tests them in a second loop measured 12.2 ms.)
+      LocateResult res{-1, 0, false};
+      if (active) res = locate_point(nodes, grid, cellgeo, x, cell_nodes, padding, p);
       if (active) {
         out_cell[pidx] = res.cell;
         out_ncoll[pidx] = (uint8_t)min(res.ncoll, 255);
