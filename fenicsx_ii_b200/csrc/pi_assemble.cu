@@ -1006,6 +1006,49 @@ __device__ __noinline__ void make_point_with_frame(const CoopArgs& ca, int kind,
   make_point(kind, fr, s_tab, pts_in, w_in, s_in, r, l, pidx, p, W, S);
 }
 
+// Bitonic sort of the 4*team keys of a sub-warp team held four per lane (element e = 4*l + r): the
+// steps that pair elements of different lanes exchange them with shuffles, the others swap registers.
+// Replaces ~120 conflicted 64-bit shared-memory accesses per lane (team of 8) by 48 shuffles.
+__device__ __forceinline__ void cswap(uint64_t& a, uint64_t& b, bool up) {
+  const bool sw = (a > b) == up;
+  const uint64_t lo = sw ? b : a, hi = sw ? a : b;
+  a = lo;
+  b = hi;
+}
+__device__ __forceinline__ void team_sort_regs4(uint64_t (&key)[4], int team, int l) {
+  const uint32_t S = 4u * (uint32_t)team;
+  for (uint32_t k = 2; k <= S; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 4) {
+        const uint32_t lm = j >> 2;                 // partner lane = l ^ lm (inside the team)
+        const bool up = ((4u * (uint32_t)l) & k) == 0;  // k >= 8 here: the direction depends on the lane only
+        const bool lower = ((uint32_t)l & lm) == 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const uint64_t other = __shfl_xor_sync(0xffffffffu, key[r], (int)lm);
+          const bool take_min = lower == up;
+          const bool other_smaller = other < key[r];
+          key[r] = (take_min == other_smaller) ? other : key[r];
+        }
+      } else if (j == 2) {
+        // pairs (0,2), (1,3); direction: k == 4 -> by lane parity, k >= 8 -> by lane
+        const bool up = ((4u * (uint32_t)l) & k) == 0;  // k >= 4: bits of r (0..3) never reach k
+        cswap(key[0], key[2], up);
+        cswap(key[1], key[3], up);
+      } else {  // j == 1: pairs (0,1), (2,3)
+        if (k == 2) {  // direction alternates inside the lane: e & 2
+          cswap(key[0], key[1], true);
+          cswap(key[2], key[3], false);
+        } else {
+          const bool up = ((4u * (uint32_t)l) & k) == 0;
+          cswap(key[0], key[1], up);
+          cswap(key[2], key[3], up);
+        }
+      }
+    }
+  }
+}
+
 #ifndef FXII_FUSED_MINBLOCKS
 #define FXII_FUSED_MINBLOCKS 4
 #endif
@@ -1177,10 +1220,15 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
     int n_cells;
     const int u = team_prefix(leader, team, team_id, l, s_wcnt, n_cells);
     const uint32_t M = (uint32_t)n_cells * ND;
+    const bool reg_sort = ND == 4 && team <= 32;  // sub-warp P1 teams sort in registers (team >= 2 here)
     uint32_t S = 2;
-    while (S < M) S <<= 1;
-    if (team < 32) {  // teams sharing a warp iterate in lockstep: use the warp-wide maximum
-      for (int o = 16; o > 0; o >>= 1) S = max(S, __shfl_xor_sync(0xffffffffu, S, o));
+    if (reg_sort) {
+      S = 4u * (uint32_t)team;
+    } else {
+      while (S < M) S <<= 1;
+      if (team < 32) {  // teams sharing a warp iterate in lockstep: use the warp-wide maximum
+        for (int o = 16; o > 0; o >>= 1) S = max(S, __shfl_xor_sync(0xffffffffu, S, o));
+      }
     }
     for (uint32_t e = M + l; e < S; e += team) ekey[e] = ~0ULL;
     if (leader) {
@@ -1195,6 +1243,16 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
     }
     team_sync(team, team_id);
     // ---- D: team-local bitonic sort -----------------------------------------------------------------
+    if (reg_sort) {
+      uint64_t key[4];
+      const ulonglong2 k01 = *reinterpret_cast<const ulonglong2*>(ekey + 4 * l);
+      const ulonglong2 k23 = *reinterpret_cast<const ulonglong2*>(ekey + 4 * l + 2);
+      key[0] = k01.x, key[1] = k01.y, key[2] = k23.x, key[3] = k23.y;
+      team_sort_regs4(key, team, l);
+      *reinterpret_cast<ulonglong2*>(ekey + 4 * l) = make_ulonglong2(key[0], key[1]);
+      *reinterpret_cast<ulonglong2*>(ekey + 4 * l + 2) = make_ulonglong2(key[2], key[3]);
+      team_sync(team, team_id);
+    } else
     for (uint32_t k = 2; k <= S; k <<= 1) {
       for (uint32_t j = k >> 1; j > 0; j >>= 1) {
         for (uint32_t t = l; t < S / 2; t += team) {
