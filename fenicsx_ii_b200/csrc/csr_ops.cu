@@ -363,24 +363,56 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
         }
       }
     } else
-    for (int64_t ka = a0; ka < a1; ++ka) {
-      const int k = a_idx[ka];
-      const double av = NUMERIC ? a_val[ka] : 0.0;
-      const int64_t b0 = b_ptr[k], b1 = b_ptr[k + 1];
-      if (overflow_limit > 0) {  // group-uniform: read after a barrier
-        // B rows are shorter than the head-room left above the limit, so the table cannot fill up
-        // between two checks
-        overflow = *(volatile int*)&s_new[gid] > overflow_limit;
-        if (overflow) break;
+    {
+      // k-sequential loop (long rows of B, and every block-per-row bin).  The row pointer chain of the NEXT k
+      // (A column -> B row bounds) is requested one iteration ahead, and the entries of B's row are
+      // loaded four per lane before the first insert, so that a row costs one memory latency, not
+      // one per dependent load.
+      int k_n = 0;
+      double av_n = 0.0;
+      int64_t b0_n = 0, b1_n = 0;
+      if (a0 < a1) {
+        k_n = __ldg(&a_idx[a0]);
+        av_n = NUMERIC ? __ldg(&a_val[a0]) : 0.0;
+        b0_n = __ldg(&b_ptr[k_n]);
+        b1_n = __ldg(&b_ptr[k_n + 1]);
       }
-      for (int64_t kb = b0 + tid; kb < b1; kb += nthreads) {
-        bool is_new;
-        const uint32_t slot = hash_insert(keys, tcap, __ldg(&b_idx[kb]), is_new);
-        if (NUMERIC) vals[slot] += av * __ldg(&b_val[kb]);
-        if (overflow_limit > 0 && is_new) atomicAdd(&s_new[gid], 1);
-        if (!NUMERIC && slot == 0xffffffffu) atomicAdd(&s_new[gid], (int)tcap);  // full: force the retry
+      for (int64_t ka = a0; ka < a1; ++ka) {
+        const double av = av_n;
+        const int64_t b0 = b0_n, b1 = b1_n;
+        if (ka + 1 < a1) {
+          k_n = __ldg(&a_idx[ka + 1]);
+          av_n = NUMERIC ? __ldg(&a_val[ka + 1]) : 0.0;
+          b0_n = __ldg(&b_ptr[k_n]);
+          b1_n = __ldg(&b_ptr[k_n + 1]);
+        }
+        if (overflow_limit > 0) {  // group-uniform: read after a barrier
+          // B rows are shorter than the head-room left above the limit, so the table cannot fill up
+          // between two checks
+          overflow = *(volatile int*)&s_new[gid] > overflow_limit;
+          if (overflow) break;
+        }
+        for (int64_t kb0 = b0 + tid; kb0 < b1; kb0 += 4 * (int64_t)nthreads) {
+          int32_t col[4];
+          double bv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int64_t kb = kb0 + u * (int64_t)nthreads;
+            col[u] = kb < b1 ? __ldg(&b_idx[kb]) : kEmpty;
+            bv[u] = (NUMERIC && kb < b1) ? __ldg(&b_val[kb]) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (col[u] == kEmpty) continue;
+            bool is_new;
+            const uint32_t slot = hash_insert(keys, tcap, col[u], is_new);
+            if (NUMERIC) vals[slot] += av * bv[u];
+            if (overflow_limit > 0 && is_new) atomicAdd(&s_new[gid], 1);
+            if (!NUMERIC && slot == 0xffffffffu) atomicAdd(&s_new[gid], (int)tcap);  // full: force the retry
+          }
+        }
+        if (NUMERIC || overflow_limit > 0) group_sync<BLOCK>();
       }
-      if (NUMERIC || overflow_limit > 0) group_sync<BLOCK>();
     }
     group_sync<BLOCK>();
     if (!NUMERIC) {
