@@ -707,9 +707,19 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
   out->values.alloc(nnz, s);
   if (nnz == 0) return;
   tr.mark("bin rows (numeric) + alloc");
+  const bool long_b = b->nnz >= 64 * std::max<int64_t>(b->n_rows, 1);
   for (int bin = 0; bin < kNumBins; ++bin) {
     const int32_t* list = num.sorted_rows.p + num.offset[bin];
     const uint32_t cap = bin < kNumBins - 1 ? bin_cap(bin) : 0;  // 0: exact-size tables in global memory
+    if (long_b) {
+      // long rows of B (>= 64 entries on average): a whole block works on one output row from the 1024-slot bin
+      // on (config 3: 2048-slot bin 85 -> 47 ms; the 512-slot bin measured slower that way) — one pass of the block covers a row of B, and the 16 B/slot table is shared by 4-16 warps instead
+      // of pinning 8-32 KB of shared memory per WARP (6 resident warps per SM in the 2048-slot bin)
+      if (bin <= 3) launch(true, list, num.count[bin], cap, false, 256, 0, row_nnz.p, out->indices.p, out->values.p);
+      else if (bin == 4) launch(true, list, num.count[bin], cap, true, 128, 0, row_nnz.p, out->indices.p, out->values.p);
+      else if (bin == 5) launch(true, list, num.count[bin], cap, true, 256, 0, row_nnz.p, out->indices.p, out->values.p);
+      else launch(true, list, num.count[bin], cap, true, 512, 0, row_nnz.p, out->indices.p, out->values.p);
+    } else
     // warp per row while the tables of a block (16 B per slot and warp) stay within 64 KB; whole blocks above
     if (bin <= 3) launch(true, list, num.count[bin], cap, false, 256, 0, row_nnz.p, out->indices.p, out->values.p);       // <= 512
     else if (bin == 4) launch(true, list, num.count[bin], cap, false, 128, 0, row_nnz.p, out->indices.p, out->values.p);  // 1024
