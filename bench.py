@@ -252,8 +252,8 @@ def run_ours(args):
     values_h = torch.empty(max(nnz_local, 1), dtype=torch.float64).pin_memory().numpy()
 
     def e2e_step():
-        A, _, _ = create_interpolation_matrix(V, K, op)
-        A.device.to_host_into(indptr_h, indices_h, values_h)
+        # the public call with caller-owned pinned result arrays: Γ upload + build + CSR download, one C call each
+        A, _, _ = create_interpolation_matrix(V, K, op, host_out=(indptr_h, indices_h, values_h))
         return A
 
     e2e_steps = max(3, min(args.steps, 10))
@@ -332,7 +332,7 @@ def run_ours(args):
             "points_per_s": np_total / (ms_per_step * 1e-3),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": float(e_all.item()),
-                    "note": "create_interpolation_matrix(V,K,op) with pinned host Γ arrays + CSR download; Ω handle cached",
+                    "note": "create_interpolation_matrix(V,K,op,host_out=pinned arrays): pinned host Γ arrays in, host CSR out; Ω handle cached",
                     "cold_mesh_build_s": mesh_build_s},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -51,6 +51,21 @@ class PiStats(C.Structure):
     ]
 
 
+class RowsDesc(C.Structure):
+    """fxii_rows_desc (include/fxii.h)."""
+
+    _fields_ = [
+        ("gx", C.c_void_p), ("n_gnodes", C.c_int64),
+        ("gcells", C.c_void_p), ("n_gcells", C.c_int64),
+        ("cells_k", C.c_void_p), ("n_cells_k", C.c_int64),
+        ("xref", C.c_void_p), ("nip", C.c_int32),
+        ("row_dofs", C.c_void_p), ("n_rows_total", C.c_int64),
+        ("kind", C.c_int32), ("nq", C.c_int32),
+        ("table", C.c_void_p), ("w", C.c_void_p), ("radius", C.c_void_p),
+        ("radius_per_row", C.c_int32),
+    ]
+
+
 _vp = C.c_void_p
 _i64 = C.c_int64
 _i32 = C.c_int32
@@ -81,6 +96,9 @@ SIGNATURES = {
     "fxii_rows_set_nnz_hint": (C.c_int, [_vp, _i64]),
     "fxii_rows_get_nnz_hint": (C.c_int64, [_vp]),
     "fxii_pi_assemble": (C.c_int, [_vp, _vp, _vp, C.POINTER(_vp), C.POINTER(PiStats)]),
+    "fxii_pi_assemble_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64), C.POINTER(PiStats)]),
+    "fxii_interpolation_matrix_host": (C.c_int, [_vp, C.POINTER(RowsDesc), _i64, _vp, _vp, _vp, _vp, _i64, C.POINTER(_i64),
+                                               C.POINTER(PiStats), C.POINTER(_vp)]),
     "fxii_rows_download_diag": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "fxii_rows_download_coo": (C.c_int, [_vp, _vp, _vp, _vp]),
     "fxii_csr_upload": (C.c_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),

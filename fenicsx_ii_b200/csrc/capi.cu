@@ -279,68 +279,78 @@ int fxii_space_destroy(fxii_space* s) {
   return guarded([&] { delete s; });
 }
 
+// Γ rows handle from its description.  `sync == false` leaves the uploads in flight on `s` (the caller
+// synchronises before the host arrays may change).
+static fxii_rows* make_rows(const fxii_rows_desc& d, cudaStream_t s, bool sync) {
+  int32_t nq = d.nq;
+  FXII_CHECK(d.nip >= 1 && d.n_cells_k >= 0 && d.n_rows_total >= 0, "bad argument");
+  FXII_CHECK(d.kind == FXII_OP_TRACE || d.kind == FXII_OP_CIRCLE || d.kind == FXII_OP_DISK, "bad operator kind");
+  FXII_CHECK(d.n_cells_k == 0 || (d.gx && d.gcells && d.xref), "null argument");
+  FXII_CHECK(d.cells_k || d.n_cells_k <= d.n_gcells, "cells_k == NULL means cells 0..n_cells_k-1: n_cells_k exceeds the cell count");
+  FXII_CHECK(d.row_dofs || d.n_cells_k * d.nip <= d.n_rows_total,
+             "row_dofs == NULL means rows 0..n_cells_k*nip-1: more than n_rows_total");
+  if (d.kind == FXII_OP_TRACE) nq = 1;
+  else FXII_CHECK(nq >= 1 && d.table && d.w && d.radius, "circle/disk operators need table, w and radius");
+  {  // range checks as min/max reductions (these loops vectorise; an early-exit loop does not)
+    int32_t lo = 0, hi = -1;
+    if (d.cells_k) {
+      for (int64_t i = 0; i < d.n_cells_k; ++i) {
+        lo = d.cells_k[i] < lo ? d.cells_k[i] : lo;
+        hi = d.cells_k[i] > hi ? d.cells_k[i] : hi;
+      }
+      FXII_CHECK(lo >= 0 && hi < d.n_gcells, "cells_k out of range");
+    }
+    lo = 0, hi = -1;
+    for (int64_t i = 0; i < 2 * d.n_gcells; ++i) {
+      lo = d.gcells[i] < lo ? d.gcells[i] : lo;
+      hi = d.gcells[i] > hi ? d.gcells[i] : hi;
+    }
+    FXII_CHECK(lo >= 0 && hi < d.n_gnodes, "gamma cell node out of range");
+  }
+  auto* r = new fxii_rows();
+  try {
+    r->kind = d.kind;
+    r->nq = nq;
+    r->nip = d.nip;
+    r->n_point_rows = d.n_cells_k * d.nip;
+    r->n_rows_total = d.n_rows_total;
+    r->radius_per_row = d.radius_per_row;
+    r->gx.upload(d.gx, 3 * d.n_gnodes, s);
+    r->gcells.upload(d.gcells, 2 * d.n_gcells, s);
+    // NULL cells_k / row_dofs: the identity, generated on the device instead of uploaded
+    if (d.cells_k) r->cells_k.upload(d.cells_k, d.n_cells_k, s);
+    else {
+      r->cells_k.alloc(d.n_cells_k, s);
+      fxii::device_iota(r->cells_k.p, d.n_cells_k, s);
+    }
+    r->xref.upload(d.xref, d.nip, s);
+    if (d.row_dofs) r->row_dofs.upload(d.row_dofs, d.n_cells_k * d.nip, s);
+    else {
+      r->row_dofs.alloc(d.n_cells_k * d.nip, s);
+      fxii::device_iota(r->row_dofs.p, d.n_cells_k * d.nip, s);
+    }
+    if (d.kind != FXII_OP_TRACE) {
+      r->table.upload(d.table, 3 * (int64_t)nq, s);
+      r->w.upload(d.w, nq, s);
+      r->radius.upload(d.radius, d.radius_per_row ? d.n_cells_k * d.nip : 1, s);
+    }
+    if (sync) FXII_CUDA(cudaStreamSynchronize(s));
+  } catch (...) {
+    delete r;
+    throw;
+  }
+  return r;
+}
+
 int fxii_rows_create(const double* gx, int64_t n_gnodes, const int32_t* gcells, int64_t n_gcells, const int32_t* cells_k,
                      int64_t n_cells_k, const double* xref, int32_t nip, const int32_t* row_dofs, int64_t n_rows_total,
                      int32_t kind, int32_t nq, const double* table, const double* w, const double* radius,
                      int32_t radius_per_row, void* stream, fxii_rows** out) {
   return guarded([&] {
-    FXII_CHECK(out && nip >= 1 && n_cells_k >= 0 && n_rows_total >= 0, "bad argument");
-    FXII_CHECK(kind == FXII_OP_TRACE || kind == FXII_OP_CIRCLE || kind == FXII_OP_DISK, "bad operator kind");
-    FXII_CHECK(n_cells_k == 0 || (gx && gcells && xref), "null argument");
-    FXII_CHECK(cells_k || n_cells_k <= n_gcells, "cells_k == NULL means cells 0..n_cells_k-1: n_cells_k exceeds the cell count");
-    FXII_CHECK(row_dofs || n_cells_k * nip <= n_rows_total, "row_dofs == NULL means rows 0..n_cells_k*nip-1: more than n_rows_total");
-    if (kind == FXII_OP_TRACE) nq = 1;
-    else FXII_CHECK(nq >= 1 && table && w && radius, "circle/disk operators need table, w and radius");
-    {  // range checks as min/max reductions (these loops vectorise; an early-exit loop does not)
-      int32_t lo = 0, hi = -1;
-      if (cells_k) {
-        for (int64_t i = 0; i < n_cells_k; ++i) {
-          lo = cells_k[i] < lo ? cells_k[i] : lo;
-          hi = cells_k[i] > hi ? cells_k[i] : hi;
-        }
-        FXII_CHECK(lo >= 0 && hi < n_gcells, "cells_k out of range");
-      }
-      lo = 0, hi = -1;
-      for (int64_t i = 0; i < 2 * n_gcells; ++i) {
-        lo = gcells[i] < lo ? gcells[i] : lo;
-        hi = gcells[i] > hi ? gcells[i] : hi;
-      }
-      FXII_CHECK(lo >= 0 && hi < n_gnodes, "gamma cell node out of range");
-    }
-    auto* r = new fxii_rows();
-    cudaStream_t s = S(stream);
-    try {
-      r->kind = kind;
-      r->nq = nq;
-      r->nip = nip;
-      r->n_point_rows = n_cells_k * nip;
-      r->n_rows_total = n_rows_total;
-      r->radius_per_row = radius_per_row;
-      r->gx.upload(gx, 3 * n_gnodes, s);
-      r->gcells.upload(gcells, 2 * n_gcells, s);
-      // NULL cells_k / row_dofs: the identity, generated on the device instead of uploaded
-      if (cells_k) r->cells_k.upload(cells_k, n_cells_k, s);
-      else {
-        r->cells_k.alloc(n_cells_k, s);
-        fxii::device_iota(r->cells_k.p, n_cells_k, s);
-      }
-      r->xref.upload(xref, nip, s);
-      if (row_dofs) r->row_dofs.upload(row_dofs, n_cells_k * nip, s);
-      else {
-        r->row_dofs.alloc(n_cells_k * nip, s);
-        fxii::device_iota(r->row_dofs.p, n_cells_k * nip, s);
-      }
-      if (kind != FXII_OP_TRACE) {
-        r->table.upload(table, 3 * (int64_t)nq, s);
-        r->w.upload(w, nq, s);
-        r->radius.upload(radius, radius_per_row ? n_cells_k * nip : 1, s);
-      }
-      FXII_CUDA(cudaStreamSynchronize(s));
-    } catch (...) {
-      delete r;
-      throw;
-    }
-    *out = r;
+    FXII_CHECK(out, "bad argument");
+    const fxii_rows_desc d{gx, n_gnodes, gcells, n_gcells, cells_k, n_cells_k, xref, nip, row_dofs, n_rows_total,
+                           kind, nq, table, w, radius, radius_per_row};
+    *out = make_rows(d, S(stream), true);
   });
 }
 
@@ -411,6 +421,58 @@ int fxii_pi_assemble(const fxii_space* space, fxii_rows* rows, void* stream, fxi
   } else {
     delete c;
     if (out) *out = nullptr;
+  }
+  return rc;
+}
+
+int fxii_pi_assemble_host(const fxii_space* space, fxii_rows* rows, void* stream, int64_t* indptr, int32_t* indices,
+                          double* values, int64_t capacity, int64_t* nnz_out, fxii_pi_stats* stats) {
+  fxii_csr c;
+  fxii::HostSink sink{indptr, indices, values, capacity, false};
+  int rc = guarded([&] {
+    FXII_CHECK(space && rows && indptr && nnz_out && capacity >= 0 && (capacity == 0 || (indices && values)), "null argument");
+    rows->sink = &sink;
+    try {
+      fxii::pi_assemble(space, rows, S(stream), &c, stats, rows->keep_points);
+    } catch (...) {
+      rows->sink = nullptr;
+      throw;
+    }
+    rows->sink = nullptr;
+  });
+  if (rows) rows->sink = nullptr;
+  if (nnz_out) *nnz_out = c.nnz;
+  if (rc != FXII_OK && rc != FXII_E_NOT_FOUND) return rc;
+  if (sink.done) return rc;
+  const int rc2 = guarded([&] {
+    FXII_CHECK(c.nnz <= capacity, "host arrays too small for the matrix (see *nnz_out)");
+    cudaStream_t s = S(stream);
+    FXII_CUDA(cudaMemcpyAsync(indptr, c.indptr.p, sizeof(int64_t) * (size_t)(c.n_rows + 1), cudaMemcpyDeviceToHost, s));
+    if (c.nnz) {
+      FXII_CUDA(cudaMemcpyAsync(indices, c.indices.p, sizeof(int32_t) * (size_t)c.nnz, cudaMemcpyDeviceToHost, s));
+      FXII_CUDA(cudaMemcpyAsync(values, c.values.p, sizeof(double) * (size_t)c.nnz, cudaMemcpyDeviceToHost, s));
+    }
+    FXII_CUDA(cudaStreamSynchronize(s));
+  });
+  return rc2 != FXII_OK ? rc2 : rc;
+}
+
+int fxii_interpolation_matrix_host(const fxii_space* space, const fxii_rows_desc* desc, int64_t nnz_hint, void* stream,
+                                   int64_t* indptr, int32_t* indices, double* values, int64_t capacity, int64_t* nnz_out,
+                                   fxii_pi_stats* stats, fxii_rows** rows_out) {
+  fxii_rows* r = nullptr;
+  int rc = guarded([&] {
+    FXII_CHECK(space && desc, "null argument");
+    r = make_rows(*desc, S(stream), false);  // uploads stay in flight: the build synchronises before returning
+    if (nnz_hint > 0) r->nnz_hint = nnz_hint;
+  });
+  if (rc == FXII_OK) rc = fxii_pi_assemble_host(space, r, stream, indptr, indices, values, capacity, nnz_out, stats);
+  else cudaStreamSynchronize(S(stream));  // failed half way: nothing may still read the caller's arrays
+  if (rows_out && (rc == FXII_OK || rc == FXII_E_NOT_FOUND)) *rows_out = r;
+  else {
+    if (rows_out) *rows_out = nullptr;
+    cudaStreamSynchronize(S(stream));
+    delete r;
   }
   return rc;
 }

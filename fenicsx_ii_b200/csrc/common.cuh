@@ -115,6 +115,16 @@ struct Trace {
 extern int64_t g_launches;  // kernels launched by this library (fxii_launch_count)
 #define FXII_LAUNCHED(n) (::fxii::g_launches += (n))
 
+// Host destination of a build (fxii_pi_assemble_host): when the build runs as one cooperative launch with a known
+// nnz hint, the CSR download is enqueued behind the kernel BEFORE the single host synchronisation.
+struct HostSink {
+  int64_t* indptr;
+  int32_t* indices;
+  double* values;
+  int64_t capacity;  // entries indices/values can hold
+  bool done;         // the arrays hold the finished matrix
+};
+
 // ---- handle layouts -------------------------------------------------------------------------
 struct alignas(16) BvhNode {  // 64 B: both child boxes live in the parent
   float lo_l[3], hi_l[3];
@@ -217,6 +227,7 @@ struct fxii_rows {
   int64_t graph_cap = 0;
   int graph_kernels = 0;
   bool buffers_moved = false, last_graph = false, last_coop = false;
+  fxii::HostSink* sink = nullptr;  // set for the duration of fxii_pi_assemble_host
   ~fxii_rows() {
     for (auto& e : ev)
       if (e) fxii::event_release(e);

@@ -1684,10 +1684,20 @@ static bool pi_assemble_coop(const fxii_space* sp, fxii_rows* rows, const FusedP
   FXII_LAUNCHED(1);
   FXII_CUDA(cudaEventRecord(ev[2], s));
   FXII_CUDA(cudaMemcpyAsync(hr, ca.result, sizeof(FusedResult), cudaMemcpyDeviceToHost, s));
+  // host destination: the download is speculated on the hint and rides behind the kernel, before the one sync
+  int64_t speculated = -1;
+  if (rows->sink && hint > 0 && rows->sink->capacity >= hint) {
+    HostSink* k = rows->sink;
+    FXII_CUDA(cudaMemcpyAsync(k->indptr, out->indptr.p, sizeof(int64_t) * (size_t)(n_rows + 1), cudaMemcpyDeviceToHost, s));
+    FXII_CUDA(cudaMemcpyAsync(k->indices, out->indices.p, sizeof(int32_t) * (size_t)hint, cudaMemcpyDeviceToHost, s));
+    FXII_CUDA(cudaMemcpyAsync(k->values, out->values.p, sizeof(double) * (size_t)hint, cudaMemcpyDeviceToHost, s));
+    speculated = hint;
+  }
   FXII_CUDA(cudaStreamSynchronize(s));
   *h_counters = hr->counters;
   if (hr->conflict) return false;
   out->nnz = hr->nnz;
+  if (rows->sink && speculated >= hr->nnz) rows->sink->done = true;  // the kernel compacted (nnz <= hint) and all of it was copied
   float ms_extra = 0.f;
   if (hint <= 0 || hr->nnz > hint) {
     out->indices.alloc(hr->nnz, s);

@@ -98,9 +98,10 @@ class DeviceRows:
         self.n_point_rows, self.nq, self.n_rows_total = n_point_rows, nq, n_rows_total
         self.nd = None
 
-    @classmethod
-    def from_gamma(cls, gx, gcells, cells_k, xref, row_dofs, n_rows_total, desc: dict, stream=None) -> "DeviceRows":
-        """`cells_k` None: all cells of Γ in order; `row_dofs` None: rows 0..n_cells*nip-1 (the numbering of
+    @staticmethod
+    def _gamma_desc(gx, gcells, cells_k, xref, row_dofs, n_rows_total, desc: dict):
+        """fxii_rows_desc of a Γ-described build + the arrays it points into (keep them alive during the call).
+        `cells_k` None: all cells of Γ in order; `row_dofs` None: rows 0..n_cells*nip-1 (the numbering of
         Quadrature / DG spaces).  Neither is then uploaded — the library generates them on the device."""
         gx = np.ascontiguousarray(gx, dtype=np.float64)
         gcells = np.ascontiguousarray(gcells, dtype=np.int32)
@@ -129,13 +130,48 @@ class DeviceRows:
                 per_row = 1 if desc.get("radius_per_row") else 0
                 if per_row:
                     assert radius.shape[0] == n_cells_k * nip
+        keep = (gx, gcells, cells_k, xref, row_dofs, table, w, radius)
+
+        def addr(a):
+            return None if a is None else a.ctypes.data
+
+        d = _lib.RowsDesc(addr(gx), gx.shape[0], addr(gcells), gcells.shape[0], addr(cells_k), n_cells_k, addr(xref), nip,
+                          addr(row_dofs), int(n_rows_total), kind, nq, addr(table), addr(w), addr(radius), per_row)
+        return d, keep, n_cells_k * nip, (1 if kind == _lib.OP_TRACE else nq)
+
+    @classmethod
+    def from_gamma(cls, gx, gcells, cells_k, xref, row_dofs, n_rows_total, desc: dict, stream=None) -> "DeviceRows":
+        d, keep, n_point_rows, nq = cls._gamma_desc(gx, gcells, cells_k, xref, row_dofs, n_rows_total, desc)
         out = C.c_void_p()
         s = _lib.current_stream() if stream is None else stream
         _lib.check(_lib.load().fxii_rows_create(
-            _lib.ptr(gx), gx.shape[0], _lib.ptr(gcells), gcells.shape[0], _lib.ptr(cells_k), n_cells_k,
-            _lib.ptr(xref), nip, _lib.ptr(row_dofs), int(n_rows_total), kind, nq, _lib.ptr(table), _lib.ptr(w),
-            _lib.ptr(radius), per_row, s, C.byref(out)))
-        return cls(out, n_cells_k * nip, nq, int(n_rows_total))
+            d.gx, d.n_gnodes, d.gcells, d.n_gcells, d.cells_k, d.n_cells_k, d.xref, d.nip, d.row_dofs, d.n_rows_total,
+            d.kind, d.nq, d.table, d.w, d.radius, d.radius_per_row, s, C.byref(out)))
+        return cls(out, n_point_rows, nq, int(n_rows_total))
+
+    @classmethod
+    def build_to_host(cls, space: "DeviceSpace", gamma_args: tuple, indptr, indices, values, nnz_hint: int = 0, stream=None):
+        """One C call (fxii_interpolation_matrix_host): upload Γ + operator, build Π, download the CSR into the
+        caller's host arrays, one synchronisation.  `gamma_args` = the arguments of `from_gamma`.
+        Returns (DeviceRows, nnz, PiStats)."""
+        _lib.require_cuda()
+        d, keep, n_point_rows, nq = cls._gamma_desc(*gamma_args)
+        assert indptr.dtype == np.int64 and indices.dtype == np.int32 and values.dtype == np.float64
+        assert indptr.shape[0] >= d.n_rows_total + 1 and indices.shape[0] == values.shape[0]
+        out, st, nnz = C.c_void_p(), _lib.PiStats(), C.c_int64()
+        s = _lib.current_stream() if stream is None else stream
+        rc = _lib.load().fxii_interpolation_matrix_host(space._h, C.byref(d), int(nnz_hint), s, _lib.ptr(indptr), _lib.ptr(indices),
+                                                        _lib.ptr(values), int(indices.shape[0]), C.byref(nnz), C.byref(st),
+                                                        C.byref(out))
+        del keep
+        if rc == _lib.FXII_E_INVALID and nnz.value > indices.shape[0]:
+            raise ValueError(f"host arrays hold {indices.shape[0]} entries, the matrix has {nnz.value}")
+        if rc != _lib.FXII_OK and out.value:
+            _lib.load().fxii_rows_destroy(out)
+        _lib.check(rc)
+        rows = cls(out, n_point_rows, nq, int(d.n_rows_total))
+        rows.nd = space.nd
+        return rows, int(nnz.value), PiStats({k: getattr(st, k) for k, _ in _lib.PiStats._fields_})
 
     @classmethod
     def from_points(cls, points, weights, scales, row_dofs, n_rows_total, stream=None) -> "DeviceRows":
@@ -163,6 +199,25 @@ class DeviceRows:
 
     def nnz_hint(self) -> int:
         return int(_lib.load().fxii_rows_get_nnz_hint(self._h))
+
+    def assemble_to_host(self, space: DeviceSpace, indptr, indices, values, stream=None, allow_not_found: bool = False):
+        """Run the Π assembly and deliver the CSR into caller-owned host arrays (int64 / int32 / float64,
+        C-contiguous, ideally pinned): with an nnz hint the download rides behind the kernel, before the
+        build's single host synchronisation.  Returns (nnz, PiStats)."""
+        assert indptr.dtype == np.int64 and indices.dtype == np.int32 and values.dtype == np.float64
+        assert indptr.shape[0] >= self.n_rows_total + 1 and indices.shape[0] == values.shape[0]
+        st = _lib.PiStats()
+        nnz = C.c_int64()
+        s = _lib.current_stream() if stream is None else stream
+        rc = _lib.load().fxii_pi_assemble_host(space._h, self._h, s, _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(values),
+                                               int(indices.shape[0]), C.byref(nnz), C.byref(st))
+        self.nd = space.nd
+        stats = PiStats({k: getattr(st, k) for k, _ in _lib.PiStats._fields_})
+        if rc == _lib.FXII_E_INVALID and nnz.value > indices.shape[0]:
+            raise ValueError(f"host arrays hold {indices.shape[0]} entries, the matrix has {nnz.value}")
+        if not (rc == _lib.FXII_E_NOT_FOUND and allow_not_found):
+            _lib.check(rc)
+        return int(nnz.value), stats
 
     def set_mode(self, mode: int):
         """0: fused row reduction when possible (default); 1: always materialise the COO;
@@ -242,8 +297,10 @@ def device_space(V, tol: float = 1.0e-8) -> DeviceSpace:
     return dspace
 
 
-def device_rows(K, red_op, cells_K=None) -> DeviceRows:
-    """interpolation.py:41-64: interpolation points of K, cells_K, the operator's quadrature."""
+def device_rows(K, red_op, cells_K=None, args_only: bool = False):
+    """interpolation.py:41-64: interpolation points of K, cells_K, the operator's quadrature.
+    `args_only`: return the arguments of ``DeviceRows.from_gamma`` instead of a handle (None when the operator
+    has no device descriptor)."""
     mesh_to = K.mesh
     ref_points = np.asarray(K.element.interpolation_points, dtype=np.float64)
     assert K.element.interpolation_ident
@@ -282,8 +339,13 @@ def device_rows(K, red_op, cells_K=None) -> DeviceRows:
         from .restriction_operators import get_physical_points
 
         desc = red_op.device_descriptor(lambda: get_physical_points(mesh_to, all_or(cells_K), ref_points))
-        return DeviceRows.from_gamma(np.asarray(mesh_to.geometry.x), np.asarray(mesh_to.geometry.dofmap),
-                                     cells_K, ref_points, row_dofs, n_rows_total, desc)
+        gamma_args = (np.asarray(mesh_to.geometry.x), np.asarray(mesh_to.geometry.dofmap), cells_K, ref_points, row_dofs,
+                      n_rows_total, desc)
+        if args_only:
+            return gamma_args
+        return DeviceRows.from_gamma(*gamma_args)
+    if args_only:
+        return None
     cells_K = all_or(cells_K)
     if row_dofs is None:
         row_dofs = k_list.reshape(-1)
@@ -308,7 +370,8 @@ def _cache_key(V, K, red_op, tol, cells_K):
 
 
 def create_interpolation_matrix(V, K, red_op, tol: float = 1.0e-8, use_petsc: bool = False, cells_K=None,
-                                complex_dtype: bool = False, materialize_coo: bool = False, cache: bool = False):
+                                complex_dtype: bool = False, materialize_coo: bool = False, cache: bool = False,
+                                host_out=None):
     """Create an interpolation matrix from `V` to `K` with a specific reduction operator applied to
     the interpolation points of `K`.
 
@@ -323,6 +386,9 @@ def create_interpolation_matrix(V, K, red_op, tol: float = 1.0e-8, use_petsc: bo
         materialize_coo: (extension) force the unfused COO path, e.g. to inspect the COO.
         cache: (extension) reuse the matrix of an earlier call with the same `V`, `K`, `red_op`,
             `tol` and `cells_K` objects (see ``clear_interpolation_cache``).
+        host_out: (extension) ``(indptr int64[rows+1], indices int32[cap], values float64[cap])`` host arrays,
+            ideally pinned: the matrix is delivered into them (the returned ``MatrixCSR`` holds views) and the
+            download overlaps the build's only host synchronisation.  ``ValueError`` if ``cap < nnz``.
 
     Returns:
         ``(A, imap_K, imap_V)``: the matrix and the (serial: unchanged) index maps of K and V.
@@ -339,6 +405,19 @@ def create_interpolation_matrix(V, K, red_op, tol: float = 1.0e-8, use_petsc: bo
     if bs != int(getattr(K.dofmap, "bs", 1)):
         raise NotImplementedError("V and K must have the same block size")
     dspace = device_space(V, tol)
+    if host_out is not None and bs == 1 and not use_petsc and not materialize_coo:
+        gamma_args = device_rows(K, red_op, cells_K, args_only=True)
+        if gamma_args is not None:
+            # host arrays in, host CSR out: ONE C call and one synchronisation
+            hints = red_op.__dict__.setdefault("_fxii_nnz_hints", {}) if hasattr(red_op, "__dict__") else {}
+            hkey = (id(K), id(V), None if cells_K is None else len(cells_K))
+            indptr_h, indices_h, values_h = host_out
+            rows, nnz, stats = DeviceRows.build_to_host(dspace, gamma_args, indptr_h, indices_h, values_h, hints.get(hkey, 0))
+            hints[hkey] = nnz
+            n_rows = rows.n_rows_total
+            A = MatrixCSR(None, stats=stats, rows=rows, host=(indptr_h[: n_rows + 1], indices_h[:nnz], values_h[:nnz]),
+                          shape=(n_rows, dspace.n_dofs))
+            return A, imap_K, imap_V
     rows = device_rows(K, red_op, cells_K)
     if materialize_coo:
         rows.set_mode(1)
@@ -347,6 +426,15 @@ def create_interpolation_matrix(V, K, red_op, tol: float = 1.0e-8, use_petsc: bo
     hkey = (id(K), id(V), None if cells_K is None else len(cells_K))
     if hkey in hints:
         rows.set_nnz_hint(hints[hkey])
+    if host_out is not None and bs == 1 and not use_petsc:
+        # straight into the caller's (pinned) host arrays: one C call, one synchronisation
+        indptr_h, indices_h, values_h = host_out
+        nnz, stats = rows.assemble_to_host(dspace, indptr_h, indices_h, values_h)
+        hints[hkey] = nnz
+        n_rows = rows.n_rows_total
+        A = MatrixCSR(None, stats=stats, rows=rows, host=(indptr_h[: n_rows + 1], indices_h[:nnz], values_h[:nnz]),
+                      shape=(n_rows, dspace.n_dofs))
+        return A, imap_K, imap_V
     csr, stats = rows.assemble(dspace)
     hints[hkey] = csr.nnz
     if bs > 1:

@@ -163,20 +163,30 @@ class MatrixCSR:
     ``dolfinx.la.MatrixCSR`` the callers use (``indptr``, ``indices``, ``data``, ``to_scipy``,
     ``to_dense``) over a device-resident matrix.  Host arrays are downloaded on first access."""
 
-    def __init__(self, device: DeviceCSR, stats=None, rows=None):
-        self.device = device
+    def __init__(self, device: "DeviceCSR | None", stats=None, rows=None, host=None, shape=None):
+        self._device = device
         self.stats = stats
         self.rows = rows  # DeviceRows of the build (per-point diagnostics), may be None
-        self._host = None
+        self._host = host  # (indptr, indices, data) when the build delivered host arrays directly
+        self._shape = tuple(shape) if shape is not None else None
+        assert device is not None or (host is not None and shape is not None)
+
+    @property
+    def device(self) -> DeviceCSR:
+        """The device-resident matrix (uploaded on first use when the build delivered host arrays)."""
+        if self._device is None:
+            a, b, c = self._host
+            self._device = DeviceCSR.from_host(a, b, c, self._shape)
+        return self._device
 
     def _arrays(self):
         if self._host is None:
-            self._host = self.device.to_host()
+            self._host = self._device.to_host()
         return self._host
 
     @property
     def shape(self):
-        return self.device.shape
+        return self._shape if self._device is None else self._device.shape
 
     @property
     def indptr(self):
@@ -213,7 +223,7 @@ class MatrixCSR:
         except ImportError as e:
             raise RuntimeError("use_petsc=True needs petsc4py, which is not installed") from e
         a, b, c = self._arrays()
-        if self.device.nnz >= 2**31 and PETSc.IntType().itemsize == 4:
+        if b.shape[0] >= 2**31 and PETSc.IntType().itemsize == 4:
             raise RuntimeError("matrix needs 64-bit PETSc indices")
         A = PETSc.Mat().createAIJ(size=self.shape, csr=(a.astype(PETSc.IntType), b.astype(PETSc.IntType), c))
         A.assemble()

@@ -108,6 +108,18 @@ int fxii_rows_set_mode(fxii_rows* r, int32_t mode);
 int fxii_rows_set_nnz_hint(fxii_rows* r, int64_t nnz);
 int64_t fxii_rows_get_nnz_hint(const fxii_rows* r);
 
+/* The arguments of fxii_rows_create as one record (same meaning, same NULL conventions). */
+typedef struct {
+  const double* gx; int64_t n_gnodes;
+  const int32_t* gcells; int64_t n_gcells;
+  const int32_t* cells_k; int64_t n_cells_k;
+  const double* xref; int32_t nip;
+  const int32_t* row_dofs; int64_t n_rows_total;
+  int32_t kind, nq;
+  const double* table; const double* w; const double* radius;
+  int32_t radius_per_row;
+} fxii_rows_desc;
+
 /* ---- Π assembly -------------------------------------------------------------------------- */
 typedef struct {
   int64_t n_points;     /* Np = n_point_rows*nq */
@@ -128,6 +140,23 @@ typedef struct {
  * (fxii_rows_download_diag).  Returns FXII_E_NOT_FOUND when n_not_found > 0. */
 int fxii_pi_assemble(const fxii_space* space, fxii_rows* rows, void* stream, fxii_csr** out,
                      fxii_pi_stats* stats);
+/* The same build delivered to HOST arrays (the shape of the reference's create_interpolation_matrix,
+ * interpolation.py:15-23, which returns a host matrix): indptr i64[n_rows_total+1], indices i32[capacity],
+ * values f64[capacity], caller-allocated and ideally pinned.  With an nnz hint on `rows` the download is
+ * enqueued behind the kernels before the single host synchronisation.  *nnz_out = nnz of the matrix;
+ * FXII_E_INVALID when it exceeds `capacity` (nothing but *nnz_out is then valid). */
+int fxii_pi_assemble_host(const fxii_space* space, fxii_rows* rows, void* stream, int64_t* indptr,
+                          int32_t* indices, double* values, int64_t capacity, int64_t* nnz_out,
+                          fxii_pi_stats* stats);
+/* create_interpolation_matrix (interpolation.py:15-23) in ONE call, host arrays in, host CSR out: uploads Γ and the
+ * operator (asynchronously when the arrays are pinned), builds Π and downloads it, synchronising `stream` once
+ * before returning — the host arrays only have to stay valid during the call.  nnz_hint: nnz of an earlier build
+ * of the same problem (0: unknown; the build then takes two synchronisations).  rows_out (may be NULL) receives the
+ * rows handle for fxii_rows_download_diag; destroy it with fxii_rows_destroy. */
+int fxii_interpolation_matrix_host(const fxii_space* space, const fxii_rows_desc* desc, int64_t nnz_hint,
+                                   void* stream, int64_t* indptr, int32_t* indices, double* values,
+                                   int64_t capacity, int64_t* nnz_out, fxii_pi_stats* stats,
+                                   fxii_rows** rows_out);
 /* owning cell i32[Np], colliding-set size u8[Np] (saturating), points f64[Np,3] (any may be NULL) */
 int fxii_rows_download_diag(const fxii_rows* rows, int32_t* cell, uint8_t* n_colliding,
                             double* points, void* stream);

@@ -57,6 +57,12 @@ def main():
     def download():
         csr.to_host_into(indptr_h, indices_h, values_h)
 
+    def assemble_host_reused():
+        rows.assemble_to_host(ds, indptr_h, indices_h, values_h)
+
+    def full_host_out():
+        create_interpolation_matrix(V, K, op, host_out=(indptr_h, indices_h, values_h))
+
     def full():
         A, _, _ = create_interpolation_matrix(V, K, op)
         A.device.to_host_into(indptr_h, indices_h, values_h)
@@ -64,7 +70,9 @@ def main():
     print(f"config {args.config}: rows {K.num_dofs}, nnz {nnz}, CSR bytes {8 * (K.num_dofs + 1) + 12 * nnz}")
     for name, fn in [("device_rows (H2D of Γ + operator)", make_rows), ("assemble, reused handle", assemble_reused),
                      ("device_rows + assemble (fresh handle, hint)", assemble_fresh), ("CSR download (D2H)", download),
-                     ("create_interpolation_matrix + download", full)]:
+                     ("create_interpolation_matrix + download", full),
+                     ("assemble_to_host, reused handle", assemble_host_reused),
+                     ("create_interpolation_matrix(host_out=...): one C call", full_host_out)]:
         med, best = timeit(fn)
         print(f"  {name:48s} median {med:8.4f} ms   min {best:8.4f} ms")
 

@@ -323,3 +323,58 @@ def test_unstructured_delaunay_mesh(cuda, degree):
     np.testing.assert_allclose(np.asarray(A.to_scipy().sum(axis=1)).ravel(), 1.0, atol=1e-9)
     run_case(V, K, gamma, "circle", 0.07, 15, expect_fused=True)
     run_case(V, K, gamma, "disk", 0.05, 4, expect_fused=True)
+
+
+def test_build_delivered_to_host_arrays(cuda):
+    """create_interpolation_matrix(..., host_out=...) — fxii_pi_assemble_host — gives the same bytes as the
+    device-resident build + download, on the first call (no nnz hint) and on later ones (speculated download)."""
+    import torch
+
+    from fenicsx_ii_b200 import create_interpolation_matrix
+
+    mesh, V = small_cfg(8, 8, 8, degree=1)
+    gamma = sy.polyline_network(300, 1 / 8, n_lines=4, lo=0.25, hi=0.75)
+    K = functionspace(gamma, ("Quadrature", 4))
+    for op_name, radius, degree in (("trace", None, None), ("circle", 0.06, 9)):
+        op = make_operator(op_name, gamma, radius, degree)
+        A0, _, _ = create_interpolation_matrix(V, K, op)
+        ref = (A0.indptr.copy(), A0.indices.copy(), A0.data.copy())
+        cap = ref[1].shape[0] + 17
+        ip = torch.empty(K.num_dofs + 1, dtype=torch.int64).pin_memory().numpy()
+        ix = torch.empty(cap, dtype=torch.int32).pin_memory().numpy()
+        va = torch.empty(cap, dtype=torch.float64).pin_memory().numpy()
+        op2 = make_operator(op_name, gamma, radius, degree)  # fresh operator: no nnz hint on the first call
+        for _ in range(3):
+            ix[:] = -7
+            A, _, _ = create_interpolation_matrix(V, K, op2, host_out=(ip, ix, va))
+            assert A.shape == A0.shape
+            np.testing.assert_array_equal(A.indptr, ref[0])
+            np.testing.assert_array_equal(A.indices, ref[1])
+            assert A.data.tobytes() == ref[2].tobytes()
+        # the device matrix is rebuilt from the host arrays on demand
+        y = A.mult(np.ones(V.num_dofs))
+        np.testing.assert_allclose(y, A0.mult(np.ones(V.num_dofs)), rtol=0, atol=0)
+        small = (ip, ix[:5], va[:5])
+        with pytest.raises(ValueError):
+            create_interpolation_matrix(V, K, make_operator(op_name, gamma, radius, degree), host_out=small)
+
+
+def test_host_delivery_of_a_generic_operator(cuda):
+    """Operators without a device descriptor (uploaded points) take fxii_pi_assemble_host instead of the one-shot call."""
+    import torch
+
+    from fenicsx_ii_b200 import MappedRestriction, create_interpolation_matrix
+
+    mesh, V = small_cfg(6, 6, 6, degree=1)
+    gamma = sy.polyline_network(60, 1 / 6, n_lines=2, lo=0.3, hi=0.7)
+    K = functionspace(gamma, ("DG", 1))
+    op = MappedRestriction(gamma, lambda x: x + 0.01)
+    A0, _, _ = create_interpolation_matrix(V, K, op)
+    ip = torch.empty(K.num_dofs + 1, dtype=torch.int64).pin_memory().numpy()
+    ix = torch.empty(A0.indices.shape[0], dtype=torch.int32).pin_memory().numpy()
+    va = torch.empty(A0.indices.shape[0], dtype=torch.float64).pin_memory().numpy()
+    for _ in range(2):
+        A, _, _ = create_interpolation_matrix(V, K, op, host_out=(ip, ix, va))
+        np.testing.assert_array_equal(A.indptr, A0.indptr)
+        np.testing.assert_array_equal(A.indices, A0.indices)
+        assert A.data.tobytes() == A0.data.tobytes()
