@@ -1605,9 +1605,39 @@ static int fused_blocks_per_sm(K kernel, int B, size_t smem) {
 // compaction), one 56-byte result copy, one host synchronisation.  Without an nnz hint (first build on
 // a handle) the kernel only counts and the compaction runs as a second launch into exact-size arrays.
 // Returns false when K is not cell-local (the caller falls back to the COO path).
+// FXII_HOSTPROF=1: host wall clock of the phases of a cooperative build, averaged and printed every 100 builds
+struct HostProf {
+  bool on;
+  double t[6] = {0, 0, 0, 0, 0, 0};
+  int n = 0;
+  double last = 0;
+  HostProf() {
+    const char* e = getenv("FXII_HOSTPROF");
+    on = e && e[0] == '1';
+  }
+  void start() {
+    if (on) last = Trace::now();
+  }
+  void lap(int i) {
+    if (!on) return;
+    const double now = Trace::now();
+    t[i] += now - last;
+    last = now;
+  }
+  void done() {
+    if (!on || ++n < 100) return;
+    fprintf(stderr, "[fxii hostprof] per build, us: prep %.1f | memset+event %.1f | coop launch %.1f | event+copies %.1f | sync %.1f | post %.1f\n",
+            10 * t[0], 10 * t[1], 10 * t[2], 10 * t[3], 10 * t[4], 10 * t[5]);
+    for (auto& v : t) v = 0;
+    n = 0;
+  }
+};
+static HostProf g_hostprof;
+
 static bool pi_assemble_coop(const fxii_space* sp, fxii_rows* rows, const FusedPlan& p, cudaStream_t s, fxii_csr* out,
                              PiCounters* h_counters, float* ms_frames, float* ms_locate, float* ms_csr, bool* launched) {
   *launched = false;
+  g_hostprof.start();
   const fxii_mesh* m = sp->mesh;
   const int64_t n_rows = rows->n_rows_total;
   FusedResult* hr = static_cast<FusedResult*>(rows->host_result);
@@ -1641,7 +1671,9 @@ static bool pi_assemble_coop(const fxii_space* sp, fxii_rows* rows, const FusedP
   ca.indices = hint > 0 ? out->indices.p : nullptr;
   ca.values = hint > 0 ? out->values.p : nullptr;
   ca.capacity = hint > 0 ? hint : 0;
-  ca.result = reinterpret_cast<FusedResult*>(ws + p.off_result);
+  // the result record is written straight into the handle's pinned host slot (unified addressing): no copy node
+  memset(hr, 0, sizeof(FusedResult));
+  ca.result = hr;
   // kernel arguments (by address, cudaLaunchCooperativeKernel)
   const WideNode* a_nodes = m->wnodes.p;
   SceneGrid a_grid = m->grid;
@@ -1672,8 +1704,10 @@ static bool pi_assemble_coop(const fxii_space* sp, fxii_rows* rows, const FusedP
   void* args[] = {&a_nodes, &a_grid, &a_cellgeo, &a_x, &a_cn, &a_pad, &a_dofmap, &a_frames, &a_table, &a_wq, &a_pts, &a_win,
                   &a_sin, &a_kind, &a_nq, &a_packet, &a_team, &a_scap, &a_npr, &a_nrows, &a_rowdofs, &a_cell, &a_ncoll,
                   &a_points, &a_scol, &a_sval, &a_rowcnt, &a_src, &a_conf, &a_counters, &ca};
+  g_hostprof.lap(0);
   FXII_CUDA(cudaMemsetAsync(ws, 0, p.ws_bytes, s));
   FXII_CUDA(cudaEventRecord(ev[1], s));
+  g_hostprof.lap(1);
   const void* fn = sp->nd == 4 ? (const void*)pi_fused_kernel<4, 2> : (const void*)pi_fused_kernel<10, 2>;
   const cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(p.B), args, p.smem, s);
   if (le != cudaSuccess) {  // e.g. a shared device that cannot hold the wave: use the multi-kernel path
@@ -1682,8 +1716,8 @@ static bool pi_assemble_coop(const fxii_space* sp, fxii_rows* rows, const FusedP
   }
   *launched = true;
   FXII_LAUNCHED(1);
+  g_hostprof.lap(2);
   FXII_CUDA(cudaEventRecord(ev[2], s));
-  FXII_CUDA(cudaMemcpyAsync(hr, ca.result, sizeof(FusedResult), cudaMemcpyDeviceToHost, s));
   // host destination: the download is speculated on the hint and rides behind the kernel, before the one sync
   int64_t speculated = -1;
   if (rows->sink && hint > 0 && rows->sink->capacity >= hint) {
@@ -1693,7 +1727,9 @@ static bool pi_assemble_coop(const fxii_space* sp, fxii_rows* rows, const FusedP
     FXII_CUDA(cudaMemcpyAsync(k->values, out->values.p, sizeof(double) * (size_t)hint, cudaMemcpyDeviceToHost, s));
     speculated = hint;
   }
+  g_hostprof.lap(3);
   FXII_CUDA(cudaStreamSynchronize(s));
+  g_hostprof.lap(4);
   *h_counters = hr->counters;
   if (hr->conflict) return false;
   out->nnz = hr->nnz;
@@ -1717,6 +1753,8 @@ static bool pi_assemble_coop(const fxii_space* sp, fxii_rows* rows, const FusedP
   *ms_frames = 0.f;
   *ms_csr = ms_kernel * frac_csr + ms_extra;
   *ms_locate = ms_kernel - ms_kernel * frac_csr;
+  g_hostprof.lap(5);
+  g_hostprof.done();
   return true;
 }
 
