@@ -797,12 +797,20 @@ scale_rows_kernel(const int64_t* __restrict__ indptr, int64_t n_rows, const doub
   }
 }
 
-void csr_scale_rows(fxii_csr* a, const double* d_host, cudaStream_t s) {
+// `d_any`: host array (uploaded; the call synchronises) or device array (used in place, stream-ordered)
+void csr_scale_rows(fxii_csr* a, const double* d_any, cudaStream_t s) {
+  cudaPointerAttributes at{};
+  const bool on_device = cudaPointerGetAttributes(&at, d_any) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+  if (!on_device) cudaGetLastError();
   DevBuf<double> d;
-  d.upload(d_host, a->n_rows, s);
-  if (a->n_rows > 0) { scale_rows_kernel<<<grid_for(a->n_rows * 32, 256, 8), 256, 0, s>>>(a->indptr.p, a->n_rows, d.p, a->values.p); FXII_LAUNCHED(1); }
+  const double* dp = d_any;
+  if (!on_device) {
+    d.upload(d_any, a->n_rows, s);
+    dp = d.p;
+  }
+  if (a->n_rows > 0) { scale_rows_kernel<<<grid_for(a->n_rows * 32, 256, 8), 256, 0, s>>>(a->indptr.p, a->n_rows, dp, a->values.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
-  FXII_CUDA(cudaStreamSynchronize(s));
+  if (!on_device) FXII_CUDA(cudaStreamSynchronize(s));
 }
 
 // one warp per row; lanes stride the row, partial sums combined by a fixed shuffle tree

@@ -18,14 +18,18 @@ def shard_range(n: int, world: int, rank: int) -> tuple[int, int]:
     return begin, begin + base + (1 if rank < rem else 0)
 
 
-def allgatherv_csr(indptr, indices, values, group=None):
+def allgatherv_csr(indptr, indices, values, group=None, packed: "bool | None" = None):
     """All-gather row-sharded CSR arrays (torch tensors on the collective's device).
 
     Every rank passes its shard (indptr int64[m_r+1] starting at 0, indices int32[nnz_r],
     values float64[nnz_r]) and receives the row-concatenated matrix (indptr, indices, values).
-    NCCL has no all-gather-v: after one small all-gather of the shard sizes, every rank's shard
-    is broadcast straight into its slice of the preallocated result (no padding, no concatenation
-    copies)."""
+    NCCL has no all-gather-v.  After one small all-gather of the shard sizes:
+
+    * packed (default while the padded exchange stays below 32 MiB, i.e. latency bound): row counts, values and indices of
+      a shard travel as ONE byte record padded to the largest shard — a single all-gather — and are sliced
+      out of the received records.  24 small broadcasts cost 3.4 ms on 8 GPUs for 3 MB shards; this is one
+      collective.
+    * otherwise every shard is broadcast straight into its slice of the preallocated result (no padding)."""
     import torch
     import torch.distributed as dist
 
@@ -38,21 +42,43 @@ def allgatherv_csr(indptr, indices, values, group=None):
     all_sizes = all_sizes.view(world, 2).cpu().numpy()
     row_off = np.concatenate([[0], np.cumsum(all_sizes[:, 0])])
     nnz_off = np.concatenate([[0], np.cumsum(all_sizes[:, 1])])
-    counts = torch.empty(int(row_off[-1]), dtype=torch.int64, device=dev)
-    g_indices = torch.empty(int(nnz_off[-1]), dtype=torch.int32, device=dev)
-    g_values = torch.empty(int(nnz_off[-1]), dtype=torch.float64, device=dev)
-    counts[row_off[rank]:row_off[rank + 1]] = indptr[1:] - indptr[:-1]
-    g_indices[nnz_off[rank]:nnz_off[rank + 1]] = indices
-    g_values[nnz_off[rank]:nnz_off[rank + 1]] = values
-    ranks = dist.get_process_group_ranks(group) if group is not None else list(range(world))
-    work = []
-    for r in range(world):
-        src = ranks[r]
-        for buf, off in ((counts, row_off), (g_indices, nnz_off), (g_values, nnz_off)):
-            if off[r + 1] > off[r]:
-                work.append(dist.broadcast(buf[off[r]:off[r + 1]], src=src, group=group, async_op=True))
-    for w in work:
-        w.wait()
+    max_rows, max_nnz = int(all_sizes[:, 0].max()), int(all_sizes[:, 1].max())
+    if packed is None:  # small exchanges only (latency bound); large shards go straight into place, unpadded
+        packed = 12 * max_nnz * world <= (32 << 20)
+    if packed:
+        def pad16(n):
+            return (n + 15) // 16 * 16
+
+        o_val = pad16(8 * max_rows)
+        o_idx = o_val + pad16(8 * max_nnz)
+        rec = o_idx + pad16(4 * max_nnz)
+        send = torch.zeros(rec, dtype=torch.uint8, device=dev)
+        m, n = int(all_sizes[rank, 0]), int(all_sizes[rank, 1])
+        send[: 8 * m].view(torch.int64).copy_(indptr[1:] - indptr[:-1])
+        send[o_val:o_val + 8 * n].view(torch.float64).copy_(values)
+        send[o_idx:o_idx + 4 * n].view(torch.int32).copy_(indices)
+        recv = torch.empty(world * rec, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        recv = recv.view(world, rec)
+        counts = torch.cat([recv[r, : 8 * int(all_sizes[r, 0])].view(torch.int64) for r in range(world)])
+        g_values = torch.cat([recv[r, o_val:o_val + 8 * int(all_sizes[r, 1])].view(torch.float64) for r in range(world)])
+        g_indices = torch.cat([recv[r, o_idx:o_idx + 4 * int(all_sizes[r, 1])].view(torch.int32) for r in range(world)])
+    else:
+        counts = torch.empty(int(row_off[-1]), dtype=torch.int64, device=dev)
+        g_indices = torch.empty(int(nnz_off[-1]), dtype=torch.int32, device=dev)
+        g_values = torch.empty(int(nnz_off[-1]), dtype=torch.float64, device=dev)
+        counts[row_off[rank]:row_off[rank + 1]] = indptr[1:] - indptr[:-1]
+        g_indices[nnz_off[rank]:nnz_off[rank + 1]] = indices
+        g_values[nnz_off[rank]:nnz_off[rank + 1]] = values
+        ranks = dist.get_process_group_ranks(group) if group is not None else list(range(world))
+        work = []
+        for r in range(world):
+            src = ranks[r]
+            for buf, off in ((counts, row_off), (g_indices, nnz_off), (g_values, nnz_off)):
+                if off[r + 1] > off[r]:
+                    work.append(dist.broadcast(buf[off[r]:off[r + 1]], src=src, group=group, async_op=True))
+        for w in work:
+            w.wait()
     g_indptr = torch.zeros(counts.numel() + 1, dtype=torch.int64, device=dev)
     torch.cumsum(counts, 0, out=g_indptr[1:])
     return g_indptr, g_indices, g_values
@@ -87,7 +113,7 @@ def balanced_dof_windows(indices_t, n_cols: int, world: int):
 
     if world == 1:
         return [(0, n_cols)]
-    counts = torch.bincount(indices_t.to(torch.int64), minlength=n_cols)
+    counts = torch.bincount(indices_t, minlength=n_cols)  # int32 input: no 64-bit copy of the gathered indices
     cum = torch.cumsum(counts, 0)
     total = int(cum[-1].item())
     targets = torch.tensor([total * (r + 1) // world for r in range(world - 1)], device=cum.device, dtype=cum.dtype)
@@ -124,6 +150,7 @@ def product_pt_m_p(pi_local, gamma, K, world: int, rank: int, steps: int = 5, fl
     from .sparse import DeviceCSR
 
     diag = quadrature_mass_diagonal(gamma, K)
+    diag_dev = torch.from_numpy(diag).to("cuda") if world > 1 else None
     n_dofs = pi_local.shape[1]
 
     def once():
@@ -137,7 +164,7 @@ def product_pt_m_p(pi_local, gamma, K, world: int, rank: int, steps: int = 5, fl
             # the one exchange of the path: Π's row shards (and the mass diagonal) to every rank
             g_ptr, g_idx, g_val = allgatherv_csr(*pi_local.device_tensors())
             gp = DeviceCSR.from_device_arrays(g_ptr, g_idx, g_val, (pi_local.shape[0] * world, n_dofs))
-            gdiag = allgatherv_vector(_t.from_numpy(diag).to("cuda")).cpu().numpy()
+            gdiag = allgatherv_vector(diag_dev)  # stays on the device: scale_rows takes it in place
             r0, r1 = balanced_dof_windows(g_idx, n_dofs, world)[rank]
             del g_ptr, g_idx, g_val
         else:

@@ -126,6 +126,13 @@ class DeviceCSR:
         return DeviceCSR(out.value)
 
     def scale_rows(self, d) -> "DeviceCSR":
+        """diag(d)·A in place; `d`: numpy array, or a float64 torch CUDA tensor (used in place, no host round trip)."""
+        if hasattr(d, "data_ptr") and getattr(d, "is_cuda", False):
+            import torch
+
+            assert d.dtype == torch.float64 and d.is_contiguous() and d.numel() == self.shape[0]
+            _lib.check(_lib.load().fxii_csr_scale_rows(self._h, C.c_void_p(d.data_ptr()), _lib.current_stream()))
+            return self
         d = np.ascontiguousarray(d, dtype=np.float64)
         assert d.shape == (self.shape[0],)
         _lib.check(_lib.load().fxii_csr_scale_rows(self._h, _lib.ptr(d), _lib.current_stream()))

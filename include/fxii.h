@@ -191,7 +191,8 @@ int fxii_spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t
 /* blocked spaces (K.bs == V.bs == bs): every scalar entry becomes a bs x bs block with the value on its
  * diagonal and explicit zeros elsewhere (interpolation.py:214-248 + utils.unroll_dofmap, utils.py:36-47) */
 int fxii_csr_expand_blocks(const fxii_csr* a, int32_t bs, void* stream, fxii_csr** out);
-/* rows scaled by a diagonal: (diag(d)·A); d host [n_rows] — M_Γ·Π for a quadrature-element mass */
+/* rows scaled by a diagonal: (diag(d)·A); d [n_rows], host memory (uploaded, synchronises) or device memory (used in
+ * place, stream-ordered) — M_Γ·Π for a quadrature-element mass */
 int fxii_csr_scale_rows(fxii_csr* a, const double* d, void* stream);
 /* y = A·u (assembly.py:67); u host [n_cols], y host [n_rows] */
 int fxii_csr_spmv(const fxii_csr* a, const double* u, double* y, void* stream);

@@ -20,21 +20,22 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, shards, out_dir):
+def _worker(rank, world, port, shards, out_dir, packed):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         m = shards[rank]
         ip, ij, iv = allgatherv_csr(torch.from_numpy(m.indptr.astype(np.int64)), torch.from_numpy(m.indices.astype(np.int32)),
-                                    torch.from_numpy(m.data.astype(np.float64)))
+                                    torch.from_numpy(m.data.astype(np.float64)), packed=packed)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), indptr=ip.numpy(), indices=ij.numpy(), data=iv.numpy())
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("packed", [None, True, False])  # automatic choice, one padded all-gather, per-shard broadcasts
 @pytest.mark.parametrize("rows", [(7, 12), (5, 0), (1, 1)])
-def test_allgatherv_csr_gloo(tmp_path, rows):
+def test_allgatherv_csr_gloo(tmp_path, rows, packed):
     world = 2
     rng = np.random.default_rng(5)
     shards = []
@@ -43,7 +44,7 @@ def test_allgatherv_csr_gloo(tmp_path, rows):
         M.sort_indices()
         shards.append(M)
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, shards, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, shards, str(tmp_path), packed), nprocs=world, join=True)
     full = sp.vstack(shards).tocsr()
     full.sort_indices()
     for r in range(world):
