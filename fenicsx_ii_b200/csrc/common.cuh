@@ -228,6 +228,7 @@ struct fxii_rows {
   int graph_kernels = 0;
   bool buffers_moved = false, last_graph = false, last_coop = false;
   fxii::HostSink* sink = nullptr;  // set for the duration of fxii_pi_assemble_host
+  bool not_cell_local = false;     // a fused build found a K dof produced by two point rows
   ~fxii_rows() {
     for (auto& e : ev)
       if (e) fxii::event_release(e);

@@ -1929,7 +1929,11 @@ void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr
   FXII_CHECK(tab_smem <= 48 * 1024, "operator table too large for shared memory (nq > 1536)");
   float ms_count = 0.f, ms_fill = 0.f, ms_fr_f = 0.f, ms_loc_f = 0.f, ms_csr_f = 0.f;
   bool fused = false;
-  if (rows->mode != 1) fused = pi_assemble_fused(sp, rows, s, out, &h, &ms_fr_f, &ms_loc_f, &ms_csr_f);
+  // a handle whose rows were found not to be cell-local (continuous K) goes straight to the COO path from then on
+  if (rows->mode != 1 && !rows->not_cell_local) {
+    fused = pi_assemble_fused(sp, rows, s, out, &h, &ms_fr_f, &ms_loc_f, &ms_csr_f);
+    if (!fused && rows->host_result && static_cast<FusedResult*>(rows->host_result)->conflict == 1) rows->not_cell_local = true;
+  }
   rows->last_fused = fused;
   if (!fused) {
     if (!ev[0]) {

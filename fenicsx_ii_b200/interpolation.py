@@ -435,7 +435,12 @@ def create_interpolation_matrix(V, K, red_op, tol: float = 1.0e-8, use_petsc: bo
         A = MatrixCSR(None, stats=stats, rows=rows, host=(indptr_h[: n_rows + 1], indices_h[:nnz], values_h[:nnz]),
                       shape=(n_rows, dspace.n_dofs))
         return A, imap_K, imap_V
+    general = K.__dict__.get("_fxii_general_path", False) if hasattr(K, "__dict__") else False
+    if general and not materialize_coo:
+        rows.set_mode(1)  # this K was seen to share dofs between point rows: skip the fused attempt
     csr, stats = rows.assemble(dspace)
+    if not general and not materialize_coo and stats["fused"] == 0 and hasattr(K, "__dict__"):
+        K.__dict__["_fxii_general_path"] = True
     hints[hkey] = csr.nnz
     if bs > 1:
         csr = csr.expand_blocks(bs)  # device kernel: bs x bs blocks, explicit zeros off the diagonal

@@ -378,3 +378,33 @@ def test_host_delivery_of_a_generic_operator(cuda):
         np.testing.assert_array_equal(A.indptr, A0.indptr)
         np.testing.assert_array_equal(A.indices, A0.indices)
         assert A.data.tobytes() == A0.data.tobytes()
+
+
+def test_continuous_k_remembers_the_general_path(cuda):
+    """Continuous K (dofs shared between point rows): the first build tries the fused kernel, finds the conflict and
+    reruns the COO path; later builds on the handle — and later calls with the same K — go there directly."""
+    from fenicsx_ii_b200 import create_interpolation_matrix
+    from fenicsx_ii_b200.interpolation import device_rows, device_space
+
+    mesh, V = small_cfg(6, 6, 6, degree=1)
+    gamma = sy.polyline_network(80, 1 / 6, n_lines=2, lo=0.3, hi=0.7)
+    K = functionspace(gamma, ("Lagrange", 1))
+    op = make_operator("circle", gamma, 0.05, 7)
+    ds = device_space(V)
+    rows = device_rows(K, op)
+    out = []
+    for _ in range(3):
+        csr, st = rows.assemble(ds)
+        assert st["fused"] == 0
+        out.append(csr.to_host())
+    for r in out[1:]:
+        np.testing.assert_array_equal(r[0], out[0][0])
+        np.testing.assert_array_equal(r[1], out[0][1])
+        assert r[2].tobytes() == out[0][2].tobytes()
+    A1, _, _ = create_interpolation_matrix(V, K, op)
+    assert K.__dict__.get("_fxii_general_path") is True
+    A2, _, _ = create_interpolation_matrix(V, K, op)
+    np.testing.assert_array_equal(A1.indices, A2.indices)
+    assert A1.data.tobytes() == A2.data.tobytes() == out[0][2].tobytes()
+    ref = oracle_pi(V, K, gamma, "circle", 0.05, 7)
+    assert_csr_parity((A2.indptr, A2.indices, A2.data), ref)
