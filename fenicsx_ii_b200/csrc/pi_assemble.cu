@@ -953,6 +953,7 @@ struct CoopArgs {
   int nip, radius_per_row;
   unsigned int* barrier;  // arrival counter, zeroed with the workspace
   unsigned long long* ticket;  // next unit of point rows, zeroed with the workspace
+  int ticket_batch;            // units handed out per atomic
   int64_t* cta_sum;       // [gridDim.x] entries per slice of matrix rows, zeroed with the workspace
   int64_t* indptr;
   int32_t* indices;
@@ -995,15 +996,23 @@ __device__ __forceinline__ int64_t block_sum_i64(int64_t v, int64_t* s_red) {
   return t;
 }
 
-// frame + point in one out-of-line call: its ~30 live doubles stay out of the traversal's register budget
-__device__ __noinline__ void make_point_with_frame(const CoopArgs& ca, int kind, const double* s_tab,
-                                                   const double* __restrict__ pts_in, const double* __restrict__ w_in,
-                                                   const double* __restrict__ s_in, int64_t r, int l, int64_t pidx, double* p,
-                                                   double& W, double& S) {
+// frame + point in one out-of-line call: its ~30 live doubles stay out of the traversal's register budget.
+// Everything goes in and out BY VALUE: a pointer or reference argument would pin the caller's point (and a copy of
+// the kernel's argument record) in local memory for the whole walk.
+struct PointWS {
+  double p0, p1, p2, W, S;
+};
+__device__ __noinline__ PointWS make_point_with_frame(const double* __restrict__ gx, const int32_t* __restrict__ gcells,
+                                                      const int32_t* __restrict__ cells_k, const double* __restrict__ xref,
+                                                      int nip, const double* __restrict__ radius, int radius_per_row, int kind,
+                                                      const double* s_tab, const double* __restrict__ pts_in,
+                                                      const double* __restrict__ w_in, const double* __restrict__ s_in,
+                                                      int64_t r, int l, int64_t pidx) {
   double fr[kFrame];
-  if (kind != FXII_OP_POINTS)
-    compute_frame(ca.gx, ca.gcells, ca.cells_k, ca.xref, ca.nip, ca.radius, ca.radius_per_row, kind, r, fr);
+  if (kind != FXII_OP_POINTS) compute_frame(gx, gcells, cells_k, xref, nip, radius, radius_per_row, kind, r, fr);
+  double p[3], W, S;
   make_point(kind, fr, s_tab, pts_in, w_in, s_in, r, l, pidx, p, W, S);
+  return PointWS{p[0], p[1], p[2], W, S};
 }
 
 // Bitonic sort of the 4*team keys of a sub-warp team held four per lane (element e = 4*l + r): the
@@ -1110,18 +1119,26 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
   // every slice is accumulated here, as rows finish, so that phase needs no second grid barrier
   const int64_t slice_rows = COOP ? max((int64_t)1, (n_rows_total + gridDim.x - 1) / gridDim.x) : 1;
   int64_t rb = blockIdx.x;
+  long long tk_next = 0, tk_end = 0;  // COOP: the batch of tickets this warp / team currently owns
   while (true) {
     int64_t r;
     if (COOP) {
-      long long tk = 0;
-      if (team <= 32) {
-        if ((tid & 31) == 0) tk = (long long)atomicAdd(ca.ticket, 1ULL);
-        tk = __shfl_sync(0xffffffffu, tk, 0);
-      } else {
-        if (l == 0) s_ticket[team_id & 7] = (long long)atomicAdd(ca.ticket, 1ULL);
-        team_sync(team, team_id);
-        tk = s_ticket[team_id & 7];
+      // one atomic buys `ticket_batch` consecutive units: a single counter serialises at a few ns per atomic, which
+      // one-point rows (a unit is ~10 us of work) would otherwise be bound by
+      if (tk_next == tk_end) {
+        long long tk = 0;
+        if (team <= 32) {
+          if ((tid & 31) == 0) tk = (long long)atomicAdd(ca.ticket, (unsigned long long)ca.ticket_batch);
+          tk = __shfl_sync(0xffffffffu, tk, 0);
+        } else {
+          if (l == 0) s_ticket[team_id & 7] = (long long)atomicAdd(ca.ticket, (unsigned long long)ca.ticket_batch);
+          team_sync(team, team_id);
+          tk = s_ticket[team_id & 7];
+        }
+        tk_next = tk;
+        tk_end = tk + ca.ticket_batch;
       }
+      const long long tk = tk_next++;
       if (tk * unit_rows >= n_point_rows) break;
       r = tk * unit_rows + team_in_unit;
     } else {
@@ -1140,7 +1157,9 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
       double p[3] = {0.0, 0.0, 0.0}, W = 1.0, S = 1.0;
       if (active) {
         if (FRAMES) {
-          make_point_with_frame(ca, kind, s_tab, pts_in, w_in, s_in, r, l, pidx, p, W, S);
+          const PointWS pw = make_point_with_frame(ca.gx, ca.gcells, ca.cells_k, ca.xref, ca.nip, ca.radius, ca.radius_per_row,
+                                                   kind, s_tab, pts_in, w_in, s_in, r, l, pidx);
+          p[0] = pw.p0, p[1] = pw.p1, p[2] = pw.p2, W = pw.W, S = pw.S;
         } else {
           make_point(kind, frames + kFrame * r, s_tab, pts_in, w_in, s_in, r, l, pidx, p, W, S);
         }
@@ -1666,6 +1685,14 @@ static bool pi_assemble_coop(const fxii_space* sp, fxii_rows* rows, const FusedP
   ca.radius_per_row = rows->radius_per_row;
   ca.barrier = reinterpret_cast<unsigned int*>(ws + p.off_barrier);
   ca.ticket = reinterpret_cast<unsigned long long*>(ws + p.off_barrier + 8);
+  {
+    // units (warps of sub-warp teams, or multi-warp teams) and how many of them the grid runs at a time
+    const int64_t units = p.team >= 32 ? rows->n_point_rows : (rows->n_point_rows + 32 / p.team - 1) / (32 / p.team);
+    const int64_t slots = (int64_t)grid * (p.team >= 32 ? p.rpb : p.B / 32);
+    // only one-point rows are cheap enough for the counter to matter (1.2 M trace rows: 0.48 -> 0.35 ms); for
+    // averaging operators coarser tickets just lengthen the tail (measured: 0.84 -> 1.07 ms with batches of 16)
+    ca.ticket_batch = p.team == 1 ? (int)std::max<int64_t>(1, std::min<int64_t>(8, units / (2 * std::max<int64_t>(slots, 1)))) : 1;
+  }
   ca.cta_sum = reinterpret_cast<int64_t*>(ws + p.off_cta);
   ca.indptr = out->indptr.p;
   ca.indices = hint > 0 ? out->indices.p : nullptr;
@@ -1797,7 +1824,8 @@ static bool pi_assemble_fused(const fxii_space* sp, fxii_rows* rows, cudaStream_
   out->n_cols = sp->n_dofs;
   const int64_t hint = rows->nnz_hint;
   rows->last_coop = false;
-  if (coop_enabled(E) && rows->mode != 2) {
+  // one-point rows (PointwiseTrace, mapped points) stay launch/latency bound four times longer
+  if (coop_enabled(p.team == 1 ? E / 4 : E) && rows->mode != 2) {
     bool launched = false;
     rows->last_graph = false;
     const bool ok = pi_assemble_coop(sp, rows, p, s, out, h_counters, ms_frames, ms_locate, ms_csr, &launched);
