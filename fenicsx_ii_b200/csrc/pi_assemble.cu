@@ -1226,12 +1226,31 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
     team_sync(team, team_id);
     // ---- B: first point of every distinct cell sums that cell's points in l order ----------------
     bool leader = cell >= 0;
-    for (int j = 0; j < l && leader; ++j) leader = s_cell[t0 + j] != cell;
-    if (leader) {
-      for (int j = l + 1; j < nq; ++j) {
-        if (s_cell[t0 + j] == cell) {
+    if (team <= 32) {
+      // sub-warp teams: one MATCH gives the lanes of the team that found the same cell; the lowest is the leader and
+      // adds the others in ascending lane (= l) order — the same sums as the scan below, without its O(nq) loops
+      const int lane = tid & 31;
+      const unsigned tmask = (team == 32 ? 0xffffffffu : ((1u << team) - 1u)) << (lane & ~(team - 1));
+      const unsigned same = __match_any_sync(0xffffffffu, cell) & tmask;
+      leader = leader && (lane == __ffs(same) - 1);
+      if (leader) {
+        unsigned rest = same & ~(1u << lane);
+        const int w0 = tid - lane;  // first thread of this warp
+        while (rest) {
+          const int j = __ffs(rest) - 1;
+          rest &= rest - 1;
 #pragma unroll
-          for (int d = 0; d < ND; ++d) vals[d] += s_val[(size_t)d * B + t0 + j];
+          for (int d = 0; d < ND; ++d) vals[d] += s_val[(size_t)d * B + w0 + j];
+        }
+      }
+    } else {
+      for (int j = 0; j < l && leader; ++j) leader = s_cell[t0 + j] != cell;
+      if (leader) {
+        for (int j = l + 1; j < nq; ++j) {
+          if (s_cell[t0 + j] == cell) {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) vals[d] += s_val[(size_t)d * B + t0 + j];
+          }
         }
       }
     }

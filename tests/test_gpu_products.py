@@ -178,3 +178,22 @@ def test_transpose_window_and_sharded_product(cuda):
         np.testing.assert_array_equal(np.concatenate(ind), C_full[0])
         np.testing.assert_array_equal(np.concatenate(idx), C_full[1])
         assert np.concatenate(val).tobytes() == C_full[2].tobytes()
+
+
+def test_scale_rows_with_device_diagonal(cuda):
+    """fxii_csr_scale_rows takes the diagonal from host memory or, stream-ordered and without a copy, from device memory."""
+    import scipy.sparse as sp
+    import torch
+
+    from fenicsx_ii_b200.sparse import DeviceCSR
+
+    rng = np.random.default_rng(3)
+    M = sp.random(500, 300, density=0.02, random_state=7, format="csr")
+    M.sort_indices()
+    d = rng.uniform(-2, 2, size=500)
+    a = DeviceCSR.from_scipy(M).scale_rows(d).to_host()
+    b = DeviceCSR.from_scipy(M).scale_rows(torch.from_numpy(d).to("cuda")).to_host()
+    ref = M.data * np.repeat(d, np.diff(M.indptr))  # row-wise product in M's (sorted) entry order
+    np.testing.assert_array_equal(a[1], b[1])
+    assert a[2].tobytes() == b[2].tobytes()
+    np.testing.assert_array_equal(a[2], ref)
