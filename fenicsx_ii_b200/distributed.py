@@ -150,7 +150,7 @@ def product_pt_m_p(pi_local, gamma, K, world: int, rank: int, steps: int = 5, fl
     from .sparse import DeviceCSR
 
     diag = quadrature_mass_diagonal(gamma, K)
-    diag_dev = torch.from_numpy(diag).to("cuda") if world > 1 else None
+    diag_dev = torch.from_numpy(diag).to("cuda")  # resident like every other input of the timed product
     n_dofs = pi_local.shape[1]
 
     def once():
@@ -168,7 +168,7 @@ def product_pt_m_p(pi_local, gamma, K, world: int, rank: int, steps: int = 5, fl
             r0, r1 = balanced_dof_windows(g_idx, n_dofs, world)[rank]
             del g_ptr, g_idx, g_val
         else:
-            gp, gdiag = pi_local, diag
+            gp, gdiag = pi_local, diag_dev
             r0, r1 = 0, n_dofs
         e[1].record()
         gmp = gp.copy().scale_rows(gdiag)  # M_Γ Π (diagonal quadrature mass)
