@@ -65,3 +65,40 @@ def test_functionspace_standins():
     assert functionspace(gamma, ("Lagrange", 2)).num_dofs == 5 + 4
     with pytest.raises(NotImplementedError):
         functionspace(mesh, ("Lagrange", 3))
+
+
+def test_gamma_description_skips_identity_arrays():
+    """`device_rows(..., args_only=True)` + `DeviceRows._gamma_desc`: all cells of Γ in order and the cell-local
+    numbering of Quadrature / DG spaces are passed as NULL (generated on the device), subsets and continuous
+    spaces as arrays; the record matches fxii_rows_desc field by field (no GPU needed)."""
+    from fenicsx_ii_b200 import _lib
+    from fenicsx_ii_b200.interpolation import DeviceRows, device_rows
+
+    gamma = sy.polyline_network(12, 0.1, n_lines=2, lo=0.3, hi=0.7)
+    op = fx.Circle(gamma, 0.05, degree=7)
+    Kq = functionspace(gamma, ("Quadrature", 4))
+    args = device_rows(Kq, op, args_only=True)
+    assert args[2] is None and args[4] is None  # cells_k, row_dofs: identity
+    d, keep, n_point_rows, nq = DeviceRows._gamma_desc(*args)
+    nip = Kq.element.interpolation_points.shape[0]
+    assert (d.cells_k, d.row_dofs) == (None, None) and d.n_cells_k == 12 and d.nip == nip
+    assert n_point_rows == 12 * nip and nq == op.num_points == d.nq and d.n_rows_total == Kq.num_dofs
+    assert d.kind == _lib.OP_CIRCLE and d.radius_per_row == 0 and d.gx == keep[0].ctypes.data
+
+    # the same cells given explicitly are recognised as "all cells"
+    args = device_rows(Kq, op, np.arange(12, dtype=np.int32), args_only=True)
+    assert args[2] is None and args[4] is None
+    # a subset keeps both arrays
+    sub = np.array([1, 4, 5, 9], dtype=np.int32)
+    args = device_rows(Kq, op, sub, args_only=True)
+    np.testing.assert_array_equal(args[2], sub)
+    np.testing.assert_array_equal(args[4], Kq.dofmap.list[sub].reshape(-1))
+    d, keep, n_point_rows, _ = DeviceRows._gamma_desc(*args)
+    assert d.n_cells_k == 4 and n_point_rows == 4 * nip and d.cells_k == keep[2].ctypes.data
+    # continuous K: all cells, but shared dofs -> explicit row numbering
+    Kp = functionspace(gamma, ("Lagrange", 1))
+    args = device_rows(Kp, fx.PointwiseTrace(gamma), args_only=True)
+    assert args[2] is None
+    np.testing.assert_array_equal(args[4], Kp.dofmap.list.reshape(-1))
+    # generic operators have no device description
+    assert device_rows(Kq, fx.MappedRestriction(gamma, lambda x: x), args_only=True) is None
