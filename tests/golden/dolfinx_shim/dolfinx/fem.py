@@ -28,15 +28,25 @@ class Expression:
         if isinstance(self.e, ufl.TestFunction):  # interpolation_utils.py:63-74 -> [cells, points, dofs]
             V = self.e.V
             phi = orc.tabulate(V.element.degree, self.X)
-            return np.broadcast_to(phi[None, :, :], (len(cells),) + phi.shape).copy()
+            bs = V.dofmap.bs
+            if bs == 1:
+                return np.broadcast_to(phi[None, :, :], (len(cells),) + phi.shape).copy()
+            # blocked space: [cells, points, component, unrolled dof d*bs+c] with phi_d on the matching component
+            # (the layout interpolation_utils.py:66-69 takes its diagonal of)
+            nd = phi.shape[1]
+            vals = np.zeros((len(cells), phi.shape[0], bs, nd * bs))
+            for c in range(bs):
+                vals[:, :, c, c::bs] = phi[None, :, :]
+            return vals
         raise NotImplementedError(type(self.e))
 
 
 class FunctionSpace:
-    def __init__(self, mesh, degree, dof_list, n_dofs, interpolation_points=None, family="Lagrange"):
+    def __init__(self, mesh, degree, dof_list, n_dofs, interpolation_points=None, family="Lagrange", bs=1):
+        """`n_dofs`: number of BLOCK dofs (the index map counts blocks, as in dolfinx)."""
         self.mesh = mesh
         imap = IndexMap(MPI.COMM_WORLD, n_dofs)
-        self.dofmap = SimpleNamespace(list=np.asarray(dof_list, dtype=np.int32), bs=1, index_map=imap, index_map_bs=1,
+        self.dofmap = SimpleNamespace(list=np.asarray(dof_list, dtype=np.int32), bs=bs, index_map=imap, index_map_bs=bs,
                                       dof_layout=SimpleNamespace(num_dofs=np.asarray(dof_list).shape[1]))
         self.element = SimpleNamespace(
             degree=degree, interpolation_points=interpolation_points, interpolation_ident=True,

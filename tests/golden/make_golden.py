@@ -93,9 +93,11 @@ def quadrature_fixture():
 def shim_spaces(mesh, V, gamma, K):
     m3 = dolfinx.mesh.Mesh(mesh.geometry.x, mesh.geometry.dofmap, 3)
     m1 = dolfinx.mesh.Mesh(gamma.geometry.x, gamma.geometry.dofmap, 1)
-    Vs = dolfinx.fem.FunctionSpace(m3, V.element.degree, V.dofmap.list, V.num_dofs)
-    Ks = dolfinx.fem.FunctionSpace(m1, K.element.degree, K.dofmap.list, K.num_dofs,
-                                   interpolation_points=K.element.interpolation_points, family=K.element.family)
+    bs = int(V.dofmap.bs)
+    assert bs == int(K.dofmap.bs)
+    Vs = dolfinx.fem.FunctionSpace(m3, V.element.degree, V.dofmap.list, V.dofmap.index_map.size_local, bs=bs)
+    Ks = dolfinx.fem.FunctionSpace(m1, K.element.degree, K.dofmap.list, K.dofmap.index_map.size_local,
+                                   interpolation_points=K.element.interpolation_points, family=K.element.family, bs=bs)
     return m3, m1, Vs, Ks
 
 
@@ -111,6 +113,10 @@ CASES = {
                                        op=("circle", "callable", 9)),
     "disk_p2v_subset": dict(n=(4, 4, 4), p=2, gamma=("network", 30, 1 / 4, 2), K=("DG", 2), op=("disk", 0.05, 3),
                             cells_K=np.arange(3, 27, 2, dtype=np.int32)),
+    # blocked (vector) spaces, tests/test_interpolation_matrix.py:254-301: bs x bs blocks with explicit zeros
+    "trace_blocked3_dg2": dict(n=(4, 4, 4), p=1, bs=3, gamma=("network", 24, 1 / 4, 2), K=("DG", 2), op=("trace",)),
+    "circle_blocked2_p1k_firstvisit": dict(n=(4, 4, 4), p=1, bs=2, gamma=("network", 24, 1 / 4, 2), K=("Lagrange", 1),
+                                           op=("circle", 0.05, 5)),
 }
 
 
@@ -120,13 +126,17 @@ def callable_radius(x):
 
 def build_case(spec):
     mesh = sy.kuhn_box(*spec["n"])
-    V = functionspace(mesh, ("Lagrange", 1)) if spec["p"] == 1 else sy.kuhn_p2_space(mesh)
+    bs = spec.get("bs", 1)
+    if bs > 1:
+        V = functionspace(mesh, ("Lagrange", spec["p"], (bs,)))
+    else:
+        V = functionspace(mesh, ("Lagrange", 1)) if spec["p"] == 1 else sy.kuhn_p2_space(mesh)
     g = spec["gamma"]
     if g[0] == "line":
         gamma = sy.straight_line(g[1])
     else:
         gamma = sy.polyline_network(g[1], g[2], n_lines=g[3], lo=0.3, hi=0.7)
-    K = functionspace(gamma, spec["K"])
+    K = functionspace(gamma, spec["K"] + ((bs,),) if bs > 1 else spec["K"])
     return mesh, V, gamma, K
 
 

@@ -22,6 +22,10 @@ CASES = {
     "circle_p2v_callable_radius": dict(n=(4, 4, 4), p=2, gamma=("network", 30, 1 / 4, 2), K=("Quadrature", 4),
                                        op=("circle", "callable", 9)),
     "disk_p2v_subset": dict(n=(4, 4, 4), p=2, gamma=("network", 30, 1 / 4, 2), K=("DG", 2), op=("disk", 0.05, 3)),
+    # blocked (vector) spaces: the fixture is the scalar CSR of the bs x bs blocked matrix the reference fills
+    "trace_blocked3_dg2": dict(n=(4, 4, 4), p=1, bs=3, gamma=("network", 24, 1 / 4, 2), K=("DG", 2), op=("trace",)),
+    "circle_blocked2_p1k_firstvisit": dict(n=(4, 4, 4), p=1, bs=2, gamma=("network", 24, 1 / 4, 2), K=("Lagrange", 1),
+                                           op=("circle", 0.05, 5)),
 }
 
 
@@ -35,11 +39,15 @@ def load_case(name):
     spec = CASES[name]
     fx = np.load(os.path.join(GOLDEN_DIR, f"pi_{name}.npz"))
     mesh = sy.kuhn_box(*spec["n"])
-    V = functionspace(mesh, ("Lagrange", 1)) if spec["p"] == 1 else sy.kuhn_p2_space(mesh)
+    bs = spec.get("bs", 1)
+    if bs > 1:
+        V = functionspace(mesh, ("Lagrange", spec["p"], (bs,)))
+    else:
+        V = functionspace(mesh, ("Lagrange", 1)) if spec["p"] == 1 else sy.kuhn_p2_space(mesh)
     from fenicsx_ii_b200.mesh import Mesh
 
     gamma = Mesh(fx["gamma_x"], fx["gamma_cells"], tdim=1, name="gamma")
-    K = functionspace(gamma, spec["K"])
+    K = functionspace(gamma, spec["K"] + ((bs,),) if bs > 1 else spec["K"])
     op = spec["op"]
     radius = degree = None
     if op[0] != "trace":

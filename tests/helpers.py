@@ -56,3 +56,25 @@ def small_cfg(nx=8, ny=8, nz=16, degree=1):
     mesh = sy.kuhn_box(nx, ny, nz)
     V = functionspace(mesh, ("Lagrange", 1)) if degree == 1 else sy.kuhn_p2_space(mesh)
     return mesh, V
+
+
+def expand_blocks_csr(indptr, indices, data, bs: int):
+    """Scalar CSR of the blocked matrix the reference fills for bs > 1 (interpolation.py:214-248 with
+    utils.unroll_dofmap): entry (r, c, v) -> rows r*bs+b hold columns c*bs+bc for ALL bc, v on bc == b, 0.0 elsewhere."""
+    n = indptr.shape[0] - 1
+    counts = np.diff(indptr)
+    new_ptr = np.zeros(n * bs + 1, dtype=np.int64)
+    new_ptr[1:] = np.cumsum(np.repeat(counts * bs, bs))
+    new_idx = np.empty(new_ptr[-1], dtype=np.int32)
+    new_val = np.zeros(new_ptr[-1], dtype=np.float64)
+    for r in range(n):
+        c = indices[indptr[r]:indptr[r + 1]].astype(np.int64)
+        v = data[indptr[r]:indptr[r + 1]]
+        cols = (c[:, None] * bs + np.arange(bs)[None, :]).reshape(-1)
+        for b in range(bs):
+            lo = new_ptr[r * bs + b]
+            new_idx[lo:lo + cols.shape[0]] = cols
+            vals = np.zeros((c.shape[0], bs))
+            vals[:, b] = v
+            new_val[lo:lo + cols.shape[0]] = vals.reshape(-1)
+    return new_ptr, new_idx, new_val

@@ -86,9 +86,14 @@ def test_oracle_pi_matches_reference_orchestration(name):
     """Oracle Π == Π built by the reference's unmodified interpolation.py on the dolfinx shim:
     bit-exact pattern and ownership, values to 1e-14."""
     mesh, V, gamma, K, op_name, radius, degree, cells_K, fx = load_case(name)
+    bs = int(V.dofmap.bs)
     r = orc.assemble_pi(mesh.geometry.x, mesh.geometry.dofmap, V.dofmap.list, V.element.degree, gamma.geometry.x,
                         gamma.geometry.dofmap, K.dofmap.list, K.element.interpolation_points, op_name, radius=radius,
-                        quad_degree=degree, cells_K=cells_K, n_rows=K.num_dofs)
+                        quad_degree=degree, cells_K=cells_K, n_rows=K.dofmap.index_map.size_local)
+    if bs > 1:  # blocked spaces: the reference's matrix is the scalar one with every entry blown up to a bs x bs block
+        from tests.helpers import expand_blocks_csr
+
+        r["indptr"], r["indices"], r["data"] = expand_blocks_csr(r["indptr"], r["indices"], r["data"], bs)
     np.testing.assert_array_equal(r["indptr"], fx["indptr"])
     np.testing.assert_array_equal(r["indices"], fx["indices"])
     np.testing.assert_array_equal(r["cell"], fx["cell"])
