@@ -19,6 +19,14 @@ class _CMap:
         return orc.pull_back(v0, K, np.zeros(x.shape[0], dtype=np.int64), np.asarray(x, dtype=np.float64))
 
 
+    def push_forward(self, X, cell_geometry):
+        # x = sum_k phi_k(X) v_k for the affine interval (MappedRestriction, restriction_operators.py:339-349)
+        X = np.asarray(X, dtype=np.float64).reshape(-1)
+        cg = np.asarray(cell_geometry, dtype=np.float64)
+        assert cg.shape[0] == 2, "shim: push_forward for interval cells only"
+        return cg[0][None, :] * (1.0 - X)[:, None] + cg[1][None, :] * X[:, None]
+
+
 class _Geometry:
     def __init__(self, x, dofmap):
         self.x = np.asarray(x, dtype=np.float64)

@@ -113,6 +113,7 @@ CASES = {
                                        op=("circle", "callable", 9)),
     "disk_p2v_subset": dict(n=(4, 4, 4), p=2, gamma=("network", 30, 1 / 4, 2), K=("DG", 2), op=("disk", 0.05, 3),
                             cells_K=np.arange(3, 27, 2, dtype=np.int32)),
+    "mapped_network_dg1": dict(n=(5, 5, 5), p=1, gamma=("network", 40, 1 / 5, 2), K=("DG", 1), op=("mapped",)),
     # blocked (vector) spaces, tests/test_interpolation_matrix.py:254-301: bs x bs blocks with explicit zeros
     "trace_blocked3_dg2": dict(n=(4, 4, 4), p=1, bs=3, gamma=("network", 24, 1 / 4, 2), K=("DG", 2), op=("trace",)),
     "circle_blocked2_p1k_firstvisit": dict(n=(4, 4, 4), p=1, bs=2, gamma=("network", 24, 1 / 4, 2), K=("Lagrange", 1),
@@ -147,6 +148,10 @@ def pi_fixtures():
         op = spec["op"]
         if op[0] == "trace":
             red = rro.PointwiseTrace(m1)
+        elif op[0] == "mapped":
+            from tests.golden_cases import mapped_shift
+
+            red = rro.MappedRestriction(m1, mapped_shift)
         elif op[0] == "circle":
             red = rro.Circle(m1, callable_radius if op[1] == "callable" else op[1], degree=op[2])
         else:

@@ -22,6 +22,8 @@ CASES = {
     "circle_p2v_callable_radius": dict(n=(4, 4, 4), p=2, gamma=("network", 30, 1 / 4, 2), K=("Quadrature", 4),
                                        op=("circle", "callable", 9)),
     "disk_p2v_subset": dict(n=(4, 4, 4), p=2, gamma=("network", 30, 1 / 4, 2), K=("DG", 2), op=("disk", 0.05, 3)),
+    # generic operator: points computed on the host by the operator and uploaded (restriction_operators.py:318-362)
+    "mapped_network_dg1": dict(n=(5, 5, 5), p=1, gamma=("network", 40, 1 / 5, 2), K=("DG", 1), op=("mapped",)),
     # blocked (vector) spaces: the fixture is the scalar CSR of the bs x bs blocked matrix the reference fills
     "trace_blocked3_dg2": dict(n=(4, 4, 4), p=1, bs=3, gamma=("network", 24, 1 / 4, 2), K=("DG", 2), op=("trace",)),
     "circle_blocked2_p1k_firstvisit": dict(n=(4, 4, 4), p=1, bs=2, gamma=("network", 24, 1 / 4, 2), K=("Lagrange", 1),
@@ -31,6 +33,11 @@ CASES = {
 
 def callable_radius(x):
     return 0.03 + 0.05 * x[2] ** 2
+
+
+def mapped_shift(x):
+    """The mapping of the MappedRestriction case (vectorised: x[0] are the x coordinates, ...)."""
+    return np.stack([x[0] + 0.013, x[1] - 0.007 + 0.02 * x[2], x[2] + 0.004])
 
 
 def load_case(name):
@@ -50,7 +57,7 @@ def load_case(name):
     K = functionspace(gamma, spec["K"] + ((bs,),) if bs > 1 else spec["K"])
     op = spec["op"]
     radius = degree = None
-    if op[0] != "trace":
+    if op[0] not in ("trace", "mapped"):
         radius = callable_radius if op[1] == "callable" else op[1]
         degree = op[2]
     cells_K = fx["cells_K"] if bool(fx["has_cells_K"]) else None

@@ -14,6 +14,11 @@ def make_operator(op_name, gamma, radius=None, degree=None):
 
     if op_name == "trace":
         return PointwiseTrace(gamma)
+    if op_name == "mapped":
+        from fenicsx_ii_b200 import MappedRestriction
+        from tests.golden_cases import mapped_shift
+
+        return MappedRestriction(gamma, mapped_shift)
     if op_name == "circle":
         return Circle(gamma, radius, degree=degree)
     return Disk(gamma, radius, degree=degree)

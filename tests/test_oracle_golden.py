@@ -87,9 +87,18 @@ def test_oracle_pi_matches_reference_orchestration(name):
     bit-exact pattern and ownership, values to 1e-14."""
     mesh, V, gamma, K, op_name, radius, degree, cells_K, fx = load_case(name)
     bs = int(V.dofmap.bs)
+    extra = {}
+    if op_name == "mapped":  # generic operator: the oracle takes the mapped points (weights 1, scales 1)
+        from tests.golden_cases import mapped_shift
+
+        ck = np.arange(gamma.geometry.dofmap.shape[0]) if cells_K is None else cells_K
+        phys = orc.physical_points(gamma.geometry.x, gamma.geometry.dofmap, ck, K.element.interpolation_points)
+        pts = mapped_shift(phys.T).T
+        extra = dict(points=pts, weights=np.ones((pts.shape[0], 1)), scales=np.ones(pts.shape[0]))
+        op_name = "points"
     r = orc.assemble_pi(mesh.geometry.x, mesh.geometry.dofmap, V.dofmap.list, V.element.degree, gamma.geometry.x,
                         gamma.geometry.dofmap, K.dofmap.list, K.element.interpolation_points, op_name, radius=radius,
-                        quad_degree=degree, cells_K=cells_K, n_rows=K.dofmap.index_map.size_local)
+                        quad_degree=degree, cells_K=cells_K, n_rows=K.dofmap.index_map.size_local, **extra)
     if bs > 1:  # blocked spaces: the reference's matrix is the scalar one with every entry blown up to a bs x bs block
         from tests.helpers import expand_blocks_csr
 
