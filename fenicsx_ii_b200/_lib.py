@@ -110,6 +110,9 @@ SIGNATURES = {
     "fxii_csr_transpose": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "fxii_csr_transpose_window": (C.c_int, [_vp, _i64, _i64, _vp, C.POINTER(_vp)]),
     "fxii_spgemm": (C.c_int, [_vp, _vp, _i64, _i64, _vp, C.POINTER(_vp), C.POINTER(_i64)]),
+    "fxii_spgemm_scaled": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, C.POINTER(_vp), C.POINTER(_i64)]),
+    "fxii_csr_wrap_device": (C.c_int, [_i64, _i64, _i64, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "fxii_csr_validate": (C.c_int, [_vp, _vp]),
     "fxii_csr_expand_blocks": (C.c_int, [_vp, _i32, _vp, C.POINTER(_vp)]),
     "fxii_csr_scale_rows": (C.c_int, [_vp, _vp, _vp]),
     "fxii_csr_spmv": (C.c_int, [_vp, _vp, _vp, _vp]),

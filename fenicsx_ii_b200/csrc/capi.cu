@@ -11,8 +11,9 @@ void device_iota(int32_t* a, int64_t n, cudaStream_t s);
 void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr* out, fxii_pi_stats* stats,
                  bool keep_points);
 void csr_transpose(const fxii_csr* a, int64_t c0, int64_t c1, cudaStream_t s, fxii_csr* out);
-void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row_end, cudaStream_t s, fxii_csr* out,
-            int64_t* ip_out);
+void spgemm(const fxii_csr* a, const fxii_csr* b, const double* b_scale, int64_t row_begin, int64_t row_end, cudaStream_t s,
+            fxii_csr* out, int64_t* ip_out);
+void csr_validate(const fxii_csr* a, cudaStream_t s);
 void csr_scale_rows(fxii_csr* a, const double* d_host, cudaStream_t s);
 void csr_expand_blocks(const fxii_csr* a, int bs, cudaStream_t s, fxii_csr* out);
 void csr_spmv(const fxii_csr* a, const double* u_host, double* y_host, cudaStream_t s);
@@ -546,6 +547,33 @@ int fxii_csr_from_device(int64_t n_rows, int64_t n_cols, int64_t nnz, const int6
   });
 }
 
+int fxii_csr_wrap_device(int64_t n_rows, int64_t n_cols, int64_t nnz, int64_t* indptr_dev, int32_t* indices_dev,
+                         double* values_dev, fxii_csr** out) {
+  return guarded([&] {
+    FXII_CHECK(out && n_rows >= 0 && n_cols >= 0 && nnz >= 0 && indptr_dev, "bad CSR arguments");
+    FXII_CHECK(nnz == 0 || (indices_dev && values_dev), "null array");
+    // DevBuf::release only returns blocks the allocator handed out: foreign pointers are left alone
+    auto* c = new fxii_csr();
+    c->n_rows = n_rows;
+    c->n_cols = n_cols;
+    c->nnz = nnz;
+    c->indptr.p = indptr_dev;
+    c->indptr.n = n_rows + 1;
+    c->indices.p = indices_dev;
+    c->indices.n = nnz;
+    c->values.p = values_dev;
+    c->values.n = nnz;
+    *out = c;
+  });
+}
+
+int fxii_csr_validate(const fxii_csr* a, void* stream) {
+  return guarded([&] {
+    FXII_CHECK(a, "null csr");
+    fxii::csr_validate(a, S(stream));
+  });
+}
+
 int fxii_csr_info(const fxii_csr* a, int64_t* n_rows, int64_t* n_cols, int64_t* nnz) {
   return guarded([&] {
     FXII_CHECK(a, "null csr");
@@ -609,13 +637,19 @@ int fxii_csr_transpose_window(const fxii_csr* a, int64_t col_begin, int64_t col_
   });
 }
 
-int fxii_spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row_end, void* stream, fxii_csr** out,
-                int64_t* ip) {
+static int spgemm_entry(const fxii_csr* a, const fxii_csr* b, const double* b_scale, int64_t row_begin, int64_t row_end,
+                        void* stream, fxii_csr** out, int64_t* ip) {
   return guarded([&] {
     FXII_CHECK(a && b && out, "null argument");
+    if (b_scale) {
+      cudaPointerAttributes at{};
+      const bool on_device = cudaPointerGetAttributes(&at, b_scale) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+      if (!on_device) cudaGetLastError();
+      FXII_CHECK(on_device, "b_row_scale_dev must be device memory");
+    }
     auto* c = new fxii_csr();
     try {
-      fxii::spgemm(a, b, row_begin, row_end, S(stream), c, ip);
+      fxii::spgemm(a, b, b_scale, row_begin, row_end, S(stream), c, ip);
       FXII_CUDA(cudaStreamSynchronize(S(stream)));
     } catch (...) {
       delete c;
@@ -623,6 +657,16 @@ int fxii_spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t
     }
     *out = c;
   });
+}
+
+int fxii_spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row_end, void* stream, fxii_csr** out,
+                int64_t* ip) {
+  return spgemm_entry(a, b, nullptr, row_begin, row_end, stream, out, ip);
+}
+
+int fxii_spgemm_scaled(const fxii_csr* a, const fxii_csr* b, const double* b_row_scale_dev, int64_t row_begin,
+                       int64_t row_end, void* stream, fxii_csr** out, int64_t* ip) {
+  return spgemm_entry(a, b, b_row_scale_dev, row_begin, row_end, stream, out, ip);
 }
 
 int fxii_csr_expand_blocks(const fxii_csr* a, int32_t bs, void* stream, fxii_csr** out) {

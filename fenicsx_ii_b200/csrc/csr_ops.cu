@@ -203,6 +203,7 @@ template <bool BLOCK, bool NUMERIC>
 __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int32_t* __restrict__ a_idx,
                                    const double* __restrict__ a_val, const int64_t* __restrict__ b_ptr,
                                    const int32_t* __restrict__ b_idx, const double* __restrict__ b_val,
+                                   const double* __restrict__ b_scale,
                                    int64_t row_begin, const int32_t* __restrict__ row_list, int64_t n_list, uint32_t cap,
                                    int overflow_limit, int flatten, int* __restrict__ overflow_flag,
                                    int32_t* __restrict__ g_keys,
@@ -312,12 +313,13 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
         const int64_t ka = c0 + lane;
         int64_t b0 = 0;
         int len = 0;
-        double av = 0.0;
+        double av = 0.0, dk = 1.0;
         if (ka < a1) {
           const int k = __ldg(&a_idx[ka]);
           av = __ldg(&a_val[ka]);
           b0 = __ldg(&b_ptr[k]);
           len = (int)(__ldg(&b_ptr[k + 1]) - b0);
+          if (b_scale) dk = __ldg(&b_scale[k]);
         }
         int incl = len;
 #pragma unroll
@@ -341,6 +343,7 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
           const int len_j = __shfl_sync(0xffffffffu, len, j);
           const int64_t b0_j = __shfl_sync(0xffffffffu, b0, j);
           const double av_j = __shfl_sync(0xffffffffu, av, j);
+          const double dk_j = __shfl_sync(0xffffffffu, dk, j);
           const bool active = t < total;
           int32_t col = -2 - lane;  // inactive lanes: distinct keys that match nothing
           double prod = 0.0;
@@ -348,7 +351,7 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
           if (active) {
             const int64_t kb = b0_j + (t - (incl_j - len_j));
             col = __ldg(&b_idx[kb]);
-            prod = av_j * __ldg(&b_val[kb]);
+            prod = av_j * (dk_j * __ldg(&b_val[kb]));  // (M B) first, as the unfused product rounds
             bool is_new;
             slot = hash_insert(keys, tcap, col, is_new);
           }
@@ -369,20 +372,22 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
       // loaded four per lane before the first insert, so that a row costs one memory latency, not
       // one per dependent load.
       int k_n = 0;
-      double av_n = 0.0;
+      double av_n = 0.0, dk_n = 1.0;
       int64_t b0_n = 0, b1_n = 0;
       if (a0 < a1) {
         k_n = __ldg(&a_idx[a0]);
         av_n = NUMERIC ? __ldg(&a_val[a0]) : 0.0;
+        if (NUMERIC && b_scale) dk_n = __ldg(&b_scale[k_n]);
         b0_n = __ldg(&b_ptr[k_n]);
         b1_n = __ldg(&b_ptr[k_n + 1]);
       }
       for (int64_t ka = a0; ka < a1; ++ka) {
-        const double av = av_n;
+        const double av = av_n, dk = dk_n;
         const int64_t b0 = b0_n, b1 = b1_n;
         if (ka + 1 < a1) {
           k_n = __ldg(&a_idx[ka + 1]);
           av_n = NUMERIC ? __ldg(&a_val[ka + 1]) : 0.0;
+          if (NUMERIC && b_scale) dk_n = __ldg(&b_scale[k_n]);
           b0_n = __ldg(&b_ptr[k_n]);
           b1_n = __ldg(&b_ptr[k_n + 1]);
         }
@@ -406,7 +411,7 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
             if (col[u] == kEmpty) continue;
             bool is_new;
             const uint32_t slot = hash_insert(keys, tcap, col[u], is_new);
-            if (NUMERIC) vals[slot] += av * bv[u];
+            if (NUMERIC) vals[slot] += av * (dk * bv[u]);
             if (overflow_limit > 0 && is_new) atomicAdd(&s_new[gid], 1);
             if (!NUMERIC && slot == 0xffffffffu) atomicAdd(&s_new[gid], (int)tcap);  // full: force the retry
           }
@@ -462,9 +467,267 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
   }
 }
 
-// bin index by size: first bin with capacity >= 2*size, long rows in the last bin, empty rows skipped
+// =================================================================================================
+// Lean warp-per-row kernel for SHORT rows of B (mean length <= 32: Π has 4..32 entries per row).
+//
+// The flattened loops above spend ~4 warp instructions per intermediate product on index arithmetic
+// (a 5-step shuffle binary search per product to find its row of B).  Here G lanes (a power of two
+// >= the mean row length of B) own one row of B and the warp walks 32/G rows of B per step:
+//   stage : every lane loads ONE entry of A's row (k, a_ik), the bounds of B's row k and the optional
+//           row scale d_k — 32 independent dependent-load chains in flight;
+//   step  : three shuffles hand sub-group g the row j0+g; its lanes load B's entries (the next
+//           step's loads are issued before the current step's table work) and insert them.
+// Tables: keys i32[cap] + values f64[cap] = 12 B per slot (the round-1 kernel kept a separate 4 B/slot
+// sort buffer and sized tables for a load factor of 0.5); rows are binned by nnz <= LF*cap.
+// Numeric sum order is the sequential one (ascending k for every output column): entries of ONE row of
+// B have distinct columns, so only different sub-groups can meet in a slot, and the sub-groups of a
+// step add one after the other (ascending k), separated by __syncwarp().
+// After the products the occupied slots are compacted IN PLACE (the write cursor never passes the read
+// cursor), then sorted by column: up to 8 (column, position) keys per lane in REGISTERS — lane-crossing
+// steps are shuffles — or, for larger rows, a key/value bitonic sort in the table's own storage.
+// Symbolic passes detect a table that is too small by a probe limit (no per-insert counter atomics):
+// the row is marked -1 and retried in the next larger table.
+// =================================================================================================
+constexpr uint32_t kNoSlot = 0xffffffffu;
+constexpr uint32_t kProbeLimit = 48;  // linear probing exceeds this only beyond ~85 % load
+
+__device__ __forceinline__ uint32_t table_insert(int32_t* keys, uint32_t mask, int shift, int32_t key, uint32_t max_probe) {
+  uint32_t h = ((uint32_t)key * 0x9E3779B1u) >> shift;  // Fibonacci hashing: top bits of the product
+  for (uint32_t probe = 0; probe <= max_probe; ++probe) {
+    int32_t cur = *(volatile int32_t*)(keys + h);
+    if (cur == key) return h;  // the common case (rows compress ~10x): no atomic
+    if (cur == kEmpty) {
+      cur = atomicCAS(&keys[h], kEmpty, key);
+      if (cur == kEmpty || cur == key) return h;
+    }
+    h = (h + 1) & mask;
+  }
+  return kNoSlot;
+}
+
+// bitonic sort of the 32*R keys of a warp held R per lane (element e = R*lane + r)
+template <int R>
+__device__ __forceinline__ void warp_sort_regs(uint64_t (&key)[R], int lane) {
+  constexpr uint32_t N = 32u * R;
+#pragma unroll
+  for (uint32_t k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      if (j >= (uint32_t)R) {
+        // partner element e ^ j lives in lane ^ (j / R), same register; k >= 2R: the direction depends on the lane only
+        const int lm = (int)(j / R);
+        const bool up = (((uint32_t)R * (uint32_t)lane) & k) == 0;
+        const bool take_min = ((lane & lm) == 0) == up;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const uint64_t other = __shfl_xor_sync(0xffffffffu, key[r], lm);
+          key[r] = (take_min == (other < key[r])) ? other : key[r];
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if ((r & (int)j) == 0) {
+            const bool up = ((((uint32_t)R * (uint32_t)lane) | (uint32_t)r) & k) == 0;
+            const uint64_t a = key[r], b = key[r | (int)j];
+            const bool sw = (a > b) == up;
+            key[r] = sw ? b : a;
+            key[r | (int)j] = sw ? a : b;
+          }
+        }
+      }
+    }
+  }
+}
+
+// G: lanes per row of B (4, 8, 16, 32).  R: keys per lane of the register sort (numeric; 0: sort in shared memory).
+// One warp per output row; W = blockDim.x/32 rows per block; dynamic shared memory W * cap * (NUMERIC ? 12 : 4) bytes.
+template <int G, int R, bool NUMERIC>
 __global__ void __launch_bounds__(256)
-classify_rows_kernel(const int64_t* __restrict__ size, int64_t n_rows, int n_exact_bins, uint8_t* __restrict__ bin_of,
+spgemm_warp_kernel(const int64_t* __restrict__ a_ptr, const int32_t* __restrict__ a_idx, const double* __restrict__ a_val,
+                   const int64_t* __restrict__ b_ptr, const int32_t* __restrict__ b_idx, const double* __restrict__ b_val,
+                   const double* __restrict__ b_scale, int64_t row_begin, const int32_t* __restrict__ row_list,
+                   int64_t n_list, uint32_t cap, int shift, uint32_t max_probe, int* __restrict__ overflow_flag,
+                   int64_t* __restrict__ row_size, const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx,
+                   double* __restrict__ c_val) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  constexpr int NG = 32 / G;  // rows of B per step
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int W = blockDim.x >> 5;
+  const int sub = lane & (G - 1), grp = lane / G;
+  unsigned char* base = s_raw + (size_t)wid * cap * (NUMERIC ? 12 : 4);
+  double* vals = reinterpret_cast<double*>(base);  // NUMERIC only
+  int32_t* keys = reinterpret_cast<int32_t*>(base + (NUMERIC ? (size_t)cap * 8 : 0));
+  const uint32_t mask = cap - 1;
+  for (int64_t li = (int64_t)blockIdx.x * W + wid; li < n_list; li += (int64_t)gridDim.x * W) {
+    const int64_t i = row_list[li];
+    for (uint32_t t = lane; t < cap; t += 32) {
+      keys[t] = kEmpty;
+      if (NUMERIC) vals[t] = 0.0;
+    }
+    __syncwarp();
+    const int64_t a0 = a_ptr[row_begin + i], a1 = a_ptr[row_begin + i + 1];
+    bool overflow = false;
+    for (int64_t c0 = a0; c0 < a1 && !overflow; c0 += 32) {
+      // ---- stage: one entry of A's row per lane ----------------------------------------------------
+      const int64_t ka = c0 + lane;
+      int64_t b0 = 0;
+      int len = 0;
+      double av = 0.0, dk = 1.0;
+      if (ka < a1) {
+        const int k = __ldg(&a_idx[ka]);
+        b0 = __ldg(&b_ptr[k]);
+        len = (int)(__ldg(&b_ptr[k + 1]) - b0);
+        if (NUMERIC) {
+          av = __ldg(&a_val[ka]);
+          if (b_scale) dk = __ldg(&b_scale[k]);
+        }
+      }
+      const int nk = (int)min((int64_t)32, a1 - c0);
+      // ---- steps: NG rows of B at a time; the first G entries of the next step's rows are requested early
+      int64_t nb0 = __shfl_sync(0xffffffffu, b0, grp);
+      int nlen = __shfl_sync(0xffffffffu, len, grp);
+      double nav = NUMERIC ? __shfl_sync(0xffffffffu, av, grp) : 0.0;
+      double ndk = NUMERIC ? __shfl_sync(0xffffffffu, dk, grp) : 1.0;
+      int32_t ncol = kEmpty;
+      double nbv = 0.0;
+      if (sub < nlen) {
+        ncol = __ldg(&b_idx[nb0 + sub]);
+        if (NUMERIC) nbv = __ldg(&b_val[nb0 + sub]);
+      }
+      for (int j0 = 0; j0 < nk; j0 += NG) {
+        const int64_t b0_j = nb0;
+        const int len_j = nlen;
+        const double av_j = nav, dk_j = ndk;
+        int32_t col = ncol;
+        double bv = nbv;
+        if (j0 + NG < nk) {  // warp-uniform
+          const int jn = j0 + NG + grp;  // <= 31: j0 + NG <= 31 and a multiple of NG
+          nb0 = __shfl_sync(0xffffffffu, b0, jn);
+          nlen = __shfl_sync(0xffffffffu, len, jn);
+          if (NUMERIC) {
+            nav = __shfl_sync(0xffffffffu, av, jn);
+            ndk = __shfl_sync(0xffffffffu, dk, jn);
+          }
+          ncol = kEmpty;
+          if (sub < nlen) {
+            ncol = __ldg(&b_idx[nb0 + sub]);
+            if (NUMERIC) nbv = __ldg(&b_val[nb0 + sub]);
+          }
+        }
+        const int maxlen = __reduce_max_sync(0xffffffffu, len_j);
+        for (int t0 = 0; t0 < maxlen; t0 += G) {  // warp-uniform; one pass unless a row of B is longer than G
+          const int t = t0 + sub;
+          if (t0 > 0) {
+            col = kEmpty;
+            if (t < len_j) {
+              col = __ldg(&b_idx[b0_j + t]);
+              if (NUMERIC) bv = __ldg(&b_val[b0_j + t]);
+            }
+          }
+          const bool active = col != kEmpty;
+          uint32_t slot = 0;
+          if (active) slot = table_insert(keys, mask, shift, col, max_probe);
+          if (!NUMERIC) {
+            if (__any_sync(0xffffffffu, active && slot == kNoSlot)) overflow = true;  // warp-uniform
+          } else {
+            const double prod = av_j * (dk_j * bv);  // (d_k b_kj) first: what the unfused product M·B rounds
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+              if (active && grp == g) vals[slot] += prod;
+              if (NG > 1) __syncwarp();
+            }
+            if (NG == 1) __syncwarp();
+          }
+        }
+        if (!NUMERIC && overflow) break;
+      }
+    }
+    __syncwarp();
+    if (!NUMERIC) {
+      int local = 0;
+      for (uint32_t t = lane; t < cap; t += 32) local += keys[t] != kEmpty;
+      for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+      if (lane == 0) {
+        row_size[i] = overflow ? -1 : local;
+        if (overflow) *overflow_flag = 1;
+      }
+      __syncwarp();
+      continue;
+    }
+    // ---- in-place compaction of the occupied slots: (keys[e], vals[e]), e < nnz -------------------------
+    uint32_t n_occ = 0;
+    for (uint32_t t0 = 0; t0 < cap; t0 += 32) {
+      const int32_t key = keys[t0 + lane];
+      const double v = vals[t0 + lane];
+      const bool occ = key != kEmpty;
+      const unsigned ball = __ballot_sync(0xffffffffu, occ);
+      __syncwarp();  // every lane has read its slot before any lane overwrites one (dst <= t0 + lane)
+      if (occ) {
+        const uint32_t dst = n_occ + __popc(ball & ((1u << lane) - 1u));
+        keys[dst] = key;
+        vals[dst] = v;
+      }
+      n_occ += __popc(ball);
+    }
+    __syncwarp();
+    const int64_t out0 = c_ptr[i];
+    const uint32_t nnz = (uint32_t)(c_ptr[i + 1] - out0);  // == n_occ (symbolic count)
+    if constexpr (R > 0) {
+      uint64_t key[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const uint32_t e = (uint32_t)R * lane + r;
+        key[r] = e < nnz ? (((uint64_t)(uint32_t)keys[e] << 32) | e) : ~0ULL;
+      }
+      warp_sort_regs<R>(key, lane);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const uint32_t e = (uint32_t)R * lane + r;
+        if (e < nnz) {
+          c_idx[out0 + e] = (int32_t)(key[r] >> 32);
+          c_val[out0 + e] = vals[(uint32_t)(key[r] & 0xffffffffu)];
+        }
+      }
+    } else {
+      uint32_t scap = 2;
+      while (scap < nnz) scap <<= 1;  // <= cap (nnz <= cap)
+      for (uint32_t t = nnz + lane; t < scap; t += 32) keys[t] = 0x7fffffff;
+      __syncwarp();
+      for (uint32_t k = 2; k <= scap; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+          for (uint32_t t = lane; t < scap / 2; t += 32) {
+            const uint32_t x = 2 * t - (t & (j - 1));
+            const uint32_t y = x | j;
+            const bool up = (x & k) == 0;
+            const int32_t kx = keys[x], ky = keys[y];
+            if ((kx > ky) == up) {
+              keys[x] = ky;
+              keys[y] = kx;
+              const double vx = vals[x], vy = vals[y];
+              vals[x] = vy;
+              vals[y] = vx;
+            }
+          }
+          __syncwarp();
+        }
+      }
+      for (uint32_t t = lane; t < nnz; t += 32) {
+        c_idx[out0 + t] = keys[t];
+        c_val[out0 + t] = vals[t];
+      }
+    }
+    __syncwarp();  // the table is re-initialised by the next row
+  }
+}
+
+// bin index by size: first bin b with size <= thr.v[b] (thr.v[b] < 0: bin unused); larger rows go to the last
+// bin (long rows); empty rows are skipped
+struct BinThresholds {
+  int64_t v[kNumBins - 1];
+};
+__global__ void __launch_bounds__(256)
+classify_rows_kernel(const int64_t* __restrict__ size, int64_t n_rows, BinThresholds thr, uint8_t* __restrict__ bin_of,
                      int32_t* __restrict__ rows, unsigned long long* __restrict__ bin_count) {
   __shared__ unsigned int s_count[kNumBins + 1];
   if (threadIdx.x <= kNumBins) s_count[threadIdx.x] = 0;
@@ -474,11 +737,9 @@ classify_rows_kernel(const int64_t* __restrict__ size, int64_t n_rows, int n_exa
     int b = kNumBins;  // empty rows sort last and are never launched
     if (u > 0) {
       b = kNumBins - 1;  // long rows
-      for (int q = 0; q < n_exact_bins; ++q)
-        if (2 * u <= (int64_t)bin_cap(q)) {
-          b = q;
-          break;
-        }
+#pragma unroll
+      for (int q = kNumBins - 2; q >= 0; --q)
+        if (u <= thr.v[q]) b = q;
     }
     bin_of[i] = (uint8_t)b;
     rows[i] = (int32_t)i;
@@ -515,7 +776,7 @@ struct RowBins {
   int64_t offset[kNumBins + 1] = {0};
 };
 
-static void bin_rows(const int64_t* size, int64_t m, int n_exact_bins, cudaStream_t s, RowBins& rb) {
+static void bin_rows(const int64_t* size, int64_t m, const BinThresholds& thr, cudaStream_t s, RowBins& rb) {
   DevBuf<uint8_t> bin_of, bin_sorted;
   DevBuf<int32_t> rows;
   DevBuf<unsigned long long> counts;
@@ -525,7 +786,7 @@ static void bin_rows(const int64_t* size, int64_t m, int n_exact_bins, cudaStrea
   rb.sorted_rows.alloc(m, s);
   counts.alloc(kNumBins + 1, s);
   FXII_CUDA(cudaMemsetAsync(counts.p, 0, sizeof(unsigned long long) * (kNumBins + 1), s));
-  { classify_rows_kernel<<<grid_for(m, 256, 8), 256, 0, s>>>(size, m, n_exact_bins, bin_of.p, rows.p, counts.p); FXII_LAUNCHED(1); }
+  { classify_rows_kernel<<<grid_for(m, 256, 8), 256, 0, s>>>(size, m, thr, bin_of.p, rows.p, counts.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
   size_t tb = 0;
   FXII_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, bin_of.p, bin_sorted.p, rows.p, rb.sorted_rows.p, m, 0, 4, s));
@@ -557,8 +818,32 @@ static int flatten_mode(const fxii_csr* b) {
   return b->nnz <= 64 * std::max<int64_t>(b->n_rows, 1) ? 3 : 1;
 }
 
-void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row_end, cudaStream_t s, fxii_csr* out,
-            int64_t* ip_out) {
+// FXII_SPGEMM_LEAN=0 restores the round-1 kernels everywhere (A/B measurements); FXII_SPGEMM_LF sets the load factor
+// (percent) that bins rows into the numeric tables of the lean kernel.
+static bool lean_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("FXII_SPGEMM_LEAN");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+static int lean_load_factor_pct() {
+  static const int lf = [] {
+    const char* e = getenv("FXII_SPGEMM_LF");
+    const int v = e ? atoi(e) : 70;
+    return v < 30 ? 30 : (v > 85 ? 85 : v);
+  }();
+  return lf;
+}
+static int ilog2(uint32_t v) {
+  int l = 0;
+  while ((1u << l) < v) ++l;
+  return l;
+}
+
+// C = A[row_begin:row_end, :] · diag(b_scale) · B.  b_scale (device, [b->n_rows]) may be null.
+void spgemm(const fxii_csr* a, const fxii_csr* b, const double* b_scale, int64_t row_begin, int64_t row_end, cudaStream_t s,
+            fxii_csr* out, int64_t* ip_out) {
   FXII_CHECK(a->n_cols == b->n_rows, "spgemm: inner dimensions differ");
   if (row_end < 0) row_end = a->n_rows;
   FXII_CHECK(row_begin >= 0 && row_begin <= row_end && row_end <= a->n_rows, "spgemm: bad row window");
@@ -595,7 +880,7 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
   DevBuf<int> overflow;
   overflow.alloc(1, s);
 
-  // launch one kernel over a row list.  cap == 0: global-memory tables of 2*min(size, n_cols) slots.
+  // launch one round-1 kernel over a row list.  cap == 0: global-memory tables of 2*min(size, n_cols) slots.
   auto launch = [&](bool numeric, const int32_t* list, int64_t nl, uint32_t cap, bool block, int threads, int overflow_limit,
                     const int64_t* size, int32_t* c_idx, double* c_val) {
     if (nl == 0) return;
@@ -628,9 +913,9 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
       FXII_CUDA(cudaFuncSetAttribute(spgemm_rows_kernel<BLK, NUM>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                      (int)smem));                                                                     \
     spgemm_rows_kernel<BLK, NUM><<<grid, threads, smem, s>>>(                                                         \
-        a->indptr.p, a->indices.p, a->values.p, b->indptr.p, b->indices.p, b->values.p, row_begin, list, nl, cap,     \
-        overflow_limit, flatten_mode(b), overflow.p, global ? g_keys.p : nullptr, global ? g_vals.p : nullptr,                         \
-        global ? g_sort.p : nullptr, global ? g_off.p : nullptr, row_nnz.p, out->indptr.p, c_idx, c_val);                                          \
+        a->indptr.p, a->indices.p, a->values.p, b->indptr.p, b->indices.p, b->values.p, b_scale, row_begin, list, nl, \
+        cap, overflow_limit, flatten_mode(b), overflow.p, global ? g_keys.p : nullptr, global ? g_vals.p : nullptr,   \
+        global ? g_sort.p : nullptr, global ? g_off.p : nullptr, row_nnz.p, out->indptr.p, c_idx, c_val);             \
     FXII_CUDA(cudaGetLastError());                                                                                    \
     FXII_LAUNCHED(1);                                                                                                 \
   } while (0)
@@ -640,6 +925,52 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
     else FXII_SPGEMM_LAUNCH(false, false);
 #undef FXII_SPGEMM_LAUNCH
     if (global) FXII_CUDA(cudaStreamSynchronize(s));  // tables are freed when this scope ends
+  };
+
+  // lean warp-per-row kernel (short rows of B): G lanes per row of B from B's mean row length
+  const int64_t b_mean = b->nnz / std::max<int64_t>(b->n_rows, 1);
+  const bool lean = lean_enabled() && b->nnz <= 32 * std::max<int64_t>(b->n_rows, 1);
+  const int G = b_mean <= 4 ? 4 : (b_mean <= 8 ? 8 : (b_mean <= 16 ? 16 : 32));
+  auto launch_warp = [&](bool numeric, const int32_t* list, int64_t nl, uint32_t cap, uint32_t max_probe, int32_t* c_idx,
+                         double* c_val) {
+    if (nl == 0) return;
+    // warps per block: tables of a block within 48 KB, at most 8 warps
+    const size_t per_warp = (size_t)cap * (numeric ? 12 : 4);
+    int W = (int)std::min<size_t>(8, std::max<size_t>(1, (48 * 1024) / per_warp));
+    const size_t smem = per_warp * W;
+    const int grid = (int)std::min<int64_t>((nl + W - 1) / W, (int64_t)num_sms() * 32);
+    const int shift = 32 - ilog2(cap);
+    // register sort: R keys per lane cover 32*R >= the largest row of the bin
+    const int lf = lean_load_factor_pct();
+    const int64_t max_nnz = (int64_t)cap * lf / 100;
+    int R = 0;
+    if (numeric) R = max_nnz <= 64 ? 2 : (max_nnz <= 128 ? 4 : (max_nnz <= 256 ? 8 : (max_nnz <= 512 ? 16 : 0)));
+#define FXII_WARP_LAUNCH(GG, RR, NUM)                                                                                  \
+  do {                                                                                                                 \
+    if (smem > 48 * 1024)                                                                                              \
+      FXII_CUDA(cudaFuncSetAttribute(spgemm_warp_kernel<GG, RR, NUM>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                     (int)smem));                                                                      \
+    spgemm_warp_kernel<GG, RR, NUM><<<grid, 32 * W, smem, s>>>(                                                        \
+        a->indptr.p, a->indices.p, a->values.p, b->indptr.p, b->indices.p, b->values.p, b_scale, row_begin, list, nl,  \
+        cap, shift, max_probe, overflow.p, row_nnz.p, out->indptr.p, c_idx, c_val);                                    \
+  } while (0)
+#define FXII_WARP_R(GG)                                                                                                \
+  do {                                                                                                                 \
+    if (!numeric) FXII_WARP_LAUNCH(GG, 0, false);                                                                      \
+    else if (R == 2) FXII_WARP_LAUNCH(GG, 2, true);                                                                    \
+    else if (R == 4) FXII_WARP_LAUNCH(GG, 4, true);                                                                    \
+    else if (R == 8) FXII_WARP_LAUNCH(GG, 8, true);                                                                    \
+    else if (R == 16) FXII_WARP_LAUNCH(GG, 16, true);                                                                  \
+    else FXII_WARP_LAUNCH(GG, 0, true);                                                                                \
+  } while (0)
+    if (G == 4) FXII_WARP_R(4);
+    else if (G == 8) FXII_WARP_R(8);
+    else if (G == 16) FXII_WARP_R(16);
+    else FXII_WARP_R(32);
+#undef FXII_WARP_R
+#undef FXII_WARP_LAUNCH
+    FXII_CUDA(cudaGetLastError());
+    FXII_LAUNCHED(1);
   };
 
   // rows whose count came back as -1 (table overflow) -> list
@@ -671,22 +1002,32 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
 
   tr.mark("ub + alloc");
   // ---- symbolic --------------------------------------------------------------------------------
+  // exact bins 0..4: tables of 64..1024 slots; round-1 kernels hold ub <= cap/2, the lean kernel ub <= 0.75 cap
+  BinThresholds sym_thr;
+  for (int q = 0; q < kNumBins - 1; ++q) sym_thr.v[q] = q < 5 ? (lean ? (int64_t)bin_cap(q) * 3 / 4 : (int64_t)bin_cap(q) / 2) : -1;
   RowBins sym;
-  bin_rows(ub.p, m, 5, s, sym);  // exact bins 0..4 (ub <= 512); synchronises, so h_ip is valid
+  bin_rows(ub.p, m, sym_thr, s, sym);  // synchronises, so h_ip is valid
   tr.mark("bin rows (symbolic)");
   if (ip_out) *ip_out = h_ip;
   FXII_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
-  for (int bin = 0; bin < 5; ++bin)
-    launch(false, sym.sorted_rows.p + sym.offset[bin], sym.count[bin], bin_cap(bin), false, 256, 0, ub.p, nullptr, nullptr);
+  for (int bin = 0; bin < 5; ++bin) {
+    const int32_t* list = sym.sorted_rows.p + sym.offset[bin];
+    if (lean) launch_warp(false, list, sym.count[bin], bin_cap(bin), bin_cap(bin), nullptr, nullptr);
+    else launch(false, list, sym.count[bin], bin_cap(bin), false, 256, 0, ub.p, nullptr, nullptr);
+  }
   tr.mark("symbolic exact bins");
   const int64_t n_long = sym.count[kNumBins - 1];
   if (n_long > 0) {
-    // escalating attempts: rows that overflow a table (more distinct columns than its limit) retry
-    // in the next, larger one; the last resort counts in global memory
-    launch(false, sym.sorted_rows.p + sym.offset[kNumBins - 1], n_long, 1024, false, 256, 768, ub.p, nullptr, nullptr);
+    // escalating attempts: rows that overflow a table retry in the next, larger one; the last resort counts in
+    // global memory.  Long rows compress strongly here (C_i is a union of overlapping neighbourhoods), so most
+    // of them fit the first, 1024-slot table.
+    const int32_t* list = sym.sorted_rows.p + sym.offset[kNumBins - 1];
+    if (lean) launch_warp(false, list, n_long, 1024, kProbeLimit, nullptr, nullptr);
+    else launch(false, list, n_long, 1024, false, 256, 768, ub.p, nullptr, nullptr);
     int64_t n_retry_rows = select_overflowed();
     if (n_retry_rows > 0) {
-      launch(false, retry.p, n_retry_rows, 4096, false, 128, 3072, ub.p, nullptr, nullptr);
+      if (lean) launch_warp(false, retry.p, n_retry_rows, 8192, kProbeLimit, nullptr, nullptr);
+      else launch(false, retry.p, n_retry_rows, 4096, false, 128, 3072, ub.p, nullptr, nullptr);
       n_retry_rows = select_overflowed();
     }
     if (n_retry_rows > 0) {
@@ -700,8 +1041,14 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
   int64_t nnz = 0;
   FXII_CUDA(cudaMemcpyAsync(&nnz, out->indptr.p + m, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
   // ---- numeric ---------------------------------------------------------------------------------
+  // bins 0..7: shared-memory tables of 64..8192 slots; bin 8: exact-size tables in global memory.
+  // Lean kernel: bins 0..5 (64..2048 slots, 12 B per slot) hold nnz <= LF*cap; round-1 kernels: nnz <= cap/2.
+  BinThresholds num_thr;
+  const int lf = lean_load_factor_pct();
+  for (int q = 0; q < kNumBins - 1; ++q)
+    num_thr.v[q] = (lean && q <= 5) ? (int64_t)bin_cap(q) * lf / 100 : (int64_t)bin_cap(q) / 2;
   RowBins num;
-  bin_rows(row_nnz.p, m, 8, s, num);  // synchronises
+  bin_rows(row_nnz.p, m, num_thr, s, num);  // synchronises
   out->nnz = nnz;
   out->indices.alloc(nnz, s);
   out->values.alloc(nnz, s);
@@ -711,7 +1058,9 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row
   for (int bin = 0; bin < kNumBins; ++bin) {
     const int32_t* list = num.sorted_rows.p + num.offset[bin];
     const uint32_t cap = bin < kNumBins - 1 ? bin_cap(bin) : 0;  // 0: exact-size tables in global memory
-    if (long_b) {
+    if (lean && bin <= 5) {
+      launch_warp(true, list, num.count[bin], cap, cap, out->indices.p, out->values.p);
+    } else if (long_b) {
       // long rows of B (>= 64 entries on average): a whole block works on one output row from the 1024-slot bin
       // on (config 3: 2048-slot bin 85 -> 47 ms; the 512-slot bin measured slower that way) — one pass of the block covers a row of B, and the 16 B/slot table is shared by 4-16 warps instead
       // of pinning 8-32 KB of shared memory per WARP (6 resident warps per SM in the 2048-slot bin)
@@ -838,6 +1187,46 @@ void csr_spmv(const fxii_csr* a, const double* u_host, double* y_host, cudaStrea
     FXII_CUDA(cudaMemcpyAsync(y_host, y.p, sizeof(double) * (size_t)a->n_rows, cudaMemcpyDeviceToHost, s));
   }
   FXII_CUDA(cudaStreamSynchronize(s));
+}
+
+// ---- validation of caller-supplied matrices ---------------------------------------------------------
+// The products assume what PETSc's assembled AIJ guarantees: indptr monotone from 0 to nnz, columns in range and
+// strictly ascending (hence unique) inside every row.  bad[0] = first violation kind (1 indptr, 2 column range,
+// 3 order / duplicate).
+__global__ void __launch_bounds__(256)
+validate_csr_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, int64_t n_rows, int64_t n_cols,
+                    int64_t nnz, int* __restrict__ bad) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t a = indptr[r], b = indptr[r + 1];
+    if (a > b || a < 0 || b > nnz || (r == 0 && a != 0) || (r == n_rows - 1 && b != nnz)) {
+      atomicMax(bad, 1);
+      continue;
+    }
+    int32_t prev = -1;
+    for (int64_t k = a; k < b; ++k) {
+      const int32_t c = indices[k];
+      if (c < 0 || c >= n_cols) atomicMax(bad, 2);
+      else if (c <= prev) atomicMax(bad, 3);
+      prev = c;
+    }
+  }
+}
+
+void csr_validate(const fxii_csr* a, cudaStream_t s) {
+  DevBuf<int> bad;
+  bad.alloc(1, s);
+  FXII_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), s));
+  if (a->n_rows > 0) {
+    { validate_csr_kernel<<<grid_for(a->n_rows, 256, 8), 256, 0, s>>>(a->indptr.p, a->indices.p, a->n_rows, a->n_cols, a->nnz, bad.p); FXII_LAUNCHED(1); }
+    FXII_CUDA(cudaGetLastError());
+  }
+  int h = 0;
+  FXII_CUDA(cudaMemcpyAsync(&h, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  FXII_CUDA(cudaStreamSynchronize(s));
+  FXII_CHECK(a->n_rows > 0 || a->nnz == 0, "CSR: entries without rows");
+  FXII_CHECK(h != 1, "CSR: indptr must rise monotonically from 0 to nnz");
+  FXII_CHECK(h != 2, "CSR: column index out of range");
+  FXII_CHECK(h != 3, "CSR: columns must be strictly ascending inside every row (sort and sum duplicates first)");
 }
 
 }  // namespace fxii

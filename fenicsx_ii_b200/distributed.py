@@ -1,12 +1,16 @@
-"""Multi-GPU plumbing: Γ-row sharding, the all-gather of row-sharded CSR matrices and the
-V-dof-row-sharded block product Πᵀ(M_ΓΠ).
+"""Multi-GPU plumbing: Γ-row sharding, the all-gather-v of row-sharded CSR matrices and the
+V-dof-row-sharded block products Πᵀ(M_ΓΠ) and MΠ.
 
 Π assembly needs no communication (every Γ row is independent; Ω is replicated).  The only
-collective of the path is the all-gather-v of the CSR arrays of the row shards, done with
-``torch.distributed`` (NCCL on GPUs; gloo on CPU in the tests) on max-padded buffers.
+collective of the path is the all-gather-v of the CSR arrays of Π's row shards
+(``torch.distributed``: NCCL on GPUs, gloo on CPU in the tests).  Shard sizes are exchanged ONCE per
+Γ (``GatherPlan``); with a plan the exchange itself runs without any host synchronisation and writes
+every shard straight into its slice of the gathered arrays.
 """
 
 from __future__ import annotations
+
+from dataclasses import dataclass, field
 
 import numpy as np
 
@@ -18,97 +22,140 @@ def shard_range(n: int, world: int, rank: int) -> tuple[int, int]:
     return begin, begin + base + (1 if rank < rem else 0)
 
 
-def allgatherv_csr(indptr, indices, values, group=None, packed: "bool | None" = None):
-    """All-gather row-sharded CSR arrays (torch tensors on the collective's device).
+@dataclass
+class GatherPlan:
+    """Sizes of the row shards of one matrix on every rank (one small all-gather + one host read, done once)."""
 
-    Every rank passes its shard (indptr int64[m_r+1] starting at 0, indices int32[nnz_r],
-    values float64[nnz_r]) and receives the row-concatenated matrix (indptr, indices, values).
-    NCCL has no all-gather-v.  After one small all-gather of the shard sizes:
+    world: int
+    rank: int
+    rows: np.ndarray  # int64[world]
+    nnzs: np.ndarray  # int64[world]
+    row_off: np.ndarray = field(init=False)  # int64[world+1]
+    nnz_off: np.ndarray = field(init=False)
 
-    * packed (default while the padded exchange stays below 32 MiB, i.e. latency bound): row counts, values and indices of
-      a shard travel as ONE byte record padded to the largest shard — a single all-gather — and are sliced
-      out of the received records.  24 small broadcasts cost 3.4 ms on 8 GPUs for 3 MB shards; this is one
-      collective.
-    * otherwise every shard is broadcast straight into its slice of the preallocated result (no padding)."""
+    def __post_init__(self):
+        self.row_off = np.concatenate([[0], np.cumsum(self.rows)]).astype(np.int64)
+        self.nnz_off = np.concatenate([[0], np.cumsum(self.nnzs)]).astype(np.int64)
+
+    @property
+    def n_rows(self) -> int:
+        return int(self.row_off[-1])
+
+    @property
+    def nnz(self) -> int:
+        return int(self.nnz_off[-1])
+
+    def matches(self, n_rows_local: int, nnz_local: int) -> bool:
+        return int(self.rows[self.rank]) == n_rows_local and int(self.nnzs[self.rank]) == nnz_local
+
+
+def plan_allgatherv(n_rows_local: int, nnz_local: int, device, group=None) -> GatherPlan:
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    dev = indptr.device
-    sizes = torch.tensor([indptr.numel() - 1, indices.numel()], dtype=torch.int64, device=dev)
-    all_sizes = torch.empty(2 * world, dtype=torch.int64, device=dev)
+    sizes = torch.tensor([n_rows_local, nnz_local], dtype=torch.int64, device=device)
+    all_sizes = torch.empty(2 * world, dtype=torch.int64, device=device)
     dist.all_gather_into_tensor(all_sizes, sizes, group=group)
-    all_sizes = all_sizes.view(world, 2).cpu().numpy()
-    row_off = np.concatenate([[0], np.cumsum(all_sizes[:, 0])])
-    nnz_off = np.concatenate([[0], np.cumsum(all_sizes[:, 1])])
-    max_rows, max_nnz = int(all_sizes[:, 0].max()), int(all_sizes[:, 1].max())
+    all_sizes = all_sizes.view(world, 2).cpu().numpy()  # the one host read of the exchange; cached in the plan
+    return GatherPlan(world, rank, all_sizes[:, 0].copy(), all_sizes[:, 1].copy())
+
+
+def _gatherv_into(out, off, local, plan: GatherPlan, group):
+    """out[off[r]:off[r+1]] <- rank r's `local`, for every r, in place.  NCCL: ONE coalesced group of
+    broadcasts per array (``all_gather`` with a list of differently sized views); otherwise (gloo, or a torch
+    build without that path) one asynchronous broadcast per shard."""
+    import torch.distributed as dist
+
+    world, rank = plan.world, plan.rank
+    views = [out[int(off[r]):int(off[r + 1])] for r in range(world)]
+    if dist.get_backend(group) == "nccl" and all(v.numel() > 0 for v in views):
+        try:
+            dist.all_gather(views, local, group=group)
+            return
+        except (RuntimeError, ValueError, TypeError):
+            pass
+    views[rank].copy_(local)
+    ranks = dist.get_process_group_ranks(group) if group is not None else list(range(world))
+    work = [dist.broadcast(views[r], src=ranks[r], group=group, async_op=True) for r in range(world) if views[r].numel() > 0]
+    for w in work:
+        w.wait()
+
+
+def allgatherv_csr(indptr, indices, values, group=None, packed: "bool | None" = None, plan: "GatherPlan | None" = None,
+                   return_plan: bool = False):
+    """All-gather row-sharded CSR arrays (torch tensors on the collective's device).
+
+    Every rank passes its shard (indptr int64[m_r+1] starting at 0, indices int32[nnz_r],
+    values float64[nnz_r]) and receives the row-concatenated matrix (indptr, indices, values).
+    NCCL has no all-gather-v.  The shard sizes come from `plan` (``plan_allgatherv``; built here — one small
+    all-gather and one host read — when absent or stale); then
+
+    * packed (default while the padded exchange stays below 32 MiB, i.e. latency bound): row pointers, values and
+      indices of a shard travel as ONE byte record padded to the largest shard — a single all-gather — and are
+      sliced out of the received records (24 small broadcasts cost 3.4 ms on 8 GPUs for 3 MB shards);
+    * otherwise every shard goes straight into its slice of the preallocated result (no padding, no copies).
+
+    Row pointers are shifted by the shard's entry offset BEFORE they travel, so the gathered pointer array needs
+    no scan.  With a valid plan nothing here synchronises with the host."""
+    import torch
+    import torch.distributed as dist
+
+    dev = indptr.device
+    m, n = indptr.numel() - 1, indices.numel()
+    if plan is None or not plan.matches(m, n):
+        plan = plan_allgatherv(m, n, dev, group)
+    world, rank = plan.world, plan.rank
+    max_rows, max_nnz = int(plan.rows.max()), int(plan.nnzs.max())
     if packed is None:  # small exchanges only (latency bound); large shards go straight into place, unpadded
         packed = 12 * max_nnz * world <= (32 << 20)
+    shifted = indptr[1:] + int(plan.nnz_off[rank])  # global row ends of this shard
+    g_indptr = torch.empty(plan.n_rows + 1, dtype=torch.int64, device=dev)
+    g_indptr[:1] = 0
     if packed:
-        def pad16(n):
-            return (n + 15) // 16 * 16
+        def pad16(k):
+            return (k + 15) // 16 * 16
 
         o_val = pad16(8 * max_rows)
         o_idx = o_val + pad16(8 * max_nnz)
         rec = o_idx + pad16(4 * max_nnz)
         send = torch.zeros(rec, dtype=torch.uint8, device=dev)
-        m, n = int(all_sizes[rank, 0]), int(all_sizes[rank, 1])
-        send[: 8 * m].view(torch.int64).copy_(indptr[1:] - indptr[:-1])
+        send[: 8 * m].view(torch.int64).copy_(shifted)
         send[o_val:o_val + 8 * n].view(torch.float64).copy_(values)
         send[o_idx:o_idx + 4 * n].view(torch.int32).copy_(indices)
         recv = torch.empty(world * rec, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(recv, send, group=group)
         recv = recv.view(world, rec)
-        counts = torch.cat([recv[r, : 8 * int(all_sizes[r, 0])].view(torch.int64) for r in range(world)])
-        g_values = torch.cat([recv[r, o_val:o_val + 8 * int(all_sizes[r, 1])].view(torch.float64) for r in range(world)])
-        g_indices = torch.cat([recv[r, o_idx:o_idx + 4 * int(all_sizes[r, 1])].view(torch.int32) for r in range(world)])
+        g_indptr[1:] = torch.cat([recv[r, : 8 * int(plan.rows[r])].view(torch.int64) for r in range(world)])
+        g_values = torch.cat([recv[r, o_val:o_val + 8 * int(plan.nnzs[r])].view(torch.float64) for r in range(world)])
+        g_indices = torch.cat([recv[r, o_idx:o_idx + 4 * int(plan.nnzs[r])].view(torch.int32) for r in range(world)])
     else:
-        counts = torch.empty(int(row_off[-1]), dtype=torch.int64, device=dev)
-        g_indices = torch.empty(int(nnz_off[-1]), dtype=torch.int32, device=dev)
-        g_values = torch.empty(int(nnz_off[-1]), dtype=torch.float64, device=dev)
-        counts[row_off[rank]:row_off[rank + 1]] = indptr[1:] - indptr[:-1]
-        g_indices[nnz_off[rank]:nnz_off[rank + 1]] = indices
-        g_values[nnz_off[rank]:nnz_off[rank + 1]] = values
-        ranks = dist.get_process_group_ranks(group) if group is not None else list(range(world))
-        work = []
-        for r in range(world):
-            src = ranks[r]
-            for buf, off in ((counts, row_off), (g_indices, nnz_off), (g_values, nnz_off)):
-                if off[r + 1] > off[r]:
-                    work.append(dist.broadcast(buf[off[r]:off[r + 1]], src=src, group=group, async_op=True))
-        for w in work:
-            w.wait()
-    g_indptr = torch.zeros(counts.numel() + 1, dtype=torch.int64, device=dev)
-    torch.cumsum(counts, 0, out=g_indptr[1:])
+        g_indices = torch.empty(plan.nnz, dtype=torch.int32, device=dev)
+        g_values = torch.empty(plan.nnz, dtype=torch.float64, device=dev)
+        _gatherv_into(g_indptr[1:], plan.row_off, shifted, plan, group)
+        _gatherv_into(g_indices, plan.nnz_off, indices, plan, group)
+        _gatherv_into(g_values, plan.nnz_off, values, plan, group)
+    if return_plan:
+        return g_indptr, g_indices, g_values, plan
     return g_indptr, g_indices, g_values
 
 
 def allgatherv_vector(v, group=None):
-    """All-gather of per-rank float64 vectors of different lengths (same broadcast scheme)."""
+    """All-gather of per-rank float64 vectors of different lengths."""
     import torch
-    import torch.distributed as dist
 
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    n = torch.tensor([v.numel()], dtype=torch.int64, device=v.device)
-    all_n = torch.empty(world, dtype=torch.int64, device=v.device)
-    dist.all_gather_into_tensor(all_n, n, group=group)
-    off = np.concatenate([[0], np.cumsum(all_n.cpu().numpy())])
-    out = torch.empty(int(off[-1]), dtype=v.dtype, device=v.device)
-    out[off[rank]:off[rank + 1]] = v
-    ranks = dist.get_process_group_ranks(group) if group is not None else list(range(world))
-    work = [dist.broadcast(out[off[r]:off[r + 1]], src=ranks[r], group=group, async_op=True) for r in range(world)
-            if off[r + 1] > off[r]]
-    for w in work:
-        w.wait()
+    plan = plan_allgatherv(v.numel(), v.numel(), v.device, group)
+    out = torch.empty(plan.n_rows, dtype=v.dtype, device=v.device)
+    _gatherv_into(out, plan.row_off, v, plan, group)
     return out
 
 
 def balanced_dof_windows(indices_t, n_cols: int, world: int):
     """Contiguous ranges of 3D dofs (columns of the gathered Π) with equal numbers of Π entries — a
     proxy for equal SpGEMM work (intermediate products of row j of Πᵀ ~ entries in column j of Π).
-    Every rank computes the same boundaries from the same gathered matrix."""
+    Every rank computes the same boundaries from the same gathered matrix.  (One host read: done once per Γ and
+    kept in the ``ProductPlan``.)"""
     import torch
 
     if world == 1:
@@ -138,65 +185,150 @@ def quadrature_mass_diagonal(gamma, K) -> np.ndarray:
     return diag
 
 
-def product_pt_m_p(pi_local, gamma, K, world: int, rank: int, steps: int = 5, flush=None) -> dict:
-    """Times the block product C = Πᵀ (M_Γ Π) for the row-sharded Π of this rank.
+def p1_quadrature_coupling(gamma, Q, K):
+    """The coupling block M (Q x K) of the 3D-1D problem, ``inner(z, q) * dx`` with z in the quadrature space K and
+    q in P1(Γ) (demos/coupled_poisson.py:92-93): M[q, w] = φ_q(x_w) · weight_w · |segment|, at most 2·nip entries per
+    row.  Returns a scipy CSR matrix (what dolfinx would assemble)."""
+    import scipy.sparse as sp
 
-    N = 1: transpose + row scaling + SpGEMM on the local matrix.  N > 1: all-gather of Π's and
-    M_ΓΠ's shards (NCCL), then every rank computes the rows of C of its contiguous range of 3D
-    dofs.  Returns timings (max over ranks) and roofline numbers for the SpGEMM."""
+    from .quadrature import gauss_jacobi_interval
+
+    x, dm = gamma.geometry.x, gamma.geometry.dofmap
+    length = np.linalg.norm(x[dm[:, 1]] - x[dm[:, 0]], axis=1)
+    xref, w = gauss_jacobi_interval(K.element.degree)
+    xref, w = np.asarray(xref).reshape(-1), np.asarray(w).reshape(-1)
+    nip = xref.shape[0]
+    qd = np.asarray(Q.dofmap.list)
+    kd = np.asarray(K.dofmap.list)
+    n_cells = dm.shape[0]
+    phi = np.stack([1.0 - xref, xref], axis=0)  # [2, nip]
+    rows = np.repeat(qd[:, :, None], nip, axis=2).reshape(-1)  # (cell, a, j)
+    cols = np.repeat(kd[:, None, :], 2, axis=1).reshape(-1)
+    vals = (phi[None, :, :] * (w[None, None, :] * length[:, None, None])).reshape(-1)
+    M = sp.csr_matrix((vals, (rows, cols)), shape=(Q.num_dofs, K.num_dofs))
+    M.sum_duplicates()
+    assert M.nnz == 2 * nip * n_cells
+    return M
+
+
+@dataclass
+class ProductPlan:
+    """What the sharded products of one Γ reuse between calls: shard sizes and the 3D-dof windows."""
+
+    gather: "GatherPlan | None"
+    windows: list
+    setup_ms: float = 0.0
+
+
+class ShardedProducts:
+    """The block products of the coupled 3D-1D problem for a row-sharded Π (matrix_assembler.py:201-258):
+
+        C  = Πᵀ (M_Γ Π)   rows sharded by 3D dof (contiguous windows balanced by Π's column counts)
+        MP = M Π          rows sharded by P1(Γ) dof (optional)
+
+    `diag_dev`: the diagonal of the quadrature-element mass M_Γ for ALL Γ rows (float64 CUDA tensor; every rank
+    assembles it from the replicated Γ mesh).  `m_dev`: the coupling block M as a DeviceCSR (replicated), or None.
+    N = 1: no collective.  N > 1: one all-gather-v of Π's shards, then every rank transposes ITS window of the
+    gathered Π and multiplies; M_Γ is applied while B's rows are read (``fxii_spgemm_scaled``), M_ΓΠ is never
+    materialised."""
+
+    def __init__(self, n_dofs: int, diag_dev, m_dev=None, world: int = 1, rank: int = 0, group=None):
+        self.n_dofs, self.diag, self.m = int(n_dofs), diag_dev, m_dev
+        self.world, self.rank, self.group = world, rank, group
+        self.plan: "ProductPlan | None" = None
+
+    def _make_plan(self, pi_local):
+        import torch
+
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        if self.world == 1:
+            plan = ProductPlan(None, [(0, self.n_dofs)])
+        else:
+            ptr, idx, val = pi_local.device_tensors()
+            g_ptr, g_idx, g_val, gplan = allgatherv_csr(ptr, idx, val, group=self.group, return_plan=True)
+            plan = ProductPlan(gplan, balanced_dof_windows(g_idx, self.n_dofs, self.world))
+            del g_ptr, g_idx, g_val
+        t1.record()
+        torch.cuda.synchronize()
+        plan.setup_ms = t0.elapsed_time(t1)
+        return plan
+
+    def __call__(self, pi_local, events=None):
+        """Returns (C_window, MP_window or None, ip_c, nnz_a, ip_mp).  `events`: list receiving CUDA events after
+        [start, gather, transpose, spgemm C, spgemm MP]."""
+        import torch
+
+        from .sparse import DeviceCSR
+
+        def mark():
+            if events is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                events.append(e)
+
+        if self.plan is None or (self.plan.gather is not None and not self.plan.gather.matches(pi_local.shape[0], pi_local.nnz)):
+            self.plan = self._make_plan(pi_local)
+        mark()
+        if self.world > 1:
+            ptr, idx, val = pi_local.device_tensors()
+            g_ptr, g_idx, g_val = allgatherv_csr(ptr, idx, val, group=self.group, plan=self.plan.gather)
+            gp = DeviceCSR.wrap_device_arrays(g_ptr, g_idx, g_val, (self.plan.gather.n_rows, self.n_dofs))
+        else:
+            gp = pi_local
+        assert gp.shape[0] == self.diag.numel(), "M_Γ diagonal must cover all Γ rows"
+        r0, r1 = self.plan.windows[self.rank]
+        mark()
+        pt = gp.transpose(r0, r1)  # rows r0..r1 of Πᵀ: this rank's 3D dofs
+        mark()
+        c, ip = pt.matmult(gp, return_ip=True, row_scale=self.diag)
+        mark()
+        mp, ip_mp = None, 0
+        if self.m is not None:
+            q0, q1 = shard_range(self.m.shape[0], self.world, self.rank)
+            mp, ip_mp = self.m.matmult(gp, q0, q1, return_ip=True)
+        mark()
+        return c, mp, ip, pt.nnz, ip_mp
+
+
+def product_pt_m_p(pi_local, gamma, K, world: int, rank: int, steps: int = 5, flush=None, m_dev=None) -> dict:
+    """Times the block products C = Πᵀ (M_Γ Π) (and MΠ when `m_dev` is given) for the row-sharded Π of this rank.
+    Returns timings (max over ranks) and the SpGEMM roofline numbers."""
     import torch
     import torch.distributed as dist
 
-    from .sparse import DeviceCSR
-
-    diag = quadrature_mass_diagonal(gamma, K)
-    diag_dev = torch.from_numpy(diag).to("cuda")  # resident like every other input of the timed product
-    n_dofs = pi_local.shape[1]
+    diag_dev = torch.from_numpy(quadrature_mass_diagonal(gamma, K)).to("cuda")  # resident like every other input
+    prod = ShardedProducts(pi_local.shape[1], diag_dev, m_dev, world, rank)
+    names = ("allgather_ms", "transpose_ms", "spgemm_ms", "spgemm_mp_ms")
 
     def once():
-        import torch as _t
-
-        e = [_t.cuda.Event(enable_timing=True) for _ in range(5)]
+        ev = []
         if world > 1:
             dist.barrier()  # start together: otherwise the first collective absorbs the ranks' skew
-        e[0].record()
-        if world > 1:
-            # the one exchange of the path: Π's row shards (and the mass diagonal) to every rank
-            g_ptr, g_idx, g_val = allgatherv_csr(*pi_local.device_tensors())
-            gp = DeviceCSR.from_device_arrays(g_ptr, g_idx, g_val, (pi_local.shape[0] * world, n_dofs))
-            gdiag = allgatherv_vector(diag_dev)  # stays on the device: scale_rows takes it in place
-            r0, r1 = balanced_dof_windows(g_idx, n_dofs, world)[rank]
-            del g_ptr, g_idx, g_val
-        else:
-            gp, gdiag = pi_local, diag_dev
-            r0, r1 = 0, n_dofs
-        e[1].record()
-        gmp = gp.copy().scale_rows(gdiag)  # M_Γ Π (diagonal quadrature mass)
-        e[2].record()
-        pt = gp.transpose(r0, r1)  # only the rows of Πᵀ this rank owns (3D dofs r0..r1)
-        e[3].record()
-        c, ip = pt.matmult(gmp, return_ip=True)
-        e[4].record()
-        _t.cuda.synchronize()
-        t = dict(allgather_ms=e[0].elapsed_time(e[1]), scale_ms=e[1].elapsed_time(e[2]), transpose_ms=e[2].elapsed_time(e[3]),
-                 spgemm_ms=e[3].elapsed_time(e[4]), total_ms=e[0].elapsed_time(e[4]))
-        return t, c, ip, pt.nnz, (r1 - r0)
+        c, mp, ip, nnz_a, _ = prod(pi_local, events=ev)
+        torch.cuda.synchronize()
+        t = {n: ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(names)}
+        t["total_ms"] = ev[0].elapsed_time(ev[-1])
+        return t, c, mp, ip, nnz_a
 
     once()
     acc = None
     for _ in range(steps):
         if flush is not None:
             flush.zero_()
-        t, c, ip, nnz_a, m = once()
+        t, c, mp, ip, nnz_a = once()
         acc = t if acc is None else {k: acc[k] + t[k] for k in t}
     avg = {k: v / steps for k, v in acc.items()}
     tt = torch.tensor([avg[k] for k in sorted(avg)], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     avg = {k: float(v) for k, v in zip(sorted(avg), tt.tolist())}
+    m = prod.plan.windows[rank][1] - prod.plan.windows[rank][0]
     alg_bytes = 12 * nnz_a + 12 * ip + 12 * c.nnz + 16 * (m + 1)
-    avg.update(ip=int(ip), nnz_c_local=int(c.nnz), nnz_a=int(nnz_a),
+    avg.update(ip=int(ip), nnz_c_local=int(c.nnz), nnz_a=int(nnz_a), nnz_mp_local=int(mp.nnz) if mp is not None else 0,
+               plan_setup_ms=prod.plan.setup_ms,
                spgemm_alg_GBps=alg_bytes / (avg["spgemm_ms"] * 1e-3) / 1e9 if avg["spgemm_ms"] > 0 else 0.0,
                spgemm_s=avg["spgemm_ms"] * 1e-3, pit_m_pi_s=avg["total_ms"] * 1e-3,
-               association="Pi^T (M Pi), rows sharded by 3D dof (windows balanced by Pi column counts)")
+               association="Pi^T (M Pi), rows sharded by 3D dof (windows balanced by Pi column counts); M_Gamma fused")
     return avg

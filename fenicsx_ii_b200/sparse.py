@@ -38,9 +38,43 @@ class DeviceCSR:
 
     @classmethod
     def from_scipy(cls, mat) -> "DeviceCSR":
+        """Upload a scipy matrix.  Duplicate entries are summed and columns sorted first (the products assume
+        PETSc's assembled-AIJ form: unique ascending columns); explicit zeros are kept."""
         mat = mat.tocsr()
-        mat.sort_indices()
+        if not mat.has_canonical_format:
+            mat = mat.copy()
+            mat.sum_duplicates()
         return cls.from_host(mat.indptr, mat.indices, mat.data, mat.shape)
+
+    @classmethod
+    def wrap_device_arrays(cls, indptr_t, indices_t, values_t, shape) -> "DeviceCSR":
+        """A matrix over torch CUDA tensors WITHOUT copying them (the gathered row shards of the multi-GPU
+        product); the tensors are kept alive by the returned object."""
+        import torch
+
+        assert indptr_t.dtype == torch.int64 and indices_t.dtype == torch.int32 and values_t.dtype == torch.float64
+        assert indptr_t.is_contiguous() and indices_t.is_contiguous() and values_t.is_contiguous()
+        assert indptr_t.numel() == shape[0] + 1 and indices_t.numel() == values_t.numel()
+        out = C.c_void_p()
+        _lib.check(_lib.load().fxii_csr_wrap_device(shape[0], shape[1], int(indices_t.numel()), indptr_t.data_ptr(),
+                                                    indices_t.data_ptr(), values_t.data_ptr(), C.byref(out)))
+        m = cls(out.value)
+        m._keepalive = (indptr_t, indices_t, values_t)
+        return m
+
+    def row_slice(self, r0: int, r1: int) -> "DeviceCSR":
+        """Rows [r0, r1) as a matrix of their own, sharing this matrix's index and value arrays (only the row
+        pointers are copied).  One small host read (the entry offsets of the two boundary rows)."""
+        ptr, idx, val = self.device_tensors()
+        e0, e1 = ptr[[r0, r1]].tolist()
+        sub = DeviceCSR.wrap_device_arrays((ptr[r0:r1 + 1] - e0).contiguous(), idx[e0:e1], val[e0:e1], (r1 - r0, self.shape[1]))
+        sub._keepalive = sub._keepalive + (self,)
+        return sub
+
+    def validate(self) -> "DeviceCSR":
+        """Raise unless indptr is monotone, columns are in range and strictly ascending in every row."""
+        _lib.check(_lib.load().fxii_csr_validate(self._h, _lib.current_stream()))
+        return self
 
     @classmethod
     def from_device_arrays(cls, indptr_t, indices_t, values_t, shape) -> "DeviceCSR":
@@ -111,11 +145,22 @@ class DeviceCSR:
             _lib.check(_lib.load().fxii_csr_transpose_window(self._h, col_begin, col_end, _lib.current_stream(), C.byref(out)))
         return DeviceCSR(out.value)
 
-    def matmult(self, other: "DeviceCSR", row_begin: int = 0, row_end: int = -1, return_ip: bool = False):
+    def matmult(self, other: "DeviceCSR", row_begin: int = 0, row_end: int = -1, return_ip: bool = False, row_scale=None):
+        """``self[row_begin:row_end] @ other`` (Mat.matMult).  ``row_scale``: float64 torch CUDA tensor d of
+        ``other.shape[0]`` entries — computes ``self @ diag(d) @ other`` without materialising ``diag(d) @ other``
+        (the diagonal quadrature mass of Πᵀ(M_ΓΠ))."""
         out = C.c_void_p()
         ip = C.c_int64()
-        _lib.check(_lib.load().fxii_spgemm(self._h, other._h, row_begin, row_end, _lib.current_stream(), C.byref(out),
-                                           C.byref(ip)))
+        if row_scale is None:
+            _lib.check(_lib.load().fxii_spgemm(self._h, other._h, row_begin, row_end, _lib.current_stream(), C.byref(out),
+                                               C.byref(ip)))
+        else:
+            import torch
+
+            assert row_scale.is_cuda and row_scale.dtype == torch.float64 and row_scale.is_contiguous()
+            assert row_scale.numel() == other.shape[0]
+            _lib.check(_lib.load().fxii_spgemm_scaled(self._h, other._h, C.c_void_p(row_scale.data_ptr()), row_begin, row_end,
+                                                      _lib.current_stream(), C.byref(out), C.byref(ip)))
         c = DeviceCSR(out.value)
         return (c, ip.value) if return_ip else c
 

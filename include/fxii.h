@@ -20,7 +20,8 @@
  *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
  *    stream-ordered; functions that must return a size to the host synchronise the stream.
  *  - CSR: indptr int64[n_rows+1], indices int32[nnz] ascending and unique per row,
- *    values double[nnz]; explicit zeros are preserved.
+ *    values double[nnz]; explicit zeros are preserved.  Matrices the caller uploads must already have that
+ *    form (fxii_csr_validate checks it): the products do not detect duplicate or unsorted columns.
  *  - the library acts on the CURRENT CUDA device of the calling thread.
  */
 #ifndef FXII_H
@@ -171,6 +172,14 @@ int fxii_csr_upload(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* 
 int fxii_csr_from_device(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* indptr_dev,
                          const int32_t* indices_dev, const double* values_dev, void* stream,
                          fxii_csr** out);
+/* a matrix over DEVICE arrays the caller keeps alive and owns (no copy; *_destroy frees only the handle): the
+ * gathered row shards of Π after the NCCL exchange */
+int fxii_csr_wrap_device(int64_t n_rows, int64_t n_cols, int64_t nnz, int64_t* indptr_dev,
+                         int32_t* indices_dev, double* values_dev, fxii_csr** out);
+/* Checks what the products assume of a caller-assembled matrix (PETSc's assembled AIJ guarantees it): indptr
+ * monotone from 0 to nnz, 0 <= column < n_cols, columns strictly ascending — hence unique — in every row.
+ * FXII_E_INVALID otherwise.  Synchronises. */
+int fxii_csr_validate(const fxii_csr* a, void* stream);
 int fxii_csr_info(const fxii_csr* a, int64_t* n_rows, int64_t* n_cols, int64_t* nnz);
 int fxii_csr_device_ptrs(const fxii_csr* a, void** indptr_dev, void** indices_dev, void** values_dev);
 int fxii_csr_download(const fxii_csr* a, int64_t* indptr, int32_t* indices, double* values,
@@ -188,6 +197,11 @@ int fxii_csr_transpose_window(const fxii_csr* a, int64_t col_begin, int64_t col_
  * pass 0, -1 for all rows. */
 int fxii_spgemm(const fxii_csr* a, const fxii_csr* b, int64_t row_begin, int64_t row_end,
                 void* stream, fxii_csr** out, int64_t* ip);
+/* A · diag(d) · B with d = b_row_scale_dev (DEVICE, double[b.n_rows]): the diagonal quadrature-element mass M_Γ of
+ * Πᵀ (M_Γ Π) (demos/coupled_poisson.py:164-167, matrix_assembler.py:225-258) applied while B's rows are read,
+ * without materialising M_Γ Π.  Every term is a_ik * (d_k * b_kj): the rounding of the unfused product. */
+int fxii_spgemm_scaled(const fxii_csr* a, const fxii_csr* b, const double* b_row_scale_dev,
+                       int64_t row_begin, int64_t row_end, void* stream, fxii_csr** out, int64_t* ip);
 /* blocked spaces (K.bs == V.bs == bs): every scalar entry becomes a bs x bs block with the value on its
  * diagonal and explicit zeros elsewhere (interpolation.py:214-248 + utils.unroll_dofmap, utils.py:36-47) */
 int fxii_csr_expand_blocks(const fxii_csr* a, int32_t bs, void* stream, fxii_csr** out);

@@ -33,7 +33,8 @@ def main():
     ap.add_argument("--config", type=int, default=2)
     args = ap.parse_args()
     cfg = bench.CONFIGS[args.config]
-    mesh, V, gamma, K, op, seg_r = bench.build_workload(cfg, 0, pinned=True)
+    wl = bench.build_workload(cfg, pinned=True)
+    mesh, V, gamma, K, op, seg_r = (wl[k] for k in ("mesh", "V", "gamma", "K", "op", "seg_r"))
     ds = device_space(V)
     rows = device_rows(K, op)
     csr, st = rows.assemble(ds)

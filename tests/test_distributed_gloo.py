@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from fenicsx_ii_b200.distributed import allgatherv_csr, shard_range
+from fenicsx_ii_b200.distributed import allgatherv_csr, plan_allgatherv, shard_range
 
 
 def _free_port():
@@ -26,17 +26,25 @@ def _worker(rank, world, port, shards, out_dir, packed):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         m = shards[rank]
-        ip, ij, iv = allgatherv_csr(torch.from_numpy(m.indptr.astype(np.int64)), torch.from_numpy(m.indices.astype(np.int32)),
-                                    torch.from_numpy(m.data.astype(np.float64)), packed=packed)
+        arrays = (torch.from_numpy(m.indptr.astype(np.int64)), torch.from_numpy(m.indices.astype(np.int32)),
+                  torch.from_numpy(m.data.astype(np.float64)))
+        ip, ij, iv, plan = allgatherv_csr(*arrays, packed=packed, return_plan=True)
+        # the cached plan (no size exchange, no host read) gives the same matrix; a stale plan is rebuilt
+        ip2, ij2, iv2 = allgatherv_csr(*arrays, packed=packed, plan=plan)
+        assert torch.equal(ip, ip2) and torch.equal(ij, ij2) and torch.equal(iv, iv2)
+        stale = plan_allgatherv(m.shape[0] + 1, m.nnz, arrays[0].device)
+        ip3, _, _ = allgatherv_csr(*arrays, packed=packed, plan=stale)
+        assert torch.equal(ip, ip3)
+        assert plan.n_rows == sum(s.shape[0] for s in shards) and plan.nnz == sum(s.nnz for s in shards)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), indptr=ip.numpy(), indices=ij.numpy(), data=iv.numpy())
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("packed", [None, True, False])  # automatic choice, one padded all-gather, per-shard broadcasts
-@pytest.mark.parametrize("rows", [(7, 12), (5, 0), (1, 1)])
+@pytest.mark.parametrize("rows", [(7, 12), (5, 0), (1, 1), (4, 3, 3)])  # the last: 10 rows on 3 ranks (uneven shards)
 def test_allgatherv_csr_gloo(tmp_path, rows, packed):
-    world = 2
+    world = len(rows)
     rng = np.random.default_rng(5)
     shards = []
     for r, m in enumerate(rows):

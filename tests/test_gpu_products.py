@@ -61,6 +61,124 @@ def test_spgemm_random(cuda, m, k, n, density, heavy):
         check(Cw, refw[:3])
 
 
+def sparse_rows(m, n, mean_len, seed, heavy_rows=0, heavy_len=0):
+    """CSR with about `mean_len` entries per row (Π-like short rows) and a few rows of `heavy_len` entries."""
+    rng = np.random.default_rng(seed)
+    lens = np.minimum(rng.poisson(mean_len, size=m), n)
+    if heavy_rows:
+        lens[rng.choice(m, size=min(heavy_rows, m), replace=False)] = min(heavy_len, n)
+    indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    indices = np.concatenate([np.sort(rng.choice(n, size=k, replace=False)) for k in lens] + [np.zeros(0, dtype=np.int64)])
+    data = rng.normal(size=indices.shape[0])
+    return sp.csr_matrix((data, indices.astype(np.int32), indptr), shape=(m, n))
+
+
+# (m, k, n, mean |A_i|, mean |B_k|, heavy rows of A, their length, heavy rows of B, their length)
+LEAN_CASES = [
+    (400, 300, 4000, 6, 2, 0, 0, 0, 0),          # G = 4
+    (400, 300, 4000, 10, 7, 4, 200, 0, 0),       # G = 8, rows of a few thousand products
+    (500, 800, 6000, 8, 14, 6, 400, 5, 300),     # G = 16 (the Π shape), rows of B longer than G
+    (300, 600, 9000, 12, 20, 4, 500, 3, 2000),   # G = 32, numeric rows beyond the 2048-slot bin (block kernels)
+    (60, 3000, 20000, 5, 20, 3, 1500, 0, 0),     # symbolic escalation: 1024 -> 8192 -> 32768-slot tables
+    (12, 3000, 60000, 5, 20, 2, 3000, 0, 0),     # ... -> global-memory tables (> 16384 distinct columns)
+    (700, 50, 64, 20, 12, 0, 0, 0, 0),           # heavy compression: every row of C is (nearly) dense in 64 columns
+    (33, 1, 5, 1, 3, 0, 0, 0, 0),                # single row of B
+]
+
+
+@pytest.mark.parametrize("case", LEAN_CASES)
+def test_spgemm_short_rows_of_b(cuda, case):
+    """The lean warp kernel (rows of B of at most 32 entries on average): every sub-group width, the register sort of
+    every bin, rows of B longer than a sub-group, and the symbolic escalation chain — pattern bit-exact, values 1e-12,
+    fused row scaling bitwise equal to scaling first."""
+    import torch
+
+    m, k, n, la, lb, ha, hla, hb, hlb = case
+    A = sparse_rows(m, k, la, 11, ha, hla)
+    B = sparse_rows(k, n, lb, 12, hb, hlb)
+    a, b = as_host(A), as_host(B)
+    dA = DeviceCSR.from_host(*a, A.shape).validate()
+    dB = DeviceCSR.from_host(*b, B.shape).validate()
+    C, ip = dA.matmult(dB, return_ip=True)
+    ref = orc.spgemm(*a, *b, n)
+    assert ip == ref[3]
+    check(C, ref[:3])
+    # A · diag(d) · B: fused == scale_rows first (bitwise), == oracle on the scaled matrix
+    d = np.random.default_rng(3).uniform(0.5, 2.0, size=k)
+    Cs = dA.matmult(dB, row_scale=torch.from_numpy(d).to("cuda"))
+    Cu = dA.matmult(dB.copy().scale_rows(d))
+    np.testing.assert_array_equal(Cs.to_host()[1], Cu.to_host()[1])
+    assert Cs.to_host()[2].tobytes() == Cu.to_host()[2].tobytes()
+    bs = (b[0], b[1], b[2] * np.repeat(d, np.diff(b[0])))
+    check(Cs, orc.spgemm(*a, *bs, n)[:3])
+    if m >= 4:
+        r0, r1 = m // 4, 3 * m // 4
+        refw = orc.spgemm(*as_host(A[r0:r1]), *b, n)
+        check(dA.matmult(dB, r0, r1), refw[:3])
+
+
+def test_wrap_device_arrays_and_validate(cuda):
+    import torch
+
+    from fenicsx_ii_b200._lib import FxiiError
+
+    A = sparse_rows(50, 40, 5, 1)
+    a = as_host(A)
+    t = [torch.from_numpy(x).to("cuda") for x in a]
+    W = DeviceCSR.wrap_device_arrays(*t, A.shape).validate()
+    for x, y in zip(W.to_host(), a):
+        np.testing.assert_array_equal(x, y)
+    check(W.transpose(), orc.csr_transpose(*a, 40), rtol=0)
+    S = W.row_slice(10, 30)
+    for x, y in zip(S.to_host(), as_host(A[10:30])):
+        np.testing.assert_array_equal(x, y)
+    del W, S  # handles go, the torch tensors stay valid
+    assert int(t[1].sum().item()) == int(a[1].sum())
+    # duplicate / unsorted / out-of-range columns are rejected
+    bad = a[1].copy()
+    r = int(np.argmax(np.diff(a[0]) >= 2))
+    bad[a[0][r] + 1] = bad[a[0][r]]
+    with pytest.raises(FxiiError):
+        DeviceCSR.from_host(a[0], bad, a[2], A.shape).validate()
+    bad = a[1].copy()
+    bad[0] = 40
+    with pytest.raises(FxiiError):
+        DeviceCSR.from_host(a[0], bad, a[2], A.shape).validate()
+    # from_scipy sums duplicates instead of passing them on
+    D = sp.csr_matrix((np.array([1.0, 2.0, 3.0]), np.array([1, 1, 0]), np.array([0, 3])), shape=(1, 3))
+    dd = DeviceCSR.from_scipy(D).validate().to_host()
+    np.testing.assert_array_equal(dd[1], [0, 1])
+    np.testing.assert_array_equal(dd[2], [3.0, 3.0])
+
+
+def test_sharded_products_single_rank(cuda):
+    """ShardedProducts on one rank: C = Πᵀ(M_ΓΠ) with the mass diagonal fused and M Π — against the oracle / scipy."""
+    import torch
+
+    from fenicsx_ii_b200.distributed import ShardedProducts, p1_quadrature_coupling
+
+    mesh = sy.kuhn_box(8, 8, 8)
+    V = functionspace(mesh, ("Lagrange", 1))
+    gamma = sy.polyline_network(150, 1 / 8, n_lines=4, lo=0.2, hi=0.8)
+    W = functionspace(gamma, ("Quadrature", 10))
+    Q = functionspace(gamma, ("Lagrange", 1))
+    P, _, _ = create_interpolation_matrix(V, W, Circle(gamma, 0.06, degree=9))
+    p = (P.indptr, P.indices, P.data)
+    diag = quadrature_mass_diagonal(gamma, W)
+    M = p1_quadrature_coupling(gamma, Q, W)
+    np.testing.assert_allclose(np.asarray(M.sum(axis=0)).reshape(-1), diag, rtol=1e-14)  # P1 is a partition of unity
+    prod = ShardedProducts(V.num_dofs, torch.from_numpy(diag).to("cuda"), DeviceCSR.from_scipy(M))
+    c, mp, ip, nnz_a, ip_mp = prod(P.device)
+    pt = orc.csr_transpose(*p, V.num_dofs)
+    mpi = (p[0], p[1], p[2] * np.repeat(diag, np.diff(p[0])))
+    ref = orc.spgemm(*pt, *mpi, V.num_dofs)
+    assert ip == ref[3] and nnz_a == P.device.nnz
+    check(c, ref[:3])
+    refm = orc.spgemm(*as_host(M), *p, V.num_dofs)
+    assert ip_mp == refm[3]
+    check(mp, refm[:3])
+
+
 def test_spgemm_keeps_cancellation_and_explicit_zeros(cuda):
     A = sp.csr_matrix(np.array([[1.0, -1.0, 0.0], [0.0, 0.0, 2.0]]))
     B = sp.csr_matrix((np.array([3.0, 3.0, 0.0]), np.array([0, 0, 1]), np.array([0, 1, 2, 3])), shape=(3, 2))
