@@ -5,11 +5,15 @@ outside the path (UFL rewriting, form assembly, solver) stays with the reference
 """
 
 from .assembly import (
+    apply_matrix_replacer,
+    apply_vector_replacer,
     assign_LG_map,
     average_coefficient,
+    average_coefficients,
     restrict_columns,
     restrict_rows,
     restrict_rows_and_columns,
+    restrict_vector,
 )
 from .interpolation import clear_interpolation_cache, create_interpolation_matrix
 from .quadrature import Quadrature
@@ -25,11 +29,15 @@ __all__ = [
     "PointwiseTrace",
     "Quadrature",
     "ReductionOperator",
+    "apply_matrix_replacer",
+    "apply_vector_replacer",
     "assign_LG_map",
     "average_coefficient",
+    "average_coefficients",
     "clear_interpolation_cache",
     "create_interpolation_matrix",
     "restrict_columns",
     "restrict_rows",
     "restrict_rows_and_columns",
+    "restrict_vector",
 ]

@@ -335,7 +335,8 @@ __device__ __forceinline__ void prefetch_l1(const void* ptr) { asm volatile("pre
 // cannot collide with any other cell of a mesh.
 __device__ LocateResult locate_point(const WideNode* __restrict__ nodes, const SceneGrid& grid,
                                      const double* __restrict__ cellgeo, const double* __restrict__ x,
-                                     const int4* __restrict__ cell_nodes, double padding, const double* p) {
+                                     const int4* __restrict__ cell_nodes, double padding, const double* p,
+                                     unsigned long long* __restrict__ stack_overflow) {
   const QPoint q = quantise_point(grid, p);
   // 1.001: cells within 0.05% of the threshold still take the exact path
   const double tau2 = fmax(kCollisionD2, padding * padding) * 1.001;
@@ -368,6 +369,7 @@ __device__ LocateResult locate_point(const WideNode* __restrict__ nodes, const S
       if (kids[k] >= 0) {
         if (next < 0) next = kids[k];
         else if (sp < kStack) stack[sp++] = kids[k];
+        else *stack_overflow = 1ULL;  // a dropped subtree could hide the owning cell: reported, never silent
       } else if (!st.done) {
         test_cell(cellgeo, x, cell_nodes, padding, tau2, ~kids[k], p, st);
       }
@@ -387,7 +389,8 @@ __device__ LocateResult locate_point(const WideNode* __restrict__ nodes, const S
 // than the per-thread walk on every BASELINE config (see packet_mode()).
 __device__ LocateResult locate_packet(const WideNode* __restrict__ nodes, const SceneGrid& grid,
                                       const double* __restrict__ cellgeo, const double* __restrict__ x,
-                                      const int4* __restrict__ cell_nodes, double padding, const double* p, bool active) {
+                                      const int4* __restrict__ cell_nodes, double padding, const double* p, bool active,
+                                      unsigned long long* __restrict__ stack_overflow) {
   const QPoint q = quantise_point(grid, p);
   const double tau2 = fmax(kCollisionD2, padding * padding) * 1.001;
   int stack[kStack];  // warp-uniform contents
@@ -407,6 +410,7 @@ __device__ LocateResult locate_packet(const WideNode* __restrict__ nodes, const 
       if (kids[k] >= 0) {
         if (next < 0) next = kids[k];
         else if (sp < kStack) stack[sp++] = kids[k];
+        else *stack_overflow = 1ULL;
       } else if (hit[k] && !st.done) {
         test_cell(cellgeo, x, cell_nodes, padding, tau2, ~kids[k], p, st);
       }
@@ -420,6 +424,7 @@ __device__ LocateResult locate_packet(const WideNode* __restrict__ nodes, const 
 
 struct PiCounters {
   unsigned long long not_found, ties, fallback;
+  unsigned long long stack_overflow;  // traversals that ran out of stack (a tree deeper than kStack allows): the build fails
 };
 
 // The 3D averaging point p = r*nq + l with its weight W and scale S
@@ -526,8 +531,8 @@ pi_locate_tabulate_kernel(const WideNode* __restrict__ nodes, const SceneGrid gr
     double p[3] = {0.0, 0.0, 0.0}, W = 1.0, S = 1.0;
     if (active) make_point(kind, frames + kFrame * r, s_tab, pts_in, w_in, s_in, r, l, pidx, p, W, S);
     LocateResult res{-1, 0, false};
-    if (packet == 1) res = locate_packet(nodes, grid, cellgeo, x, cell_nodes, padding, p, active);
-    else if (active) res = locate_point(nodes, grid, cellgeo, x, cell_nodes, padding, p);
+    if (packet == 1) res = locate_packet(nodes, grid, cellgeo, x, cell_nodes, padding, p, active, &counters->stack_overflow);
+    else if (active) res = locate_point(nodes, grid, cellgeo, x, cell_nodes, padding, p, &counters->stack_overflow);
     if (!active) continue;
     out_cell[pidx] = res.cell;
     out_ncoll[pidx] = (uint8_t)min(res.ncoll, 255);
@@ -1168,7 +1173,7 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
       // 12.2 -> 11.0 ms on the 1M-segment tree together with passing the point by value to the slow-path distance.
       // A batched walk that first collects candidate cells and tests them in a second loop measured 12.2 ms.)
       LocateResult res{-1, 0, false};
-      if (active) res = locate_point(nodes, grid, cellgeo, x, cell_nodes, padding, p);
+      if (active) res = locate_point(nodes, grid, cellgeo, x, cell_nodes, padding, p, &counters->stack_overflow);
       if (active) {
         out_cell[pidx] = res.cell;
         out_ncoll[pidx] = (uint8_t)min(res.ncoll, 255);
@@ -1354,6 +1359,7 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
       ca.result->counters.not_found = __ldcg(&counters->not_found);
       ca.result->counters.ties = __ldcg(&counters->ties);
       ca.result->counters.fallback = __ldcg(&counters->fallback);
+      ca.result->counters.stack_overflow = __ldcg(&counters->stack_overflow);
     }
     return;
   }
@@ -1441,6 +1447,7 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
     ca.result->counters.not_found = __ldcg(&counters->not_found);
     ca.result->counters.ties = __ldcg(&counters->ties);
     ca.result->counters.fallback = __ldcg(&counters->fallback);
+    ca.result->counters.stack_overflow = __ldcg(&counters->stack_overflow);
     ca.result->ns_rows = t_rows - t_begin;
     ca.result->ns_csr = global_timer_ns() - t_rows;
   }
@@ -2028,6 +2035,9 @@ void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr
     stats->ms_csr_fill = ms_fill;
     stats->fused = fused ? (rows->last_coop ? 3 : (rows->last_graph ? 2 : 1)) : 0;
   }
+  if (h.stack_overflow > 0)
+    throw Error(FXII_E_UNSUPPORTED, "the traversal stack (" + std::to_string(kStack) + " entries) overflowed: the LBVH of this mesh is too deep "
+                                    "(degenerate cell distribution); ownership would be unreliable, nothing is returned");
   if (h.not_found > 0)
     throw Error(FXII_E_NOT_FOUND, std::to_string(h.not_found) + " of " + std::to_string(Np) +
                                       " points lie in no cell of the 3D mesh (interpolation.py:78)");

@@ -297,6 +297,22 @@ def device_space(V, tol: float = 1.0e-8) -> DeviceSpace:
     return dspace
 
 
+def _uses_stock_quadrature(red_op) -> bool:
+    from . import restriction_operators as ro
+
+    if not hasattr(red_op, "device_descriptor"):
+        return False
+    t = type(red_op)
+    if isinstance(red_op, ro.PointwiseTrace):
+        return t.compute_quadrature is ro.PointwiseTrace.compute_quadrature and t.device_descriptor is ro.PointwiseTrace.device_descriptor
+    if isinstance(red_op, ro._RadialAverage):
+        stock = (ro.Circle, ro.Disk)
+        base = next((b for b in stock if isinstance(red_op, b)), None)
+        return base is not None and all(getattr(t, name) is getattr(base, name) for name in
+                                        ("compute_quadrature", "quadrature", "_quadrature_R", "_weight_multiplier", "device_descriptor"))
+    return False
+
+
 def device_rows(K, red_op, cells_K=None, args_only: bool = False):
     """interpolation.py:41-64: interpolation points of K, cells_K, the operator's quadrature.
     `args_only`: return the arguments of ``DeviceRows.from_gamma`` instead of a handle (None when the operator
@@ -333,7 +349,9 @@ def device_rows(K, red_op, cells_K=None, args_only: bool = False):
     def all_or(cells):
         return np.arange(n_cells, dtype=np.int32) if cells is None else cells
 
-    on_device = hasattr(red_op, "device_descriptor") and red_op._mesh is mesh_to and mesh_to.topology.dim == 1 \
+    # points are generated on the device only for the stock operators: a subclass that overrides the plugin contract
+    # (compute_quadrature / quadrature) is a generic operator and goes through compute_quadrature on the host
+    on_device = _uses_stock_quadrature(red_op) and red_op._mesh is mesh_to and mesh_to.topology.dim == 1 \
         and np.asarray(mesh_to.geometry.dofmap).shape[1] == 2
     if on_device:
         from .restriction_operators import get_physical_points

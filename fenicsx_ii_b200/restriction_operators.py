@@ -152,6 +152,9 @@ class _RadialAverage:
         assert normals.shape[1] == 3, "Normal vectors must be 3D"
         if x0.shape[0] == 0:
             return np.zeros((0, x0.shape[1])), np.zeros((0, self._w.shape[0])), np.zeros((0,))
+        if self._radius is None:
+            raise ValueError("this operator holds one radius per Γ cell: centres alone do not determine the radius; "
+                             "use compute_quadrature(cells, reference_points)")
         return self._quadrature_R(x0, normals, np.asarray(self._radius(x0.T), dtype=np.float64))
 
     def _quadrature_R(self, x0, normals, R):

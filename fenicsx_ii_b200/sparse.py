@@ -197,6 +197,25 @@ class DeviceCSR:
         _lib.check(_lib.load().fxii_csr_spmv_t(self._h, _lib.ptr(u), _lib.ptr(y), _lib.current_stream()))
         return y
 
+    def add_scaled(self, alpha: float, other: "DeviceCSR") -> "DeviceCSR":
+        """``self + alpha * other`` as a new matrix whose pattern is the UNION of both patterns, columns sorted
+        (PETSc ``MatAXPY`` with ``DIFFERENT_NONZERO_PATTERN``; explicit zeros survive).  Computed on the device as
+        ``[I  alpha I] @ [self; other]`` with the SpGEMM kernels, so every entry is ``1*a + alpha*b`` in that order."""
+        import torch
+
+        assert self.shape == other.shape
+        m = self.shape[0]
+        p0, i0, v0 = self.device_tensors()
+        p1, i1, v1 = other.device_tensors()
+        stacked = DeviceCSR.wrap_device_arrays(torch.cat([p0, p1[1:] + self.nnz]), torch.cat([i0, i1]), torch.cat([v0, v1]),
+                                               (2 * m, self.shape[1]))
+        dev = p0.device
+        rows = torch.arange(m, dtype=torch.int32, device=dev)
+        sel = DeviceCSR.wrap_device_arrays(torch.arange(m + 1, dtype=torch.int64, device=dev) * 2,
+                                           torch.stack([rows, rows + m], dim=1).reshape(-1).contiguous(),
+                                           torch.tensor([1.0, float(alpha)], dtype=torch.float64, device=dev).repeat(m), (m, 2 * m))
+        return sel.matmult(stacked)
+
     def copy(self) -> "DeviceCSR":
         a, b, c = self.device_tensors()
         return DeviceCSR.from_device_arrays(a, b, c, self.shape)
@@ -266,6 +285,15 @@ class MatrixCSR:
 
     def scatter_reverse(self):  # serial: nothing to accumulate
         return None
+
+    def axpy(self, alpha: float, other) -> "MatrixCSR":
+        """``self += alpha * other`` (what ``apply_matrix_replacer`` does with PETSc ``Mat.axpy`` to sum the parts of a
+        form, matrix_assembler.py:172-258), on the device; the pattern becomes the union of both."""
+        o = other.device if isinstance(other, MatrixCSR) else other
+        self._device = self.device.add_scaled(alpha, o)
+        self._host = None
+        self.rows = None
+        return self
 
     def to_petsc(self):
         """PETSc AIJ with the CSR handed over in one call (instead of per-entry setValuesLocal,

@@ -124,3 +124,74 @@ def test_spgemm_keeps_symbolic_zeros_and_transpose_order():
     np.testing.assert_allclose(T.toarray(), A.T.toarray())
     for r in range(20):
         assert (np.diff(tj[tp[r] : tp[r + 1]]) > 0).all()
+
+
+# ---- the products of the oracle pinned against an independent implementation (scipy) -----------------------
+def _random_csr(m, n, density, seed, zeros=0.1):
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(seed)
+    M = sp.random(m, n, density=density, random_state=seed, format="csr")
+    M.sort_indices()
+    M.data[rng.random(M.nnz) < zeros] = 0.0  # explicit zeros must survive every product
+    return M
+
+
+@pytest.mark.parametrize("m,k,n,da,db", [(40, 30, 50, 0.15, 0.1), (200, 150, 80, 0.03, 0.2), (5, 300, 7, 0.3, 0.3), (1, 1, 1, 1.0, 1.0)])
+def test_oracle_spgemm_and_transpose_against_scipy(m, k, n, da, db):
+    """``orc.spgemm`` / ``orc.csr_transpose`` restate PETSc's MatMatMult / MatTranspose; here they are checked against
+    scipy: the pattern is that of the product of the all-ones matrices (symbolic: cancellation and explicit zeros keep
+    their slots, which scipy's numeric product would drop), values are scipy's on that pattern, IP is the sum over A's
+    entries of B's row lengths, and the transpose is scipy's ``.T`` with sorted rows."""
+    import scipy.sparse as sp
+
+    A, B = _random_csr(m, k, da, 1), _random_csr(k, n, db, 2)
+    a = (A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data)
+    b = (B.indptr.astype(np.int64), B.indices.astype(np.int32), B.data)
+    ci, cj, cv, ip = orc.spgemm(*a, *b, n)
+    ones = lambda M: sp.csr_matrix((np.ones(M.nnz), M.indices, M.indptr), shape=M.shape)  # noqa: E731
+    pat = (ones(A) @ ones(B)).tocsr()
+    pat.sort_indices()
+    np.testing.assert_array_equal(ci, pat.indptr)
+    np.testing.assert_array_equal(cj, pat.indices)
+    assert ip == int(np.diff(B.indptr)[A.indices].sum()) == int(pat.data.sum())
+    dense = (A @ B).toarray()
+    rows = np.repeat(np.arange(m), np.diff(ci))
+    np.testing.assert_allclose(cv, dense[rows, cj], rtol=1e-13, atol=1e-15)
+    assert (np.diff(cj)[np.setdiff1d(np.arange(cj.size - 1), ci[1:-1] - 1)] > 0).all()  # strictly ascending inside rows
+    ti, tj, tv = orc.csr_transpose(*a, k)
+    T = A.T.tocsr()  # scipy keeps explicit zeros in a transpose
+    T.sort_indices()
+    np.testing.assert_array_equal(ti, T.indptr)
+    np.testing.assert_array_equal(tj, T.indices)
+    np.testing.assert_array_equal(tv, T.data)
+
+
+def test_oracle_products_on_a_reference_generated_pi():
+    """The same check on a Π that the reference's own interpolation.py produced (golden fixture): Πᵀ(MΠ) has the
+    pattern of the all-ones product, is symmetric, and (ΠᵀMΠ) 1 = Πᵀ m because Π's rows sum to one."""
+    import glob
+    import os
+
+    import scipy.sparse as sp
+
+    path = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "pi_circle*.npz")))[0]
+    z = np.load(path)
+    ip_, ij_, iv_ = z["indptr"].astype(np.int64), z["indices"].astype(np.int32), z["data"].astype(np.float64)
+    n_rows, n_cols = ip_.shape[0] - 1, int(ij_.max()) + 1
+    P = sp.csr_matrix((iv_, ij_, ip_), shape=(n_rows, n_cols))
+    mdiag = np.linspace(0.5, 1.5, n_rows)
+    ti, tj, tv = orc.csr_transpose(ip_, ij_, iv_, n_cols)
+    mp = (ip_, ij_, iv_ * np.repeat(mdiag, np.diff(ip_)))
+    ci, cj, cv, _ = orc.spgemm(ti, tj, tv, *mp, n_cols)
+    ones = sp.csr_matrix((np.ones(P.nnz), P.indices, P.indptr), shape=P.shape)
+    pat = (ones.T @ ones).tocsr()
+    pat.sort_indices()
+    np.testing.assert_array_equal(ci, pat.indptr)
+    np.testing.assert_array_equal(cj, pat.indices)
+    C = sp.csr_matrix((cv, cj, ci), shape=(n_cols, n_cols))
+    ref = (P.T @ sp.diags(mdiag) @ P).toarray()
+    np.testing.assert_allclose(C.toarray(), ref, rtol=1e-13, atol=1e-16)
+    np.testing.assert_allclose(C.toarray(), C.toarray().T, rtol=1e-13, atol=1e-16)
+    live = np.diff(ip_) > 0  # rows of cells outside cells_K are empty
+    np.testing.assert_allclose(C @ np.ones(n_cols), P.T @ (mdiag * live), rtol=1e-12, atol=1e-15)
