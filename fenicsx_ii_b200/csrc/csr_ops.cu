@@ -10,6 +10,7 @@
 // zeros stay), columns are sorted, and c_ij accumulates a_ik*b_kj over k in A's column order, so
 // results are bitwise reproducible run to run.
 #include <cub/cub.cuh>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -351,7 +352,7 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
           if (active) {
             const int64_t kb = b0_j + (t - (incl_j - len_j));
             col = __ldg(&b_idx[kb]);
-            prod = av_j * (dk_j * __ldg(&b_val[kb]));  // (M B) first, as the unfused product rounds
+            prod = __dmul_rn(av_j, __dmul_rn(dk_j, __ldg(&b_val[kb])));  // (M B) first, as the unfused product rounds
             bool is_new;
             slot = hash_insert(keys, tcap, col, is_new);
           }
@@ -359,7 +360,7 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
           const int rank = __popc(same & ((1u << lane) - 1));
           unsigned pending = __ballot_sync(0xffffffffu, active);
           for (int r = 0; pending; ++r) {
-            if (active && rank == r) vals[slot] += prod;
+            if (active && rank == r) vals[slot] = __dadd_rn(vals[slot], prod);
             __syncwarp();
             pending = __ballot_sync(0xffffffffu, active && rank > r);
           }
@@ -411,7 +412,7 @@ __global__ void spgemm_rows_kernel(const int64_t* __restrict__ a_ptr, const int3
             if (col[u] == kEmpty) continue;
             bool is_new;
             const uint32_t slot = hash_insert(keys, tcap, col[u], is_new);
-            if (NUMERIC) vals[slot] += av * (dk * bv[u]);
+            if (NUMERIC) vals[slot] = __dadd_rn(vals[slot], __dmul_rn(av, __dmul_rn(dk, bv[u])));
             if (overflow_limit > 0 && is_new) atomicAdd(&s_new[gid], 1);
             if (!NUMERIC && slot == 0xffffffffu) atomicAdd(&s_new[gid], (int)tcap);  // full: force the retry
           }
@@ -540,26 +541,60 @@ __device__ __forceinline__ void warp_sort_regs(uint64_t (&key)[R], int lane) {
 }
 
 // G: lanes per row of B (4, 8, 16, 32).  R: keys per lane of the register sort (numeric; 0: sort in shared memory).
+// SCALE: a row scale of B is applied (a_ik * (d_k * b_kj)); compiled out otherwise.
 // One warp per output row; W = blockDim.x/32 rows per block; dynamic shared memory W * cap * (NUMERIC ? 12 : 4) bytes.
-template <int G, int R, bool NUMERIC>
+// Entry offsets of B travel as 32 bits (the host takes this path only while nnz(B) < 2^31).
+//
+// Instruction budget (ncu, round 2: these kernels are ISSUE bound, 62-87 % issue-active, so instructions per product
+// are what counts).  The first version ran ~120 instructions per step of NG rows: a software pipeline that renamed 12
+// registers per step, 64-bit address arithmetic, a max-reduction per step for rows of B longer than G.  Now the loads
+// of S steps are issued together into registers (no pipeline moves, S*2 loads in flight per lane), the steps are
+// unrolled, and only the rows of B that are longer than G take a second pass for their tails.
+template <int G, int R, bool NUMERIC, bool SCALE>
 __global__ void __launch_bounds__(256)
 spgemm_warp_kernel(const int64_t* __restrict__ a_ptr, const int32_t* __restrict__ a_idx, const double* __restrict__ a_val,
                    const int64_t* __restrict__ b_ptr, const int32_t* __restrict__ b_idx, const double* __restrict__ b_val,
                    const double* __restrict__ b_scale, int64_t row_begin, const int32_t* __restrict__ row_list,
                    int64_t n_list, uint32_t cap, int shift, uint32_t max_probe, int* __restrict__ overflow_flag,
                    int64_t* __restrict__ row_size, const int64_t* __restrict__ c_ptr, int32_t* __restrict__ c_idx,
-                   double* __restrict__ c_val) {
+                   double* __restrict__ c_val, unsigned long long* __restrict__ ticket, int chunk) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  constexpr int NG = 32 / G;  // rows of B per step
+  constexpr int NG = 32 / G;                              // rows of B per step
+  constexpr int S = G >= 16 ? 4 : (G == 8 ? 2 : 1);       // steps whose loads are issued together (NG*S divides 32)
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
-  const int W = blockDim.x >> 5;
   const int sub = lane & (G - 1), grp = lane / G;
   unsigned char* base = s_raw + (size_t)wid * cap * (NUMERIC ? 12 : 4);
   double* vals = reinterpret_cast<double*>(base);  // NUMERIC only
   int32_t* keys = reinterpret_cast<int32_t*>(base + (NUMERIC ? (size_t)cap * 8 : 0));
   const uint32_t mask = cap - 1;
-  for (int64_t li = (int64_t)blockIdx.x * W + wid; li < n_list; li += (int64_t)gridDim.x * W) {
+  // one table operation of this lane: insert the column, then (numeric) add in sub-group order
+  auto process = [&](int32_t col, double bv, double av_j, double dk_j, bool& fail) {
+    const bool active = col != kEmpty;
+    uint32_t slot = 0;
+    if (active) slot = table_insert(keys, mask, shift, col, max_probe);
+    if (!NUMERIC) {
+      fail = fail || (active && slot == kNoSlot);
+    } else {
+      // explicit roundings (no FMA contraction, which differs between template instantiations): every term is
+      // fl(a_ik * fl(d_k * b_kj)) added with one rounding — the arithmetic of the unfused product and of the oracle
+      const double prod = SCALE ? __dmul_rn(av_j, __dmul_rn(dk_j, bv)) : __dmul_rn(av_j, bv);
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        if (active && grp == g) vals[slot] = __dadd_rn(vals[slot], prod);
+        __syncwarp();
+      }
+    }
+  };
+  // Rows are handed out dynamically, `chunk` consecutive list entries per atomic (consecutive entries are consecutive
+  // rows of A, whose rows of B overlap: a chunk keeps them in one warp's L1).
+  for (;;) {
+  long long tk = 0;
+  if (lane == 0) tk = (long long)atomicAdd(ticket, (unsigned long long)chunk);
+  tk = __shfl_sync(0xffffffffu, tk, 0);
+  if (tk >= n_list) break;
+  const int64_t li_end = min((int64_t)tk + chunk, n_list);
+  for (int64_t li = tk; li < li_end; ++li) {
     const int64_t i = row_list[li];
     for (uint32_t t = lane; t < cap; t += 32) {
       keys[t] = kEmpty;
@@ -571,77 +606,83 @@ spgemm_warp_kernel(const int64_t* __restrict__ a_ptr, const int32_t* __restrict_
     for (int64_t c0 = a0; c0 < a1 && !overflow; c0 += 32) {
       // ---- stage: one entry of A's row per lane ----------------------------------------------------
       const int64_t ka = c0 + lane;
-      int64_t b0 = 0;
+      uint32_t b0 = 0;
       int len = 0;
       double av = 0.0, dk = 1.0;
       if (ka < a1) {
         const int k = __ldg(&a_idx[ka]);
-        b0 = __ldg(&b_ptr[k]);
-        len = (int)(__ldg(&b_ptr[k + 1]) - b0);
+        const int64_t p0 = __ldg(&b_ptr[k]);
+        b0 = (uint32_t)p0;
+        len = (int)(__ldg(&b_ptr[k + 1]) - p0);
         if (NUMERIC) {
           av = __ldg(&a_val[ka]);
-          if (b_scale) dk = __ldg(&b_scale[k]);
+          if (SCALE) dk = __ldg(&b_scale[k]);
         }
       }
       const int nk = (int)min((int64_t)32, a1 - c0);
-      // ---- steps: NG rows of B at a time; the first G entries of the next step's rows are requested early
-      int64_t nb0 = __shfl_sync(0xffffffffu, b0, grp);
-      int nlen = __shfl_sync(0xffffffffu, len, grp);
-      double nav = NUMERIC ? __shfl_sync(0xffffffffu, av, grp) : 0.0;
-      double ndk = NUMERIC ? __shfl_sync(0xffffffffu, dk, grp) : 1.0;
-      int32_t ncol = kEmpty;
-      double nbv = 0.0;
-      if (sub < nlen) {
-        ncol = __ldg(&b_idx[nb0 + sub]);
-        if (NUMERIC) nbv = __ldg(&b_val[nb0 + sub]);
-      }
-      for (int j0 = 0; j0 < nk; j0 += NG) {
-        const int64_t b0_j = nb0;
-        const int len_j = nlen;
-        const double av_j = nav, dk_j = ndk;
-        int32_t col = ncol;
-        double bv = nbv;
-        if (j0 + NG < nk) {  // warp-uniform
-          const int jn = j0 + NG + grp;  // <= 31: j0 + NG <= 31 and a multiple of NG
-          nb0 = __shfl_sync(0xffffffffu, b0, jn);
-          nlen = __shfl_sync(0xffffffffu, len, jn);
+      bool fail = false;
+      // ---- pass A: the first G entries of every row of B, NG rows per step, S steps per load group -------
+      for (int j0 = 0; j0 < nk; j0 += NG * S) {  // warp-uniform
+        int32_t col[S];
+        double bv[S];
+#pragma unroll
+        for (int st = 0; st < S; ++st) {
+          const int j = j0 + st * NG + grp;  // <= 31
+          const uint32_t b0_j = __shfl_sync(0xffffffffu, b0, j);
+          const int len_j = __shfl_sync(0xffffffffu, len, j);  // 0 beyond the row of A
+          col[st] = kEmpty;
+          bv[st] = 0.0;
+          if (sub < len_j) {
+            col[st] = __ldg(&b_idx[b0_j + (uint32_t)sub]);
+            if (NUMERIC) bv[st] = __ldg(&b_val[b0_j + (uint32_t)sub]);
+          }
+        }
+#pragma unroll
+        for (int st = 0; st < S; ++st) {
+          if (st > 0 && j0 + st * NG >= nk) break;  // warp-uniform
+          const int j = j0 + st * NG + grp;
+          double av_j = 0.0, dk_j = 1.0;
           if (NUMERIC) {
-            nav = __shfl_sync(0xffffffffu, av, jn);
-            ndk = __shfl_sync(0xffffffffu, dk, jn);
+            av_j = __shfl_sync(0xffffffffu, av, j);
+            if (SCALE) dk_j = __shfl_sync(0xffffffffu, dk, j);
           }
-          ncol = kEmpty;
-          if (sub < nlen) {
-            ncol = __ldg(&b_idx[nb0 + sub]);
-            if (NUMERIC) nbv = __ldg(&b_val[nb0 + sub]);
-          }
+          process(col[st], bv[st], av_j, dk_j, fail);
+        }
+      }
+      // ---- pass B: the tails of the rows of B that are longer than G, NG rows per step --------------------
+      // (their contributions follow the heads of the later rows of this batch: the sum order of a column is fixed,
+      // ascending k inside each pass)
+      unsigned longmask = __ballot_sync(0xffffffffu, len > G);
+      while (longmask) {  // warp-uniform
+        int j = -1;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          const int bit = longmask ? __ffs(longmask) - 1 : -1;
+          if (grp == g) j = bit;
+          longmask &= longmask - 1;  // 0 stays 0
+        }
+        const int src = j < 0 ? 0 : j;  // every lane takes part in the shuffles; sub-groups without a row get length 0
+        const uint32_t b0_j = __shfl_sync(0xffffffffu, b0, src);
+        int len_j = __shfl_sync(0xffffffffu, len, src);
+        if (j < 0) len_j = 0;
+        double av_j = 0.0, dk_j = 1.0;
+        if (NUMERIC) {
+          av_j = __shfl_sync(0xffffffffu, av, src);
+          if (SCALE) dk_j = __shfl_sync(0xffffffffu, dk, src);
         }
         const int maxlen = __reduce_max_sync(0xffffffffu, len_j);
-        for (int t0 = 0; t0 < maxlen; t0 += G) {  // warp-uniform; one pass unless a row of B is longer than G
+        for (int t0 = G; t0 < maxlen; t0 += G) {  // warp-uniform
           const int t = t0 + sub;
-          if (t0 > 0) {
-            col = kEmpty;
-            if (t < len_j) {
-              col = __ldg(&b_idx[b0_j + t]);
-              if (NUMERIC) bv = __ldg(&b_val[b0_j + t]);
-            }
+          int32_t col = kEmpty;
+          double bv = 0.0;
+          if (t < len_j) {
+            col = __ldg(&b_idx[b0_j + (uint32_t)t]);
+            if (NUMERIC) bv = __ldg(&b_val[b0_j + (uint32_t)t]);
           }
-          const bool active = col != kEmpty;
-          uint32_t slot = 0;
-          if (active) slot = table_insert(keys, mask, shift, col, max_probe);
-          if (!NUMERIC) {
-            if (__any_sync(0xffffffffu, active && slot == kNoSlot)) overflow = true;  // warp-uniform
-          } else {
-            const double prod = av_j * (dk_j * bv);  // (d_k b_kj) first: what the unfused product M·B rounds
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-              if (active && grp == g) vals[slot] += prod;
-              if (NG > 1) __syncwarp();
-            }
-            if (NG == 1) __syncwarp();
-          }
+          process(col, bv, av_j, dk_j, fail);
         }
-        if (!NUMERIC && overflow) break;
       }
+      if (!NUMERIC && __any_sync(0xffffffffu, fail)) overflow = true;  // warp-uniform; checked once per batch of A
     }
     __syncwarp();
     if (!NUMERIC) {
@@ -674,21 +715,27 @@ spgemm_warp_kernel(const int64_t* __restrict__ a_ptr, const int32_t* __restrict_
     const int64_t out0 = c_ptr[i];
     const uint32_t nnz = (uint32_t)(c_ptr[i + 1] - out0);  // == n_occ (symbolic count)
     if constexpr (R > 0) {
-      uint64_t key[R];
+      // sort (column, position) keys in registers: 32*R keys, or 16*R when the row fits half of that
+      auto sort_write = [&](auto rr_tag) {
+        constexpr int RR = decltype(rr_tag)::value;
+        uint64_t key[RR];
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const uint32_t e = (uint32_t)R * lane + r;
-        key[r] = e < nnz ? (((uint64_t)(uint32_t)keys[e] << 32) | e) : ~0ULL;
-      }
-      warp_sort_regs<R>(key, lane);
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const uint32_t e = (uint32_t)R * lane + r;
-        if (e < nnz) {
-          c_idx[out0 + e] = (int32_t)(key[r] >> 32);
-          c_val[out0 + e] = vals[(uint32_t)(key[r] & 0xffffffffu)];
+        for (int r = 0; r < RR; ++r) {
+          const uint32_t e = (uint32_t)RR * lane + r;
+          key[r] = e < nnz ? (((uint64_t)(uint32_t)keys[e] << 32) | e) : ~0ULL;
         }
-      }
+        warp_sort_regs<RR>(key, lane);
+#pragma unroll
+        for (int r = 0; r < RR; ++r) {
+          const uint32_t e = (uint32_t)RR * lane + r;
+          if (e < nnz) {
+            c_idx[out0 + e] = (int32_t)(key[r] >> 32);
+            c_val[out0 + e] = vals[(uint32_t)(key[r] & 0xffffffffu)];
+          }
+        }
+      };
+      if (R >= 2 && nnz <= 16u * R) sort_write(std::integral_constant<int, (R >= 2 ? R / 2 : 1)>{});  // warp-uniform
+      else sort_write(std::integral_constant<int, R>{});
     } else {
       uint32_t scap = 2;
       while (scap < nnz) scap <<= 1;  // <= cap (nnz <= cap)
@@ -718,6 +765,7 @@ spgemm_warp_kernel(const int64_t* __restrict__ a_ptr, const int32_t* __restrict_
       }
     }
     __syncwarp();  // the table is re-initialised by the next row
+  }
   }
 }
 
@@ -929,45 +977,64 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, const double* b_scale, int64_t
 
   // lean warp-per-row kernel (short rows of B): G lanes per row of B from B's mean row length
   const int64_t b_mean = b->nnz / std::max<int64_t>(b->n_rows, 1);
-  const bool lean = lean_enabled() && b->nnz <= 32 * std::max<int64_t>(b->n_rows, 1);
+  const bool lean = lean_enabled() && b->nnz <= 32 * std::max<int64_t>(b->n_rows, 1) && b->nnz < ((int64_t)1 << 31);
   const int G = b_mean <= 4 ? 4 : (b_mean <= 8 ? 8 : (b_mean <= 16 ? 16 : 32));
+  constexpr int kMaxWarpLaunches = 32;
+  DevBuf<unsigned long long> tickets;
+  int n_warp_launches = 0;
+  if (lean) {
+    tickets.alloc(kMaxWarpLaunches, s);
+    FXII_CUDA(cudaMemsetAsync(tickets.p, 0, sizeof(unsigned long long) * kMaxWarpLaunches, s));
+  }
   auto launch_warp = [&](bool numeric, const int32_t* list, int64_t nl, uint32_t cap, uint32_t max_probe, int32_t* c_idx,
                          double* c_val) {
     if (nl == 0) return;
+    FXII_CHECK(n_warp_launches < kMaxWarpLaunches, "spgemm: too many kernel launches in one product");
+    unsigned long long* ticket = tickets.p + n_warp_launches++;
     // warps per block: tables of a block within 48 KB, at most 8 warps
     const size_t per_warp = (size_t)cap * (numeric ? 12 : 4);
     int W = (int)std::min<size_t>(8, std::max<size_t>(1, (48 * 1024) / per_warp));
     const size_t smem = per_warp * W;
     const int grid = (int)std::min<int64_t>((nl + W - 1) / W, (int64_t)num_sms() * 32);
+    // rows per ticket: about an eighth of a warp's share, 1..16
+    const int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(16, nl / ((int64_t)grid * W * 8)));
     const int shift = 32 - ilog2(cap);
     // register sort: R keys per lane cover 32*R >= the largest row of the bin
     const int lf = lean_load_factor_pct();
     const int64_t max_nnz = (int64_t)cap * lf / 100;
     int R = 0;
     if (numeric) R = max_nnz <= 64 ? 2 : (max_nnz <= 128 ? 4 : (max_nnz <= 256 ? 8 : (max_nnz <= 512 ? 16 : 0)));
-#define FXII_WARP_LAUNCH(GG, RR, NUM)                                                                                  \
+#define FXII_WARP_LAUNCH(GG, RR, NUM, SC)                                                                              \
   do {                                                                                                                 \
     if (smem > 48 * 1024)                                                                                              \
-      FXII_CUDA(cudaFuncSetAttribute(spgemm_warp_kernel<GG, RR, NUM>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+      FXII_CUDA(cudaFuncSetAttribute(spgemm_warp_kernel<GG, RR, NUM, SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)smem));                                                                      \
-    spgemm_warp_kernel<GG, RR, NUM><<<grid, 32 * W, smem, s>>>(                                                        \
+    FXII_CUDA(cudaFuncSetAttribute(spgemm_warp_kernel<GG, RR, NUM, SC>, cudaFuncAttributePreferredSharedMemoryCarveout,\
+                                   cudaSharedmemCarveoutMaxShared));                                                   \
+    spgemm_warp_kernel<GG, RR, NUM, SC><<<grid, 32 * W, smem, s>>>(                                                    \
         a->indptr.p, a->indices.p, a->values.p, b->indptr.p, b->indices.p, b->values.p, b_scale, row_begin, list, nl,  \
-        cap, shift, max_probe, overflow.p, row_nnz.p, out->indptr.p, c_idx, c_val);                                    \
+        cap, shift, max_probe, overflow.p, row_nnz.p, out->indptr.p, c_idx, c_val, ticket, chunk);                     \
+  } while (0)
+#define FXII_WARP_S(GG, RR)                                                                                            \
+  do {                                                                                                                 \
+    if (b_scale) FXII_WARP_LAUNCH(GG, RR, true, true);                                                                 \
+    else FXII_WARP_LAUNCH(GG, RR, true, false);                                                                        \
   } while (0)
 #define FXII_WARP_R(GG)                                                                                                \
   do {                                                                                                                 \
-    if (!numeric) FXII_WARP_LAUNCH(GG, 0, false);                                                                      \
-    else if (R == 2) FXII_WARP_LAUNCH(GG, 2, true);                                                                    \
-    else if (R == 4) FXII_WARP_LAUNCH(GG, 4, true);                                                                    \
-    else if (R == 8) FXII_WARP_LAUNCH(GG, 8, true);                                                                    \
-    else if (R == 16) FXII_WARP_LAUNCH(GG, 16, true);                                                                  \
-    else FXII_WARP_LAUNCH(GG, 0, true);                                                                                \
+    if (!numeric) FXII_WARP_LAUNCH(GG, 0, false, false);                                                               \
+    else if (R == 2) FXII_WARP_S(GG, 2);                                                                               \
+    else if (R == 4) FXII_WARP_S(GG, 4);                                                                               \
+    else if (R == 8) FXII_WARP_S(GG, 8);                                                                               \
+    else if (R == 16) FXII_WARP_S(GG, 16);                                                                             \
+    else FXII_WARP_S(GG, 0);                                                                                           \
   } while (0)
     if (G == 4) FXII_WARP_R(4);
     else if (G == 8) FXII_WARP_R(8);
     else if (G == 16) FXII_WARP_R(16);
     else FXII_WARP_R(32);
 #undef FXII_WARP_R
+#undef FXII_WARP_S
 #undef FXII_WARP_LAUNCH
     FXII_CUDA(cudaGetLastError());
     FXII_LAUNCHED(1);
