@@ -57,14 +57,15 @@ class Topology:
     def __init__(self, dim: int, n_cells: int, n_vertices: int):
         self.dim = dim
         self._maps = {dim: IndexMap(n_cells), 0: IndexMap(n_vertices)}
-        self.cell_name = {1: "interval", 3: "tetrahedron"}.get(dim, "unknown")
+        self.cell_name = {1: "interval", 3: "tetrahedron"}.get(dim, "unknown")  # "hexahedron" is set by Mesh
 
     def index_map(self, dim: int) -> IndexMap:
         return self._maps[dim]
 
 
 class Mesh:
-    """Affine simplex mesh given by node coordinates ``x [n,3]`` and cells ``[n_cells, tdim+1]``."""
+    """Mesh given by node coordinates ``x [n,3]`` and cells: simplices ``[n_cells, tdim+1]`` (intervals, tetrahedra) or
+    hexahedra ``[n_cells, 8]`` with Q1 geometry, vertices in dolfinx's tensor-product order v = i + 2j + 4k."""
 
     def __init__(self, x, cells, tdim: int, name: str = "mesh"):
         x = np.ascontiguousarray(x, dtype=np.float64)
@@ -73,9 +74,11 @@ class Mesh:
             xx[:, : x.shape[1]] = x
             x = xx
         cells = np.ascontiguousarray(cells, dtype=np.int32)
-        assert cells.shape[1] == tdim + 1
+        assert cells.shape[1] == tdim + 1 or (tdim == 3 and cells.shape[1] == 8)
         self.geometry = Geometry(x=x, dofmap=cells, dim=3)
         self.topology = Topology(tdim, cells.shape[0], x.shape[0])
+        if tdim == 3 and cells.shape[1] == 8:
+            self.topology.cell_name = "hexahedron"
         self.name = name
         self.comm = None
 
@@ -149,6 +152,10 @@ def functionspace(mesh: Mesh, element, dof_list: np.ndarray | None = None, n_dof
     cells = mesh.geometry.dofmap
     n_cells, n_nodes = cells.shape[0], mesh.geometry.x.shape[0]
     tdim = mesh.topology.dim
+    if tdim == 3 and cells.shape[1] == 8:
+        if family != "Lagrange" or degree != 1:
+            raise NotImplementedError("hexahedra: Lagrange degree 1 (Q1)")
+        return FunctionSpace(mesh, Element("Lagrange", 1, np.zeros((0, 3))), DofMap(cells.copy(), n_nodes))
     if tdim == 3:
         if family != "Lagrange" or degree not in (1, 2):
             raise NotImplementedError("3D spaces: Lagrange degree 1 or 2 on affine tetrahedra")

@@ -38,6 +38,30 @@ def kuhn_box(nx: int, ny: int, nz: int, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0), 
     return mesh
 
 
+def hex_box(nx: int, ny: int, nz: int, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0), taper: float = 0.0, name="hex_volume") -> Mesh:
+    """nx*ny*nz hexahedra (what dolfinx ``create_box(..., CellType.hexahedron)`` produces, before its reordering);
+    cell vertices in tensor-product order v = i + 2j + 4k.  ``taper`` != 0 maps (x, y, z) -> (x (1 + taper z),
+    y (1 + taper z), z): every cell becomes a frustum with PLANAR faces whose trilinear map is not affine — the
+    case the Newton pull-back exists for."""
+    lo = np.asarray(lo, dtype=np.float64)
+    hi = np.asarray(hi, dtype=np.float64)
+    xs = lo[0] + (hi[0] - lo[0]) * (np.arange(nx + 1) / nx)
+    ys = lo[1] + (hi[1] - lo[1]) * (np.arange(ny + 1) / ny)
+    zs = lo[2] + (hi[2] - lo[2]) * (np.arange(nz + 1) / nz)
+    Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij")
+    x = np.stack([X.reshape(-1), Y.reshape(-1), Z.reshape(-1)], axis=1)
+    if taper != 0.0:
+        s = 1.0 + taper * x[:, 2]
+        x = np.stack([x[:, 0] * s, x[:, 1] * s, x[:, 2]], axis=1)
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    base = ((k * (ny + 1) + j) * (nx + 1) + i).reshape(-1).astype(np.int64)
+    corner_off = (_CORNER[:, 2] * (ny + 1) + _CORNER[:, 1]) * (nx + 1) + _CORNER[:, 0]
+    cells = (base[:, None] + corner_off[None, :]).astype(np.int32)  # _CORNER is already v = i + 2j + 4k
+    mesh = Mesh(x, cells, tdim=3, name=name)
+    mesh.grid_shape = (nx, ny, nz)
+    return mesh
+
+
 def kuhn_p2_space(mesh: Mesh) -> FunctionSpace:
     """P2 space on a ``kuhn_box`` mesh with a closed-form edge numbering (no global sort).
 

@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""All-gather-v variants over NCCL for the CSR shards of config 5 (84.3 M entries in total), run under torchrun:
+uneven all_gather (coalesced broadcasts, in place), batch_isend_irecv, padded all_gather_into_tensor (+ unpack copies).
+Prints ms per variant (max over ranks) and GB/s received per rank."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    total = int(os.environ.get("GATHER_NNZ", "84290030"))
+    base, rem = divmod(total, world)
+    sizes = [base + (1 if r < rem else 0) + 1000 * ((r * 7) % 5) for r in range(world)]  # slightly uneven
+    off = [0]
+    for s in sizes:
+        off.append(off[-1] + s)
+    n = sizes[rank]
+    idx = torch.randint(0, 1 << 24, (n,), dtype=torch.int32, device="cuda")
+    val = torch.rand(n, dtype=torch.float64, device="cuda")
+    g_idx = torch.empty(off[-1], dtype=torch.int32, device="cuda")
+    g_val = torch.empty(off[-1], dtype=torch.float64, device="cuda")
+
+    def uneven():
+        dist.all_gather([g_idx[off[r]:off[r + 1]] for r in range(world)], idx)
+        dist.all_gather([g_val[off[r]:off[r + 1]] for r in range(world)], val)
+
+    def p2p():
+        ops = []
+        for buf, loc in ((g_idx, idx), (g_val, val)):
+            buf[off[rank]:off[rank + 1]].copy_(loc)
+            for r in range(world):
+                if r != rank:
+                    ops.append(dist.P2POp(dist.isend, loc, r))
+                    ops.append(dist.P2POp(dist.irecv, buf[off[r]:off[r + 1]], r))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+    mx = max(sizes)
+    pad_i = torch.zeros(mx, dtype=torch.int32, device="cuda")
+    pad_v = torch.zeros(mx, dtype=torch.float64, device="cuda")
+    rec_i = torch.empty(world * mx, dtype=torch.int32, device="cuda")
+    rec_v = torch.empty(world * mx, dtype=torch.float64, device="cuda")
+
+    def padded():
+        pad_i[:n].copy_(idx)
+        pad_v[:n].copy_(val)
+        dist.all_gather_into_tensor(rec_i, pad_i)
+        dist.all_gather_into_tensor(rec_v, pad_v)
+        for r in range(world):
+            g_idx[off[r]:off[r + 1]].copy_(rec_i[r * mx:r * mx + sizes[r]])
+            g_val[off[r]:off[r + 1]].copy_(rec_v[r * mx:r * mx + sizes[r]])
+
+    def padded_only():
+        dist.all_gather_into_tensor(rec_i, pad_i)
+        dist.all_gather_into_tensor(rec_v, pad_v)
+
+    res = {}
+    for name, fn in (("uneven_all_gather", uneven), ("batch_isend_irecv", p2p), ("padded_all_gather+unpack", padded),
+                     ("padded_all_gather_only", padded_only)):
+        try:
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b) / reps], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res[name] = float(t.item())
+        except Exception as e:  # noqa: BLE001
+            res[name] = f"failed: {type(e).__name__}: {e}"[:200]
+    # correctness of the in-place variant
+    uneven()
+    chk = torch.tensor([float(g_val[off[rank]:off[rank + 1]].sum() - val.sum())], device="cuda")
+    if rank == 0:
+        recv_gb = 12 * (off[-1] - n) / 1e9
+        print(f"world={world} entries={off[-1]} received per rank {recv_gb:.3f} GB")
+        for k, v in res.items():
+            print(f"  {k:28s} {v if isinstance(v, str) else f'{v:8.3f} ms  {recv_gb / (v * 1e-3):7.1f} GB/s'}")
+        print("  self-check", float(chk.item()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
