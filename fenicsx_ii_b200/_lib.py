@@ -81,6 +81,7 @@ SIGNATURES = {
     "fxii_launch_count": (C.c_int64, []),
     "fxii_trim_memory": (C.c_int, []),
     "fxii_mesh_create": (C.c_int, [_vp, _i64, _vp, _i64, _dbl, _vp, C.POINTER(_vp)]),
+    "fxii_mesh_create_cells": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _dbl, _vp, C.POINTER(_vp)]),
     "fxii_mesh_info": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i32)]),
     "fxii_mesh_destroy": (C.c_int, [_vp]),
     "fxii_space_create": (C.c_int, [_vp, _vp, _i32, _i32, _i64, _vp, C.POINTER(_vp)]),

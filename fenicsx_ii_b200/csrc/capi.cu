@@ -5,7 +5,7 @@
 #include "common.cuh"
 
 namespace fxii {
-void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* cell_nodes, int64_t n_cells,
+void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* cell_nodes, int64_t n_cells, int npc,
                 double padding, cudaStream_t s);
 void device_iota(int32_t* a, int64_t n, cudaStream_t s);
 void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr* out, fxii_pi_stats* stats,
@@ -225,19 +225,26 @@ int fxii_sm_count(int* n) {
   });
 }
 
-int fxii_mesh_create(const double* x, int64_t n_nodes, const int32_t* cell_nodes, int64_t n_cells, double padding,
-                     void* stream, fxii_mesh** out) {
+int fxii_mesh_create_cells(const double* x, int64_t n_nodes, const int32_t* cell_nodes, int64_t n_cells,
+                           int32_t nodes_per_cell, double padding, void* stream, fxii_mesh** out) {
   return guarded([&] {
     FXII_CHECK(x && cell_nodes && out, "null argument");
+    if (nodes_per_cell != 4 && nodes_per_cell != 8)
+      throw fxii::Error(FXII_E_UNSUPPORTED, "cells must be affine tetrahedra (4 nodes) or Q1 hexahedra (8 nodes)");
     auto* m = new fxii_mesh();
     try {
-      fxii::mesh_build(m, x, n_nodes, cell_nodes, n_cells, padding, S(stream));
+      fxii::mesh_build(m, x, n_nodes, cell_nodes, n_cells, nodes_per_cell, padding, S(stream));
     } catch (...) {
       delete m;
       throw;
     }
     *out = m;
   });
+}
+
+int fxii_mesh_create(const double* x, int64_t n_nodes, const int32_t* cell_nodes, int64_t n_cells, double padding,
+                     void* stream, fxii_mesh** out) {
+  return fxii_mesh_create_cells(x, n_nodes, cell_nodes, n_cells, 4, padding, stream, out);
 }
 
 int fxii_mesh_info(const fxii_mesh* m, int64_t* n_cells, int64_t* n_nodes, int64_t* device_bytes, int32_t* max_depth) {
@@ -258,8 +265,11 @@ int fxii_space_create(fxii_mesh* mesh, const int32_t* dofmap, int32_t nd, int32_
                       fxii_space** out) {
   return guarded([&] {
     FXII_CHECK(mesh && dofmap && out, "null argument");
-    if (!((degree == 1 && nd == 4) || (degree == 2 && nd == 10)))
-      throw fxii::Error(FXII_E_UNSUPPORTED, "only Lagrange P1 (nd=4) and P2 (nd=10) on affine tetrahedra are supported");
+    const bool tet_ok = mesh->npc == 4 && ((degree == 1 && nd == 4) || (degree == 2 && nd == 10));
+    const bool hex_ok = mesh->npc == 8 && degree == 1 && nd == 8;
+    if (!(tet_ok || hex_ok))
+      throw fxii::Error(FXII_E_UNSUPPORTED,
+                        "supported spaces: Lagrange P1 (nd=4) / P2 (nd=10) on affine tetrahedra, Q1 (nd=8) on hexahedra");
     auto* s = new fxii_space();
     s->mesh = mesh;
     s->nd = nd;

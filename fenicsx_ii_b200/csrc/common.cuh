@@ -185,10 +185,13 @@ __device__ void bitonic_sort_u64(uint64_t* keys, uint32_t cap, int tid, int nthr
 
 struct fxii_mesh {
   int64_t n_cells = 0, n_nodes = 0;
+  int32_t npc = 4;                   // geometry nodes per cell: 4 (affine tetrahedra) or 8 (Q1 hexahedra)
   double padding = 0;
   fxii::DevBuf<double> x;            // [n_nodes,3]
-  fxii::DevBuf<int32_t> cell_nodes;  // [n_cells,4]
-  fxii::DevBuf<double> cellgeo;      // [n_cells,12]: v0 (3) + K=J^{-1} row-major (9), 96 B per cell
+  fxii::DevBuf<int32_t> cell_nodes;  // [n_cells,npc]
+  // tetrahedra: [n_cells,12] v0 (3) + K=J^{-1} row-major (9), 96 B per cell (the affine pull-back precomputed);
+  // hexahedra:  [n_cells,24] the eight vertices gathered, 192 B per cell (the Newton pull-back and the hull test read them)
+  fxii::DevBuf<double> cellgeo;
   fxii::DevBuf<fxii::WideNode> wnodes; // [max(n_cells-1,1)], indexed like the binary LBVH nodes
   fxii::SceneGrid grid;
   int32_t root = 0;

@@ -29,13 +29,28 @@ expand_rows_kernel(const int64_t* __restrict__ indptr, int64_t n_rows, int32_t* 
   }
 }
 
+// row_of == nullptr: the source row of entry `src` is found by binary search in indptr (window transposes touch
+// only a fraction of the entries: no O(nnz) expansion of the row indices)
 __global__ void __launch_bounds__(256)
 gather_transposed_kernel(const int32_t* __restrict__ perm, const int32_t* __restrict__ row_of,
+                         const int64_t* __restrict__ indptr, int64_t n_rows,
                          const double* __restrict__ values, int64_t nnz, int32_t* __restrict__ t_indices,
                          double* __restrict__ t_values) {
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) {
     const int32_t src = perm[k];
-    t_indices[k] = row_of[src];
+    int32_t row;
+    if (row_of) {
+      row = row_of[src];
+    } else {  // last row r with indptr[r] <= src (empty rows share their successor's offset and are skipped)
+      int64_t lo = 0, hi = n_rows - 1;
+      while (lo < hi) {
+        const int64_t mid = (lo + hi + 1) >> 1;
+        if (__ldg(&indptr[mid]) <= (int64_t)src) lo = mid;
+        else hi = mid - 1;
+      }
+      row = (int32_t)lo;
+    }
+    t_indices[k] = row;
     t_values[k] = values[src];
   }
 }
@@ -56,7 +71,7 @@ struct InWindow {
   const int32_t* indices;
   int32_t c0, c1;
   __device__ bool operator()(const int32_t& k) const {
-    const int32_t c = indices[k];
+    const int32_t c = __ldg(&indices[k]);
     return c >= c0 && c < c1;
   }
 };
@@ -92,22 +107,26 @@ void csr_transpose(const fxii_csr* a, int64_t c0, int64_t c1, cudaStream_t s, fx
   DevBuf<int32_t> row_of, iota, sel, keys, perm, keys_sorted;
   int64_t n_sel = nnz;
   if (nnz > 0) {
-    row_of.alloc(nnz, s);
-    iota.alloc(nnz, s);
-    { expand_rows_kernel<<<grid_for(a->n_rows * 32, 256, 8), 256, 0, s>>>(a->indptr.p, a->n_rows, row_of.p); FXII_LAUNCHED(1); }
-    { iota32_kernel<<<grid_for(nnz, 256, 8), 256, 0, s>>>(iota.p, nnz); FXII_LAUNCHED(1); }
     if (window) {
+      // ordered selection of the entry positions whose column lies in the window, straight from a counting iterator:
+      // the only O(nnz) work of a window transpose is one read of the column indices
       sel.alloc(nnz, s);
       DevBuf<int64_t> n_sel_dev;
       n_sel_dev.alloc(1, s);
       InWindow pred{a->indices.p, (int32_t)c0, (int32_t)c1};
+      cub::CountingInputIterator<int32_t> positions(0);
       size_t tb = 0;
-      FXII_CUDA(cub::DeviceSelect::If(nullptr, tb, iota.p, sel.p, n_sel_dev.p, nnz, pred, s));
+      FXII_CUDA(cub::DeviceSelect::If(nullptr, tb, positions, sel.p, n_sel_dev.p, nnz, pred, s));
       DevBuf<uint8_t> tmp;
       tmp.alloc((int64_t)tb, s);
-      FXII_CUDA(cub::DeviceSelect::If(tmp.p, tb, iota.p, sel.p, n_sel_dev.p, nnz, pred, s));
+      FXII_CUDA(cub::DeviceSelect::If(tmp.p, tb, positions, sel.p, n_sel_dev.p, nnz, pred, s));
       FXII_CUDA(cudaMemcpyAsync(&n_sel, n_sel_dev.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
       FXII_CUDA(cudaStreamSynchronize(s));
+    } else {
+      row_of.alloc(nnz, s);
+      iota.alloc(nnz, s);
+      { expand_rows_kernel<<<grid_for(a->n_rows * 32, 256, 8), 256, 0, s>>>(a->indptr.p, a->n_rows, row_of.p); FXII_LAUNCHED(1); }
+      { iota32_kernel<<<grid_for(nnz, 256, 8), 256, 0, s>>>(iota.p, nnz); FXII_LAUNCHED(1); }
     }
   }
   out->nnz = n_sel;
@@ -133,8 +152,8 @@ void csr_transpose(const fxii_csr* a, int64_t c0, int64_t c1, cudaStream_t s, fx
   tmp.alloc((int64_t)tb, s);
   FXII_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.p, keys_sorted.p, src, perm.p, n_sel, 0, end_bit, s));
   tr.mark("radix sort");
-  { gather_transposed_kernel<<<grid_for(n_sel, 256, 8), 256, 0, s>>>(perm.p, row_of.p, a->values.p, n_sel, out->indices.p,
-                                                                 out->values.p); FXII_LAUNCHED(1); }
+  { gather_transposed_kernel<<<grid_for(n_sel, 256, 8), 256, 0, s>>>(perm.p, window ? nullptr : row_of.p, a->indptr.p, a->n_rows,
+                                                                 a->values.p, n_sel, out->indices.p, out->values.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
 }
 

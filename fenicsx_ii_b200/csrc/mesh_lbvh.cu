@@ -127,6 +127,43 @@ cell_geom_morton_kernel(const double* __restrict__ x, const int4* __restrict__ c
   }
 }
 
+// One thread per hexahedron (Q1 geometry, vertices v = i + 2j + 4k): the eight vertices gathered into one 192 B
+// record — the Newton pull-back (interpolation_utils.py:36-38 for non-affine cells) and the convex-hull collision
+// test read them from there — and the Morton key of the vertex mean.
+__global__ void __launch_bounds__(256)
+hex_geom_morton_kernel(const double* __restrict__ x, const int32_t* __restrict__ cell_nodes, int64_t n_cells,
+                       const unsigned long long* __restrict__ bounds, double* __restrict__ hexgeo,
+                       uint64_t* __restrict__ keys, int32_t* __restrict__ ids) {
+  const double sx0 = dec_ordered(bounds[0]), sy0 = dec_ordered(bounds[1]), sz0 = dec_ordered(bounds[2]);
+  const double ex = fmax(dec_ordered(bounds[3]) - sx0, 1e-300);
+  const double ey = fmax(dec_ordered(bounds[4]) - sy0, 1e-300);
+  const double ez = fmax(dec_ordered(bounds[5]) - sz0, 1e-300);
+  for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
+    double cx = 0.0, cy = 0.0, cz = 0.0;
+    double* out = hexgeo + 24 * c;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int64_t id = __ldg(&cell_nodes[8 * c + k]);
+      const double vx = __ldg(&x[3 * id]), vy = __ldg(&x[3 * id + 1]), vz = __ldg(&x[3 * id + 2]);
+      out[3 * k] = vx;
+      out[3 * k + 1] = vy;
+      out[3 * k + 2] = vz;
+      cx += vx;
+      cy += vy;
+      cz += vz;
+    }
+    cx *= 0.125;
+    cy *= 0.125;
+    cz *= 0.125;
+    const double s = 2097151.0;  // 2^21 - 1
+    uint32_t qx = (uint32_t)fmin(fmax((cx - sx0) / ex * s, 0.0), s);
+    uint32_t qy = (uint32_t)fmin(fmax((cy - sy0) / ey * s, 0.0), s);
+    uint32_t qz = (uint32_t)fmin(fmax((cz - sz0) / ez * s, 0.0), s);
+    keys[c] = (spread21(qx) << 2) | (spread21(qy) << 1) | spread21(qz);
+    ids[c] = (int32_t)c;
+  }
+}
+
 // ---- Karras 2012 ------------------------------------------------------------------------------
 __device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, int i, int j) {
   if (j < 0 || j >= n) return -1;
@@ -194,18 +231,29 @@ __device__ __forceinline__ void store_child_box(BvhNode* node, bool is_left, con
 // `padding`) widened by the point_in_bbox slack and rounded OUTWARD to fp32, so the fp32 traversal
 // never rejects a point the fp64 leaf test would accept.
 __global__ void __launch_bounds__(256)
-refit_kernel(const double* __restrict__ x, const int4* __restrict__ cell_nodes, const int32_t* __restrict__ sorted_cells,
+refit_kernel(const double* __restrict__ x, const int32_t* __restrict__ cell_nodes, int npc,
+             const int32_t* __restrict__ sorted_cells,
              const int32_t* __restrict__ leaf_parent, int n, double padding, BvhNode* nodes, int32_t* flags) {
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const int cell = sorted_cells[k];
-    int4 nd = __ldg(&cell_nodes[cell]);
-    const int id[4] = {nd.x, nd.y, nd.z, nd.w};
+    int id[8];
+    if (npc == 4) {
+      const int4 nd = __ldg(reinterpret_cast<const int4*>(cell_nodes) + cell);
+      id[0] = nd.x, id[1] = nd.y, id[2] = nd.z, id[3] = nd.w;
+      id[4] = nd.x, id[5] = nd.x, id[6] = nd.x, id[7] = nd.x;
+    } else {
+      const int4 n0 = __ldg(reinterpret_cast<const int4*>(cell_nodes) + 2 * (int64_t)cell);
+      const int4 n1 = __ldg(reinterpret_cast<const int4*>(cell_nodes) + 2 * (int64_t)cell + 1);
+      id[0] = n0.x, id[1] = n0.y, id[2] = n0.z, id[3] = n0.w;
+      id[4] = n1.x, id[5] = n1.y, id[6] = n1.z, id[7] = n1.w;
+    }
     BoxF box;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       double lo = 1e300, hi = -1e300;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 8; ++q) {
+        if (q >= npc) break;
         double v = __ldg(&x[3 * (int64_t)id[q] + d]);
         lo = fmin(lo, v);
         hi = fmax(hi, v);
@@ -355,16 +403,18 @@ static void finish_wide(fxii_mesh* m, DevBuf<BvhNode>& bnodes, DevBuf<unsigned l
   FXII_CUDA(cudaStreamSynchronize(s));
 }
 
-void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* cell_nodes, int64_t n_cells,
+void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* cell_nodes, int64_t n_cells, int npc,
                 double padding, cudaStream_t s) {
-  FXII_CHECK(n_cells >= 1 && n_nodes >= 4, "mesh needs at least one tetrahedron");
+  FXII_CHECK(npc == 4 || npc == 8, "cells must have 4 (tetrahedron) or 8 (hexahedron) geometry nodes");
+  FXII_CHECK(n_cells >= 1 && n_nodes >= npc, "mesh needs at least one cell");
   FXII_CHECK(n_cells < (int64_t)1 << 31, "n_cells must fit int32");
   m->n_cells = n_cells;
   m->n_nodes = n_nodes;
+  m->npc = npc;
   m->padding = padding;
   m->x.upload(x, 3 * n_nodes, s);
-  m->cell_nodes.upload(cell_nodes, 4 * n_cells, s);
-  m->cellgeo.alloc(12 * n_cells, s);
+  m->cell_nodes.upload(cell_nodes, (int64_t)npc * n_cells, s);
+  m->cellgeo.alloc((npc == 4 ? 12 : 24) * n_cells, s);
   const int n = (int)n_cells;
   const int n_internal = n > 1 ? n - 1 : 1;
   DevBuf<BvhNode> bnodes;  // binary LBVH, only needed until the wide collapse
@@ -390,8 +440,13 @@ void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* c
   ids_sorted.alloc(n, s);
   leaf_parent.alloc(n, s);
   flags.alloc(n_internal, s);
-  { cell_geom_morton_kernel<<<grid_for(n_cells, 256, 8), 256, 0, s>>>(
-      m->x.p, reinterpret_cast<const int4*>(m->cell_nodes.p), n_cells, bounds.p, m->cellgeo.p, keys.p, ids.p); FXII_LAUNCHED(1); }
+  if (npc == 4) {
+    { cell_geom_morton_kernel<<<grid_for(n_cells, 256, 8), 256, 0, s>>>(
+        m->x.p, reinterpret_cast<const int4*>(m->cell_nodes.p), n_cells, bounds.p, m->cellgeo.p, keys.p, ids.p); FXII_LAUNCHED(1); }
+  } else {
+    { hex_geom_morton_kernel<<<grid_for(n_cells, 256, 8), 256, 0, s>>>(m->x.p, m->cell_nodes.p, n_cells, bounds.p, m->cellgeo.p,
+                                                                     keys.p, ids.p); FXII_LAUNCHED(1); }
+  }
   FXII_CUDA(cudaGetLastError());
 
   size_t tmp_bytes = 0;
@@ -421,7 +476,7 @@ void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* c
   FXII_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int32_t) * (size_t)n_internal, s));
   { karras_internal_kernel<<<grid_for(n - 1, 256, 8), 256, 0, s>>>(keys_sorted.p, ids_sorted.p, n, bnodes.p, leaf_parent.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
-  { refit_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(m->x.p, reinterpret_cast<const int4*>(m->cell_nodes.p), ids_sorted.p,
+  { refit_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(m->x.p, m->cell_nodes.p, npc, ids_sorted.p,
                                                    leaf_parent.p, n, padding, bnodes.p, flags.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
   DevBuf<int32_t> depth;

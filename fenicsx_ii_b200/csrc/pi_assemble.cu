@@ -217,6 +217,95 @@ __device__ __noinline__ double cell_distance2(const double* __restrict__ x, cons
   return best;
 }
 
+// ---- hexahedra (Q1 geometry, vertices v = i + 2j + 4k; mirrors oracle/pi_oracle.py: q1_tabulate, pull_back_hex,
+// point_hex_distance2) -----------------------------------------------------------------------------------------------
+struct HexX {
+  double X0, X1, X2;
+  int conv;
+};
+constexpr double kNewtonTol2 = 1.0e-12;  // |dX| < 1e-6: dolfinx CoordinateElement::pull_back_nonaffine defaults [3P-recall]
+constexpr int kNewtonMaxIt = 15;
+
+// Newton pull-back into the hexahedron whose eight vertices are hv[24] (interpolation_utils.py:36-38 for non-affine
+// cells): X = 0; X += J^{-1} (x - x(X)) until |dX| < tol.  The vertices are re-read from L1 in every iteration
+// instead of being held in registers (24 doubles); point and result travel by value.
+__device__ __noinline__ HexX hex_pull_back(const double* __restrict__ hv, double p0, double p1, double p2) {
+  double X[3] = {0.0, 0.0, 0.0};
+  int conv = 0;
+  for (int it = 0; it < kNewtonMaxIt; ++it) {
+    const double fx[2] = {1.0 - X[0], X[0]}, fy[2] = {1.0 - X[1], X[1]}, fz[2] = {1.0 - X[2], X[2]};
+    double xk[3] = {0.0, 0.0, 0.0};
+    double J[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      const double a = fx[v & 1], b = fy[(v >> 1) & 1], c = fz[(v >> 2) & 1];
+      const double sa = (v & 1) ? 1.0 : -1.0, sb = ((v >> 1) & 1) ? 1.0 : -1.0, sc = ((v >> 2) & 1) ? 1.0 : -1.0;
+      const double ph = (a * b) * c;
+      const double g0 = (sa * b) * c, g1 = (a * sb) * c, g2 = (a * b) * sc;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const double vd = __ldg(&hv[3 * v + d]);
+        xk[d] += ph * vd;
+        J[d][0] += vd * g0;
+        J[d][1] += vd * g1;
+        J[d][2] += vd * g2;
+      }
+    }
+    const double r0 = p0 - xk[0], r1 = p1 - xk[1], r2 = p2 - xk[2];
+    const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+    const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+    const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    const double det = (J[0][0] * c00 + J[0][1] * c01) + J[0][2] * c02;
+    if (!(fabs(det) > 1e-300)) break;  // singular map: not converged
+    const double dX0 = ((c00 * r0 + (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * r1) + (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * r2) / det;
+    const double dX1 = ((c01 * r0 + (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * r1) + (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * r2) / det;
+    const double dX2 = ((c02 * r0 + (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * r1) + (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * r2) / det;
+    X[0] += dX0;
+    X[1] += dX1;
+    X[2] += dX2;
+    if ((dX0 * dX0 + dX1 * dX1) + dX2 * dX2 < kNewtonTol2) {
+      conv = 1;
+      break;
+    }
+  }
+  return HexX{X[0], X[1], X[2], conv};
+}
+
+// Squared distance of a point to a hexahedron in the sense of dolfinx's GJK test on the convex hull of the eight
+// vertices, for cells with planar faces: 0 when the Newton pull-back converges into the closed reference cube (the
+// trilinear image lies inside the hull), else the minimum over the twelve boundary triangles.  Returns -1 when the
+// point is outside the padded box (dolfinx point_in_bbox, slack 1e-14*extent): not a candidate.
+__device__ __noinline__ double hex_distance2(const double* __restrict__ hv, double p0, double p1, double p2, double padding) {
+  const double p[3] = {p0, p1, p2};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    double lo = __ldg(&hv[d]), hi = lo;
+#pragma unroll
+    for (int v = 1; v < 8; ++v) {
+      const double c = __ldg(&hv[3 * v + d]);
+      lo = fmin(lo, c);
+      hi = fmax(hi, c);
+    }
+    lo -= padding;
+    hi += padding;
+    const double eps = 1e-14 * (hi - lo);
+    if (!(p[d] >= lo - eps && p[d] <= hi + eps)) return -1.0;
+  }
+  const HexX r = hex_pull_back(hv, p0, p1, p2);
+  if (r.conv && r.X0 >= 0.0 && r.X0 <= 1.0 && r.X1 >= 0.0 && r.X1 <= 1.0 && r.X2 >= 0.0 && r.X2 <= 1.0) return 0.0;
+  // faces x=0, x=1, y=0, y=1, z=0, z=1, each as two triangles along a fixed diagonal
+  const int face[6][4] = {{0, 2, 6, 4}, {1, 3, 7, 5}, {0, 1, 5, 4}, {2, 3, 7, 6}, {0, 1, 3, 2}, {4, 5, 7, 6}};
+  double best = 1e300;
+  for (int f = 0; f < 6; ++f) {
+    double q[4][3];
+    for (int k = 0; k < 4; ++k)
+      for (int d = 0; d < 3; ++d) q[k][d] = __ldg(&hv[3 * face[f][k] + d]);
+    best = fmin(best, tri_dist2(p, q[0], q[1], q[2]));
+    best = fmin(best, tri_dist2(p, q[0], q[2], q[3]));
+  }
+  return best;
+}
+
 struct LocateResult {
   int cell;      // lowest colliding cell index, or nearest-cell fallback, or -1
   int ncoll;     // size of the colliding set
@@ -264,6 +353,21 @@ __device__ __forceinline__ void test_cell(const double* __restrict__ cellgeo, co
   far = far || ((X[1] < 0) && (X[1] * X[1] > t2));
   far = far || ((X[2] < 0) && (X[2] * X[2] > t3));
   const double d2 = far ? -1.0 : cell_distance2(x, cell_nodes, cell, p[0], p[1], p[2], padding);
+  if (d2 >= 0.0) {
+    if (d2 < kCollisionD2) {
+      st.best = min(st.best, cell);
+      ++st.ncoll;
+    } else if (d2 < st.fb_d2 || (d2 == st.fb_d2 && cell < st.fb_cell)) {
+      st.fb_d2 = d2;
+      st.fb_cell = cell;
+    }
+  }
+}
+
+// Leaf test of one candidate hexahedron: same bookkeeping as test_cell (no early exit: `done` stays false).
+__device__ __forceinline__ void test_cell_hex(const double* __restrict__ hexgeo, double padding, int cell, const double* p,
+                                              LocateState& st) {
+  const double d2 = hex_distance2(hexgeo + 24 * (int64_t)cell, p[0], p[1], p[2], padding);
   if (d2 >= 0.0) {
     if (d2 < kCollisionD2) {
       st.best = min(st.best, cell);
@@ -333,6 +437,7 @@ __device__ __forceinline__ void prefetch_l1(const void* ptr) { asm volatile("pre
 // LOWEST colliding cell index wins, independent of tree shape (north_star tie-break); the only early
 // exit is the provably final one: a point strictly inside a cell (by more than the collision distance)
 // cannot collide with any other cell of a mesh.
+template <bool HEX>
 __device__ LocateResult locate_point(const WideNode* __restrict__ nodes, const SceneGrid& grid,
                                      const double* __restrict__ cellgeo, const double* __restrict__ x,
                                      const int4* __restrict__ cell_nodes, double padding, const double* p,
@@ -357,9 +462,10 @@ __device__ LocateResult locate_point(const WideNode* __restrict__ nodes, const S
       if (kids[k] >= 0) {
         prefetch_l1(nodes + kids[k]);
       } else {
-        const double* g = cellgeo + 12 * (int64_t)(~kids[k]);
+        const double* g = cellgeo + (HEX ? 24 : 12) * (int64_t)(~kids[k]);
         prefetch_l1(g);
         prefetch_l1(g + 11);
+        if (HEX) prefetch_l1(g + 23);
       }
     }
     int next = -1;
@@ -371,7 +477,8 @@ __device__ LocateResult locate_point(const WideNode* __restrict__ nodes, const S
         else if (sp < kStack) stack[sp++] = kids[k];
         else *stack_overflow = 1ULL;  // a dropped subtree could hide the owning cell: reported, never silent
       } else if (!st.done) {
-        test_cell(cellgeo, x, cell_nodes, padding, tau2, ~kids[k], p, st);
+        if (HEX) test_cell_hex(cellgeo, padding, ~kids[k], p, st);
+        else test_cell(cellgeo, x, cell_nodes, padding, tau2, ~kids[k], p, st);
       }
     }
     if (st.done) break;
@@ -387,6 +494,7 @@ __device__ LocateResult locate_point(const WideNode* __restrict__ nodes, const S
 // and lanes vote with __ballot_sync on the children to descend into.  Results are identical to
 // locate_point.  All 32 lanes must call this (inactive lanes pass active=false).  Measured slower
 // than the per-thread walk on every BASELINE config (see packet_mode()).
+template <bool HEX>
 __device__ LocateResult locate_packet(const WideNode* __restrict__ nodes, const SceneGrid& grid,
                                       const double* __restrict__ cellgeo, const double* __restrict__ x,
                                       const int4* __restrict__ cell_nodes, double padding, const double* p, bool active,
@@ -412,7 +520,8 @@ __device__ LocateResult locate_packet(const WideNode* __restrict__ nodes, const 
         else if (sp < kStack) stack[sp++] = kids[k];
         else *stack_overflow = 1ULL;
       } else if (hit[k] && !st.done) {
-        test_cell(cellgeo, x, cell_nodes, padding, tau2, ~kids[k], p, st);
+        if (HEX) test_cell_hex(cellgeo, padding, ~kids[k], p, st);
+        else test_cell(cellgeo, x, cell_nodes, padding, tau2, ~kids[k], p, st);
       }
     }
     if (next >= 0) node = next;
@@ -463,6 +572,16 @@ __device__ __forceinline__ void make_point(int kind, const double* __restrict__ 
 template <int ND>
 __device__ __forceinline__ void tabulate_vals(const double* __restrict__ cellgeo, int cell, const double* p, double W,
                                               double S, double* vals) {
+  if (ND == 8) {  // Q1 on a hexahedron: Newton pull-back, tensor-product basis in vertex order v = i + 2j + 4k
+    const HexX r = hex_pull_back(cellgeo + 24 * (int64_t)cell, p[0], p[1], p[2]);
+    const double fx[2] = {1.0 - r.X0, r.X0}, fy[2] = {1.0 - r.X1, r.X1}, fz[2] = {1.0 - r.X2, r.X2};
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      const double phi = (fx[v & 1] * fy[(v >> 1) & 1]) * fz[(v >> 2) & 1];
+      vals[v % ND] = (phi * W) / S;
+    }
+    return;
+  }
   CellGeo g;
   load_cellgeo(cellgeo, cell, g);
   double X[3];
@@ -531,8 +650,8 @@ pi_locate_tabulate_kernel(const WideNode* __restrict__ nodes, const SceneGrid gr
     double p[3] = {0.0, 0.0, 0.0}, W = 1.0, S = 1.0;
     if (active) make_point(kind, frames + kFrame * r, s_tab, pts_in, w_in, s_in, r, l, pidx, p, W, S);
     LocateResult res{-1, 0, false};
-    if (packet == 1) res = locate_packet(nodes, grid, cellgeo, x, cell_nodes, padding, p, active, &counters->stack_overflow);
-    else if (active) res = locate_point(nodes, grid, cellgeo, x, cell_nodes, padding, p, &counters->stack_overflow);
+    if (packet == 1) res = locate_packet<ND == 8>(nodes, grid, cellgeo, x, cell_nodes, padding, p, active, &counters->stack_overflow);
+    else if (active) res = locate_point<ND == 8>(nodes, grid, cellgeo, x, cell_nodes, padding, p, &counters->stack_overflow);
     if (!active) continue;
     out_cell[pidx] = res.cell;
     out_ncoll[pidx] = (uint8_t)min(res.ncoll, 255);
@@ -1173,7 +1292,7 @@ pi_fused_kernel(const WideNode* __restrict__ nodes, const SceneGrid grid, const 
       // 12.2 -> 11.0 ms on the 1M-segment tree together with passing the point by value to the slow-path distance.
       // A batched walk that first collects candidate cells and tests them in a second loop measured 12.2 ms.)
       LocateResult res{-1, 0, false};
-      if (active) res = locate_point(nodes, grid, cellgeo, x, cell_nodes, padding, p, &counters->stack_overflow);
+      if (active) res = locate_point<ND == 8>(nodes, grid, cellgeo, x, cell_nodes, padding, p, &counters->stack_overflow);
       if (active) {
         out_cell[pidx] = res.cell;
         out_ncoll[pidx] = (uint8_t)min(res.ncoll, 255);
@@ -1581,6 +1700,7 @@ static void enqueue_fused(const fxii_space* sp, fxii_rows* rows, const FusedPlan
     FXII_CUDA(cudaGetLastError());
   };
   if (sp->nd == 4) launch(pi_fused_kernel<4, 0>);
+  else if (sp->nd == 8) launch(pi_fused_kernel<8, 0>);
   else launch(pi_fused_kernel<10, 0>);
   FXII_CUDA(cudaEventRecordWithFlags(ev[2], s, ev_flags));
   size_t tb = p.scan_tmp_bytes;
@@ -1610,6 +1730,9 @@ static void set_fused_attributes(const fxii_space* sp, const FusedPlan& p) {
   if (sp->nd == 4) {
     set(pi_fused_kernel<4, 0>);
     set(pi_fused_kernel<4, 2>);
+  } else if (sp->nd == 8) {
+    set(pi_fused_kernel<8, 0>);
+    set(pi_fused_kernel<8, 2>);
   } else {
     set(pi_fused_kernel<10, 0>);
     set(pi_fused_kernel<10, 2>);
@@ -1688,8 +1811,9 @@ static bool pi_assemble_coop(const fxii_space* sp, fxii_rows* rows, const FusedP
   FusedResult* hr = static_cast<FusedResult*>(rows->host_result);
   cudaEvent_t* ev = rows->ev;
   const int64_t n_groups = (rows->n_point_rows + p.rpb - 1) / p.rpb;
-  const int per_sm = sp->nd == 4 ? fused_blocks_per_sm(pi_fused_kernel<4, 2>, p.B, p.smem)
-                                 : fused_blocks_per_sm(pi_fused_kernel<10, 2>, p.B, p.smem);
+  const int per_sm = sp->nd == 4   ? fused_blocks_per_sm(pi_fused_kernel<4, 2>, p.B, p.smem)
+                     : sp->nd == 8 ? fused_blocks_per_sm(pi_fused_kernel<8, 2>, p.B, p.smem)
+                                   : fused_blocks_per_sm(pi_fused_kernel<10, 2>, p.B, p.smem);
   if (per_sm <= 0) return false;
   const int grid = (int)std::min<int64_t>(std::min<int64_t>(n_groups, (int64_t)per_sm * num_sms()), p.max_grid);
   const int64_t hint = rows->nnz_hint;
@@ -1761,7 +1885,9 @@ static bool pi_assemble_coop(const fxii_space* sp, fxii_rows* rows, const FusedP
   FXII_CUDA(cudaMemsetAsync(ws, 0, p.ws_bytes, s));
   FXII_CUDA(cudaEventRecord(ev[1], s));
   g_hostprof.lap(1);
-  const void* fn = sp->nd == 4 ? (const void*)pi_fused_kernel<4, 2> : (const void*)pi_fused_kernel<10, 2>;
+  const void* fn = sp->nd == 4   ? (const void*)pi_fused_kernel<4, 2>
+                   : sp->nd == 8 ? (const void*)pi_fused_kernel<8, 2>
+                                 : (const void*)pi_fused_kernel<10, 2>;
   const cudaError_t le = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(p.B), args, p.smem, s);
   if (le != cudaSuccess) {  // e.g. a shared device that cannot hold the wave: use the multi-kernel path
     cudaGetLastError();
@@ -2005,6 +2131,11 @@ void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr
       const int4* cn = reinterpret_cast<const int4*>(m->cell_nodes.p);
       if (nd == 4)
         { pi_locate_tabulate_kernel<4><<<grid, threads, smem, s>>>(
+            m->wnodes.p, m->grid, m->cellgeo.p, m->x.p, cn, m->padding, sp->dofmap.p, rows->frames.p, rows->table.p, rows->w.p,
+            rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, nq, (rows->kind != FXII_OP_POINTS) ? packet_mode() : 0, Np, rows->cell.p, rows->ncoll.p, rows->points.p,
+            rows->coo_cols.p, rows->coo_vals.p, counters.p); FXII_LAUNCHED(1); }
+      else if (nd == 8)
+        { pi_locate_tabulate_kernel<8><<<grid, threads, smem, s>>>(
             m->wnodes.p, m->grid, m->cellgeo.p, m->x.p, cn, m->padding, sp->dofmap.p, rows->frames.p, rows->table.p, rows->w.p,
             rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, nq, (rows->kind != FXII_OP_POINTS) ? packet_mode() : 0, Np, rows->cell.p, rows->ncoll.p, rows->points.p,
             rows->coo_cols.p, rows->coo_vals.p, counters.p); FXII_LAUNCHED(1); }

@@ -92,9 +92,11 @@ def allgatherv_csr(indptr, indices, values, group=None, packed: "bool | None" = 
     NCCL has no all-gather-v.  The shard sizes come from `plan` (``plan_allgatherv``; built here — one small
     all-gather and one host read — when absent or stale); then
 
-    * packed (default while the padded exchange stays below 32 MiB, i.e. latency bound): row pointers, values and
-      indices of a shard travel as ONE byte record padded to the largest shard — a single all-gather — and are
-      sliced out of the received records (24 small broadcasts cost 3.4 ms on 8 GPUs for 3 MB shards);
+    * packed (default unless a shard is more than 25 % smaller than the largest): row pointers, values and indices of
+      a shard travel as ONE byte record padded to the largest shard — a single ``all_gather_into_tensor`` — and are
+      copied out of the received records.  Measured on 8 B200 for the 84.3 M entries of config 5 (0.885 GB received
+      per rank, profiles/r02_gather_variants_n8.txt): 2.36 ms including the unpack copies, against 3.61 ms for
+      per-shard broadcasts written in place (``all_gather`` with uneven views) and 3.19 ms for grouped send/recv;
     * otherwise every shard goes straight into its slice of the preallocated result (no padding, no copies).
 
     Row pointers are shifted by the shard's entry offset BEFORE they travel, so the gathered pointer array needs
@@ -108,31 +110,34 @@ def allgatherv_csr(indptr, indices, values, group=None, packed: "bool | None" = 
         plan = plan_allgatherv(m, n, dev, group)
     world, rank = plan.world, plan.rank
     max_rows, max_nnz = int(plan.rows.max()), int(plan.nnzs.max())
-    if packed is None:  # small exchanges only (latency bound); large shards go straight into place, unpadded
-        packed = 12 * max_nnz * world <= (32 << 20)
-    shifted = indptr[1:] + int(plan.nnz_off[rank])  # global row ends of this shard
+    if packed is None:  # padding waste bounded: balanced shards (the normal case) always take the single collective
+        packed = 4 * int(plan.nnzs.min()) >= 3 * max_nnz and 4 * int(plan.rows.min()) >= 3 * max_rows
     g_indptr = torch.empty(plan.n_rows + 1, dtype=torch.int64, device=dev)
     g_indptr[:1] = 0
+    g_indices = torch.empty(plan.nnz, dtype=torch.int32, device=dev)
+    g_values = torch.empty(plan.nnz, dtype=torch.float64, device=dev)
     if packed:
         def pad16(k):
             return (k + 15) // 16 * 16
 
-        o_val = pad16(8 * max_rows)
-        o_idx = o_val + pad16(8 * max_nnz)
+        o_ptr = pad16(8 * max_nnz)
+        o_idx = o_ptr + pad16(8 * max_rows)
         rec = o_idx + pad16(4 * max_nnz)
-        send = torch.zeros(rec, dtype=torch.uint8, device=dev)
-        send[: 8 * m].view(torch.int64).copy_(shifted)
-        send[o_val:o_val + 8 * n].view(torch.float64).copy_(values)
+        send = torch.empty(rec, dtype=torch.uint8, device=dev)  # padding bytes are never read
+        send[: 8 * n].view(torch.float64).copy_(values)
+        torch.add(indptr[1:], int(plan.nnz_off[rank]), out=send[o_ptr:o_ptr + 8 * m].view(torch.int64))  # global row ends
         send[o_idx:o_idx + 4 * n].view(torch.int32).copy_(indices)
         recv = torch.empty(world * rec, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(recv, send, group=group)
         recv = recv.view(world, rec)
-        g_indptr[1:] = torch.cat([recv[r, : 8 * int(plan.rows[r])].view(torch.int64) for r in range(world)])
-        g_values = torch.cat([recv[r, o_val:o_val + 8 * int(plan.nnzs[r])].view(torch.float64) for r in range(world)])
-        g_indices = torch.cat([recv[r, o_idx:o_idx + 4 * int(plan.nnzs[r])].view(torch.int32) for r in range(world)])
+        for r in range(world):
+            mr, nr = int(plan.rows[r]), int(plan.nnzs[r])
+            r0, e0 = int(plan.row_off[r]), int(plan.nnz_off[r])
+            g_values[e0:e0 + nr].copy_(recv[r, : 8 * nr].view(torch.float64))
+            g_indptr[1 + r0:1 + r0 + mr].copy_(recv[r, o_ptr:o_ptr + 8 * mr].view(torch.int64))
+            g_indices[e0:e0 + nr].copy_(recv[r, o_idx:o_idx + 4 * nr].view(torch.int32))
     else:
-        g_indices = torch.empty(plan.nnz, dtype=torch.int32, device=dev)
-        g_values = torch.empty(plan.nnz, dtype=torch.float64, device=dev)
+        shifted = indptr[1:] + int(plan.nnz_off[rank])  # global row ends of this shard
         _gatherv_into(g_indptr[1:], plan.row_off, shifted, plan, group)
         _gatherv_into(g_indices, plan.nnz_off, indices, plan, group)
         _gatherv_into(g_values, plan.nnz_off, values, plan, group)
@@ -151,17 +156,23 @@ def allgatherv_vector(v, group=None):
     return out
 
 
-def balanced_dof_windows(indices_t, n_cols: int, world: int):
-    """Contiguous ranges of 3D dofs (columns of the gathered Π) with equal numbers of Π entries — a
-    proxy for equal SpGEMM work (intermediate products of row j of Πᵀ ~ entries in column j of Π).
-    Every rank computes the same boundaries from the same gathered matrix.  (One host read: done once per Γ and
-    kept in the ``ProductPlan``.)"""
+def balanced_dof_windows(indices_t, n_cols: int, world: int, indptr_t=None):
+    """Contiguous ranges of 3D dofs (columns of the gathered Π) of equal SpGEMM work.  The work of row j of
+    C = Πᵀ(MΠ) is its number of intermediate products, the sum of the lengths of the Π rows with an entry in column j
+    (`indptr_t` given), or, as a proxy, the number of entries in column j.  Every rank computes the same boundaries
+    from the same gathered matrix.  (One host read: done once per Γ and kept in the ``ProductPlan``.)"""
     import torch
 
     if world == 1:
         return [(0, n_cols)]
-    counts = torch.bincount(indices_t, minlength=n_cols)  # int32 input: no 64-bit copy of the gathered indices
-    cum = torch.cumsum(counts, 0)
+    if indptr_t is None:
+        counts = torch.bincount(indices_t, minlength=n_cols)  # int32 input: no 64-bit copy of the gathered indices
+        cum = torch.cumsum(counts, 0)
+    else:
+        row_len = (indptr_t[1:] - indptr_t[:-1]).to(torch.int32)
+        w = torch.repeat_interleave(row_len, row_len.to(torch.int64)).to(torch.float64)  # length of the row of every entry
+        cum = torch.cumsum(torch.bincount(indices_t, weights=w, minlength=n_cols), 0).to(torch.int64)
+        del w
     total = int(cum[-1].item())
     targets = torch.tensor([total * (r + 1) // world for r in range(world - 1)], device=cum.device, dtype=cum.dtype)
     cuts = torch.searchsorted(cum, targets, right=False).add_(1).clamp_(max=n_cols).cpu().tolist()
@@ -248,7 +259,7 @@ class ShardedProducts:
         else:
             ptr, idx, val = pi_local.device_tensors()
             g_ptr, g_idx, g_val, gplan = allgatherv_csr(ptr, idx, val, group=self.group, return_plan=True)
-            plan = ProductPlan(gplan, balanced_dof_windows(g_idx, self.n_dofs, self.world))
+            plan = ProductPlan(gplan, balanced_dof_windows(g_idx, self.n_dofs, self.world, indptr_t=g_ptr))
             del g_ptr, g_idx, g_val
         t1.record()
         torch.cuda.synchronize()

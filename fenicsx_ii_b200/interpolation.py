@@ -31,7 +31,7 @@ class PiStats(dict):
 
 
 class DeviceMesh:
-    """Ω on the device: packed cell geometry + LBVH.  Built once per (mesh, tol) and cached on the
+    """Ω on the device (affine tetrahedra or Q1 hexahedra): packed cell geometry + LBVH.  Built once per (mesh, tol) and cached on the
     mesh object — the reference rebuilds dolfinx's tree on every call (interpolation.py:66-68)."""
 
     def __init__(self, x: np.ndarray, cells: np.ndarray, padding: float, stream: int | None = None):
@@ -40,15 +40,15 @@ class DeviceMesh:
         cells = np.ascontiguousarray(cells, dtype=np.int32)
         if x.ndim != 2 or x.shape[1] != 3:
             raise ValueError("mesh.geometry.x must have shape (n, 3)")
-        if cells.ndim != 2 or cells.shape[1] != 4:
-            raise NotImplementedError("only affine tetrahedra (4 geometry nodes per cell) are supported")
+        if cells.ndim != 2 or cells.shape[1] not in (4, 8):
+            raise NotImplementedError("only affine tetrahedra (4 geometry nodes) and Q1 hexahedra (8 geometry nodes) are supported")
         if cells.size and (cells.min() < 0 or cells.max() >= x.shape[0]):
             raise ValueError("cell node index out of range")
         self.n_cells, self.n_nodes, self.padding = cells.shape[0], x.shape[0], float(padding)
         out = C.c_void_p()
         s = _lib.current_stream() if stream is None else stream
-        _lib.check(_lib.load().fxii_mesh_create(_lib.ptr(x), x.shape[0], _lib.ptr(cells), cells.shape[0], float(padding), s,
-                                                C.byref(out)))
+        _lib.check(_lib.load().fxii_mesh_create_cells(_lib.ptr(x), x.shape[0], _lib.ptr(cells), cells.shape[0], cells.shape[1],
+                                                      float(padding), s, C.byref(out)))
         self._h = out
 
     def info(self) -> dict:

@@ -68,12 +68,18 @@ int fxii_trim_memory(void);
  * padding: AABB padding of determine_point_ownership (tol of interpolation.py:19). */
 int fxii_mesh_create(const double* x, int64_t n_nodes, const int32_t* cell_nodes, int64_t n_cells,
                      double padding, void* stream, fxii_mesh** out);
+/* The same for cells with `nodes_per_cell` geometry nodes: 4 = affine tetrahedra, 8 = hexahedra with Q1 geometry,
+ * vertices in dolfinx's tensor-product order v = i + 2j + 4k.  Hexahedra are pulled back by Newton's method
+ * (interpolation_utils.py:36-38 with a non-affine cmap; tests/test_interpolation_matrix.py:31-34); ownership is the
+ * collision with the convex hull of the eight vertices (cells with planar faces). */
+int fxii_mesh_create_cells(const double* x, int64_t n_nodes, const int32_t* cell_nodes, int64_t n_cells,
+                           int32_t nodes_per_cell, double padding, void* stream, fxii_mesh** out);
 int fxii_mesh_info(const fxii_mesh* m, int64_t* n_cells, int64_t* n_nodes, int64_t* device_bytes,
                    int32_t* max_depth);
 int fxii_mesh_destroy(fxii_mesh* m);
 
 /* ---- V space ----------------------------------------------------------------------------- */
-/* dofmap: [n_cells, nd] i32 with nd = 4 (degree 1) or 10 (degree 2), basix dof order. */
+/* dofmap: [n_cells, nd] i32, basix dof order: tetrahedra nd = 4 (degree 1) or 10 (degree 2); hexahedra nd = 8 (Q1). */
 int fxii_space_create(fxii_mesh* mesh, const int32_t* dofmap, int32_t nd, int32_t degree,
                       int64_t n_dofs, void* stream, fxii_space** out);
 int fxii_space_destroy(fxii_space* s);

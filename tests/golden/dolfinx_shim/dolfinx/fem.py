@@ -27,7 +27,11 @@ class Expression:
             return v[:, None, :, :]
         if isinstance(self.e, ufl.TestFunction):  # interpolation_utils.py:63-74 -> [cells, points, dofs]
             V = self.e.V
-            phi = orc.tabulate(V.element.degree, self.X)
+            if V.mesh.geometry.dofmap.shape[1] == 8:  # hexahedron: Q1
+                assert V.element.degree == 1
+                phi = orc.q1_tabulate(self.X)
+            else:
+                phi = orc.tabulate(V.element.degree, self.X)
             bs = V.dofmap.bs
             if bs == 1:
                 return np.broadcast_to(phi[None, :, :], (len(cells),) + phi.shape).copy()

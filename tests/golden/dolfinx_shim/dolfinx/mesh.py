@@ -15,8 +15,12 @@ class _CMap:
         from oracle import pi_oracle as orc
 
         cg = np.asarray(cell_geometry, dtype=np.float64)
+        x = np.asarray(x, dtype=np.float64)
+        if cg.shape[0] == 8:  # hexahedron: non-affine pull-back by Newton's method
+            X, _ = orc.pull_back_hex(np.repeat(cg[None, :, :], x.shape[0], axis=0), x)
+            return X
         v0, K = orc.cell_jacobian_inverse(cg, np.arange(4).reshape(1, 4))
-        return orc.pull_back(v0, K, np.zeros(x.shape[0], dtype=np.int64), np.asarray(x, dtype=np.float64))
+        return orc.pull_back(v0, K, np.zeros(x.shape[0], dtype=np.int64), x)
 
 
     def push_forward(self, X, cell_geometry):

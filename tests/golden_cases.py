@@ -28,6 +28,12 @@ CASES = {
     "trace_blocked3_dg2": dict(n=(4, 4, 4), p=1, bs=3, gamma=("network", 24, 1 / 4, 2), K=("DG", 2), op=("trace",)),
     "circle_blocked2_p1k_firstvisit": dict(n=(4, 4, 4), p=1, bs=2, gamma=("network", 24, 1 / 4, 2), K=("Lagrange", 1),
                                            op=("circle", 0.05, 5)),
+    # hexahedra (tests/test_interpolation_matrix.py:31-34): Q1 on boxes with the line on mesh edges, and on tapered
+    # (non-affine, planar-faced) cells where the pull-back is a genuine Newton iteration
+    "trace_hex_line_on_edges": dict(n=(4, 4, 8), p=1, hex=0.0, gamma=("line", 9), K=("Quadrature", 10), op=("trace",)),
+    "circle_hex_tapered_dg1": dict(n=(5, 5, 5), p=1, hex=0.3, gamma=("network", 40, 1 / 5, 2), K=("DG", 1), op=("circle", 0.05, 7)),
+    "disk_hex_tapered_p1k_firstvisit": dict(n=(5, 6, 4), p=1, hex=-0.2, gamma=("network", 40, 1 / 5, 2), K=("Lagrange", 1),
+                                            op=("disk", 0.04, 3)),
 }
 
 
@@ -45,9 +51,11 @@ def load_case(name):
     itself so the test does not depend on the generator's random stream."""
     spec = CASES[name]
     fx = np.load(os.path.join(GOLDEN_DIR, f"pi_{name}.npz"))
-    mesh = sy.kuhn_box(*spec["n"])
+    mesh = sy.hex_box(*spec["n"], taper=spec["hex"]) if "hex" in spec else sy.kuhn_box(*spec["n"])
     bs = spec.get("bs", 1)
-    if bs > 1:
+    if "hex" in spec:
+        V = functionspace(mesh, ("Lagrange", 1))
+    elif bs > 1:
         V = functionspace(mesh, ("Lagrange", spec["p"], (bs,)))
     else:
         V = functionspace(mesh, ("Lagrange", 1)) if spec["p"] == 1 else sy.kuhn_p2_space(mesh)

@@ -87,3 +87,28 @@ def test_balanced_dof_windows_cover_and_balance():
         assert sum(loads) == idx.numel()
         if world > 1:
             assert max(loads) <= 1.3 * idx.numel() / world + 600
+
+
+def test_balanced_dof_windows_by_intermediate_products():
+    """With the row pointers given the windows balance the SpGEMM work (sum over a column's entries of the length of
+    their rows), not the entry counts."""
+    from fenicsx_ii_b200.distributed import balanced_dof_windows
+
+    rng = np.random.default_rng(3)
+    n_rows, n_cols = 4000, 3000
+    # rows touching the low columns are 10x longer than the rows touching the high columns
+    lens = np.where(np.arange(n_rows) < n_rows // 2, 40, 4)
+    cols = [np.sort(rng.choice(n_cols // 2, size=k, replace=False)) + (0 if i < n_rows // 2 else n_cols // 2)
+            for i, k in enumerate(lens)]
+    indptr = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64))
+    idx = torch.from_numpy(np.concatenate(cols).astype(np.int32))
+    work = np.zeros(n_cols)
+    np.add.at(work, idx.numpy(), np.repeat(lens, lens))
+    for world in (2, 3, 8):
+        w = balanced_dof_windows(idx, n_cols, world, indptr_t=indptr)
+        assert w[0][0] == 0 and w[-1][1] == n_cols and all(a[1] == b[0] for a, b in zip(w[:-1], w[1:]))
+        loads = np.array([work[a:b].sum() for a, b in w])
+        assert loads.max() <= 1.15 * work.sum() / world + work.max()
+        by_count = balanced_dof_windows(idx, n_cols, world)
+        loads_c = np.array([work[a:b].sum() for a, b in by_count])
+        assert loads.max() <= loads_c.max() + 1e-9

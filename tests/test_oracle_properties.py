@@ -195,3 +195,50 @@ def test_oracle_products_on_a_reference_generated_pi():
     np.testing.assert_allclose(C.toarray(), C.toarray().T, rtol=1e-13, atol=1e-16)
     live = np.diff(ip_) > 0  # rows of cells outside cells_K are empty
     np.testing.assert_allclose(C @ np.ones(n_cols), P.T @ (mdiag * live), rtol=1e-12, atol=1e-15)
+
+
+def test_cells_near_points_is_complete():
+    """The sub-mesh around a sample of points reproduces the full-mesh location exactly (owner, colliding-set size),
+    for tetrahedra and hexahedra, including points on cell boundaries."""
+    from fenicsx_ii_b200 import synthetic as sy
+
+    rng = np.random.default_rng(5)
+    for mesh in (sy.kuhn_box(10, 9, 8), sy.hex_box(7, 8, 6, taper=0.2)):
+        x, cells = mesh.geometry.x, mesh.geometry.dofmap
+        pts = np.vstack([rng.uniform(0.2, 0.45, size=(300, 3)), x[rng.choice(x.shape[0], 40)]])  # interior + mesh vertices
+        pts[:, :2] *= 1.0 if cells.shape[1] == 4 else (1.0 + 0.2 * pts[:, 2:3])
+        sel = orc.cells_near_points(x, cells, pts)
+        assert sel.shape[0] <= cells.shape[0] and (np.diff(sel) > 0).all()
+        c_full, n_full = orc.GridLocator(x, cells).locate(pts)
+        c_sub, n_sub = orc.GridLocator(x, cells[sel]).locate(pts)
+        found = c_full >= 0
+        np.testing.assert_array_equal(found, c_sub >= 0)
+        np.testing.assert_array_equal(sel[c_sub[found]], c_full[found])
+        np.testing.assert_array_equal(n_sub, n_full)
+
+
+def test_hex_oracle_newton_and_ownership():
+    """Hexahedra in the oracle: the Newton pull-back inverts the trilinear map on tapered cells, ownership agrees with a
+    brute-force search over all cells, and an isoparametric Q1 space reproduces linear functions."""
+    from fenicsx_ii_b200 import synthetic as sy
+
+    rng = np.random.default_rng(2)
+    mesh = sy.hex_box(5, 4, 6, taper=0.3)
+    x, cells = mesh.geometry.x, mesh.geometry.dofmap
+    c = rng.integers(0, cells.shape[0], 500)
+    X = rng.uniform(0, 1, (500, 3))
+    X[:60] = np.round(X[:60])  # cell vertices: ties between up to eight cells
+    pts = np.einsum("nv,nvd->nd", orc.q1_tabulate(X), x[cells[c]])
+    Xb, conv = orc.pull_back_hex(x[cells[c]], pts)
+    assert conv.all()
+    np.testing.assert_allclose(Xb, X, rtol=0, atol=1e-13)
+    owner, ncoll = orc.GridLocator(x, cells).locate(pts)
+    # brute force: distance of every point to every cell
+    for i in range(0, 500, 25):
+        d2 = orc.point_hex_distance2(x, cells, np.arange(cells.shape[0]), np.repeat(pts[i:i + 1], cells.shape[0], axis=0))
+        hit = np.nonzero(d2 < orc.COLLISION_D2)[0]
+        assert owner[i] == hit.min() and ncoll[i] == hit.size and c[i] in hit
+    phi = orc.q1_tabulate(Xb)
+    u = 0.3 * x[:, 0] - 1.7 * x[:, 1] + 0.5 * x[:, 2] + 2.0
+    np.testing.assert_allclose(np.einsum("nv,nv->n", phi, u[cells[c]]), 0.3 * pts[:, 0] - 1.7 * pts[:, 1] + 0.5 * pts[:, 2] + 2.0,
+                               rtol=0, atol=1e-13)
