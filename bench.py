@@ -249,10 +249,14 @@ def run_ours(args):
     stage = {k: 0.0 for k in pi_keys + prod_keys}
     stage["pi_ms"] = 0.0
     launches = 0
+    from fenicsx_ii_b200 import distributed as fdist
+
+    gather_parts = np.zeros(3)
     for a, b in ev:
         flush.zero_()  # L2 flush between timed iterations, outside the event pair
         if world > 1:
             dist.barrier()
+            fdist.GATHER_TRACE = []
         l0 = lib.fxii_launch_count()
         pe = []
         a.record()
@@ -260,6 +264,10 @@ def run_ours(args):
         b.record()
         launches += lib.fxii_launch_count() - l0
         torch.cuda.synchronize()
+        if world > 1 and fdist.GATHER_TRACE and len(fdist.GATHER_TRACE) >= 4:
+            g = fdist.GATHER_TRACE
+            gather_parts += np.array([g[0].elapsed_time(g[1]), g[1].elapsed_time(g[2]), g[2].elapsed_time(g[3])])
+        fdist.GATHER_TRACE = None
         for k in pi_keys:
             stage[k] += st[k]
         if pe:
@@ -277,6 +285,18 @@ def run_ours(args):
     if out is not None:
         c_mat, mp_mat, ip, nnz_a, ip_mp = out
         c_nnz, mp_nnz = int(c_mat.nnz), int(mp_mat.nnz) if mp_mat is not None else 0
+    # per-rank view of the stages that wait on other ranks (diagnostics of the scaling curve)
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([stage["pi_ms"] / args.steps, stage["allgather_ms"] / args.steps, stage["spgemm_ms"] / args.steps,
+                             stage["transpose_ms"] / args.steps, float(nnz_local), float(c_nnz), float(ip)] + list(gather_parts / args.steps),
+                            device="cuda", dtype=torch.float64)
+        allr = torch.empty(world * mine.numel(), device="cuda", dtype=torch.float64)
+        dist.all_gather_into_tensor(allr, mine)
+        allr = allr.view(world, -1).cpu().numpy()
+        names = ("pi_ms", "allgather_ms", "spgemm_ms", "transpose_ms", "nnz_pi", "nnz_c", "ip_c", "gather_pack_ms", "gather_nccl_ms",
+                 "gather_unpack_ms")
+        per_rank = {n: [round(float(v), 3) for v in allr[:, i]] for i, n in enumerate(names)}
     # max over ranks of the times; sum over ranks of the work
     keys = sorted(stage)
     t_all = torch.tensor([total_ms] + [stage[k] for k in keys], device="cuda", dtype=torch.float64)
@@ -392,6 +412,7 @@ def run_ours(args):
                     "rows_per_gpu": int(n_rows_local), "nnz_pi_global": int(nnz_total), "nnz_c_global": int(c_total),
                     "nnz_mp_global": int(mp_total), "ip_c_global": int(ip_total)},
             "stage_ms": stage_ms,
+            "per_rank": per_rank,
             "pi": {"ms": pi_ms, "nnz_per_s": nnz_total / (pi_ms * 1e-3) if pi_ms > 0 else None,
                    "points_per_s": np_total / (pi_ms * 1e-3) if pi_ms > 0 else None},
             "products": ({"pit_m_pi_s": (stage_ms["allgather_ms"] + stage_ms["transpose_ms"] + stage_ms["spgemm_ms"]) * 1e-3,

@@ -178,6 +178,37 @@ void cache_trim() {
 }
 }  // namespace fxii
 
+namespace fxii {
+// the live block of the library's allocator that contains p (nullptr: not ours)
+void* alloc_base_of(const void* p) {
+  std::lock_guard<std::mutex> lock(g_mem_mutex);
+  for (const auto& kv : g_live) {
+    const char* b = static_cast<const char*>(kv.first);
+    if (static_cast<const char*>(p) >= b && static_cast<const char*>(p) < b + kv.second.second) return kv.first;
+  }
+  return nullptr;
+}
+}  // namespace fxii
+
+namespace fxii {
+// SM copy: peer (NVLink-mapped) or local source -> local destination, four independent vector loads per thread in
+// flight.  A copy-engine cudaMemcpyAsync out of an IPC-mapped peer allocation reached ~130 GB/s on this pool (2 GPUs,
+// 0.47 GB: 3.5 ms); loads issued from all SMs keep enough bytes in flight to fill the link.
+template <typename T>
+__global__ void __launch_bounds__(256) peer_copy_kernel(T* __restrict__ dst, const T* __restrict__ src, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    const T a = src[i], b = src[i + stride], c = src[i + 2 * stride], d = src[i + 3 * stride];
+    dst[i] = a;
+    dst[i + stride] = b;
+    dst[i + 2 * stride] = c;
+    dst[i + 3 * stride] = d;
+  }
+  for (; i < n; i += stride) dst[i] = src[i];
+}
+}  // namespace fxii
+
 template <typename F>
 static int guarded(F&& f) {
   try {
@@ -581,6 +612,67 @@ int fxii_csr_validate(const fxii_csr* a, void* stream) {
   return guarded([&] {
     FXII_CHECK(a, "null csr");
     fxii::csr_validate(a, S(stream));
+  });
+}
+
+// ---- peer-to-peer exchange of device arrays between the ranks of one node (CUDA IPC over NVLink) ---------------
+
+int fxii_alloc_base(const void* dev_ptr, void** base) {
+  return guarded([&] {
+    FXII_CHECK(base, "null argument");
+    *base = dev_ptr ? fxii::alloc_base_of(dev_ptr) : nullptr;
+  });
+}
+
+int fxii_ipc_export(const void* base_ptr, unsigned char* handle64) {
+  return guarded([&] {
+    FXII_CHECK(base_ptr && handle64, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    if (fxii::alloc_base_of(base_ptr) != base_ptr)
+      throw fxii::Error(FXII_E_UNSUPPORTED, "fxii_ipc_export: not the base of a block of this library's allocator");
+    cudaIpcMemHandle_t h;
+    FXII_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(base_ptr)));
+    memcpy(handle64, &h, 64);
+  });
+}
+
+int fxii_ipc_open(const unsigned char* handle64, void** dev_ptr) {
+  return guarded([&] {
+    FXII_CHECK(handle64 && dev_ptr, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    FXII_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  });
+}
+
+int fxii_ipc_close(void* dev_ptr) {
+  return guarded([&] {
+    if (dev_ptr) FXII_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  });
+}
+
+
+int fxii_copy_dev_async(void* dst_dev, const void* src_dev, int64_t bytes, void* stream) {
+  return guarded([&] {
+    FXII_CHECK(bytes >= 0 && (bytes == 0 || (dst_dev && src_dev)), "bad argument");
+    if (bytes == 0) return;
+    const uintptr_t al = (uintptr_t)dst_dev | (uintptr_t)src_dev | (uintptr_t)bytes;
+    const int grid = fxii::num_sms() * 8;
+    if (bytes < (1 << 20)) {
+      FXII_CUDA(cudaMemcpyAsync(dst_dev, src_dev, (size_t)bytes, cudaMemcpyDefault, S(stream)));
+    } else if ((al & 15) == 0) {
+      fxii::peer_copy_kernel<uint4><<<grid, 256, 0, S(stream)>>>((uint4*)dst_dev, (const uint4*)src_dev, bytes / 16);
+      FXII_LAUNCHED(1);
+    } else if ((al & 7) == 0) {
+      fxii::peer_copy_kernel<uint2><<<grid, 256, 0, S(stream)>>>((uint2*)dst_dev, (const uint2*)src_dev, bytes / 8);
+      FXII_LAUNCHED(1);
+    } else if ((al & 3) == 0) {
+      fxii::peer_copy_kernel<uint32_t><<<grid, 256, 0, S(stream)>>>((uint32_t*)dst_dev, (const uint32_t*)src_dev, bytes / 4);
+      FXII_LAUNCHED(1);
+    } else {
+      FXII_CUDA(cudaMemcpyAsync(dst_dev, src_dev, (size_t)bytes, cudaMemcpyDefault, S(stream)));
+    }
+    FXII_CUDA(cudaGetLastError());
   });
 }
 

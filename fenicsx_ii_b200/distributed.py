@@ -83,6 +83,10 @@ def _gatherv_into(out, off, local, plan: GatherPlan, group):
         w.wait()
 
 
+# diagnostics: set to a list to receive CUDA events [start, packed, gathered, unpacked] of every packed exchange
+GATHER_TRACE = None
+
+
 def allgatherv_csr(indptr, indices, values, group=None, packed: "bool | None" = None, plan: "GatherPlan | None" = None,
                    return_plan: bool = False):
     """All-gather row-sharded CSR arrays (torch tensors on the collective's device).
@@ -116,6 +120,15 @@ def allgatherv_csr(indptr, indices, values, group=None, packed: "bool | None" = 
     g_indptr[:1] = 0
     g_indices = torch.empty(plan.nnz, dtype=torch.int32, device=dev)
     g_values = torch.empty(plan.nnz, dtype=torch.float64, device=dev)
+    trace = GATHER_TRACE if dev.type == "cuda" else None
+
+    def mark():
+        if trace is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            trace.append(e)
+
+    mark()
     if packed:
         def pad16(k):
             return (k + 15) // 16 * 16
@@ -128,7 +141,9 @@ def allgatherv_csr(indptr, indices, values, group=None, packed: "bool | None" = 
         torch.add(indptr[1:], int(plan.nnz_off[rank]), out=send[o_ptr:o_ptr + 8 * m].view(torch.int64))  # global row ends
         send[o_idx:o_idx + 4 * n].view(torch.int32).copy_(indices)
         recv = torch.empty(world * rec, dtype=torch.uint8, device=dev)
+        mark()
         dist.all_gather_into_tensor(recv, send, group=group)
+        mark()
         recv = recv.view(world, rec)
         for r in range(world):
             mr, nr = int(plan.rows[r]), int(plan.nnzs[r])
@@ -136,6 +151,7 @@ def allgatherv_csr(indptr, indices, values, group=None, packed: "bool | None" = 
             g_values[e0:e0 + nr].copy_(recv[r, : 8 * nr].view(torch.float64))
             g_indptr[1 + r0:1 + r0 + mr].copy_(recv[r, o_ptr:o_ptr + 8 * mr].view(torch.int64))
             g_indices[e0:e0 + nr].copy_(recv[r, o_idx:o_idx + 4 * nr].view(torch.int32))
+        mark()
     else:
         shifted = indptr[1:] + int(plan.nnz_off[rank])  # global row ends of this shard
         _gatherv_into(g_indptr[1:], plan.row_off, shifted, plan, group)
@@ -144,6 +160,131 @@ def allgatherv_csr(indptr, indices, values, group=None, packed: "bool | None" = 
     if return_plan:
         return g_indptr, g_indices, g_values, plan
     return g_indptr, g_indices, g_values
+
+
+class PeerGather:
+    """All-gather-v of the row shards of a ``DeviceCSR`` as direct peer-to-peer copies over NVLink (one node).
+
+    Every rank exports CUDA IPC handles of its three CSR arrays; the peers map them once (re-mapping only when a
+    pointer changes — the library's allocator hands the same blocks back to equally sized builds) and then PULL every
+    shard straight into its slice of the gathered arrays with ``cudaMemcpyAsync``: no padding, no staging copies, the
+    copy engines at NVLink rate (770 GB/s peer copy measured on this pool against ~430-475 GB/s for the NCCL all-gather
+    plus its pack/unpack copies).  Ordering: a rank enters after its own build has synchronised, so once the (tiny)
+    pointer all-gather has been read on the host every peer's shard is complete; a closing all-reduce on the stream keeps
+    any rank from releasing its shard before all peers have copied it.  Any failure (IPC not permitted, no peer access)
+    disables the path for the process and the caller falls back to the NCCL exchange."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.enabled = True
+        self.seen = set()       # (rank, block base) whose handle has been exchanged (the same set on every rank)
+        self.mapped = {}        # (peer rank, block base on the peer) -> local mapping
+
+    def _fail(self, why):
+        import warnings
+
+        self.enabled = False
+        warnings.warn(f"peer-to-peer gather disabled, using NCCL: {why}")
+
+    def gather(self, pi_local, plan: GatherPlan):
+        """Returns (g_indptr, g_indices, g_values) torch tensors, or None when the path is unavailable (disabled, or
+        some rank's arrays do not live in blocks of the library's allocator, e.g. torch tensors: this call then goes
+        through NCCL)."""
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+
+        if not self.enabled:
+            return None
+        lib = _lib.load()
+        world, rank = plan.world, plan.rank
+        dev = torch.device("cuda", torch.cuda.current_device())
+        p = [C.c_void_p(), C.c_void_p(), C.c_void_p()]
+        _lib.check(lib.fxii_csr_device_ptrs(pi_local._h, C.byref(p[0]), C.byref(p[1]), C.byref(p[2])))
+        row = []
+        for a, v in enumerate(p):  # (block base, offset) per array; base 0: not exportable
+            ptr = int(v.value or 0)
+            base = C.c_void_p()
+            if ptr:
+                _lib.check(lib.fxii_alloc_base(C.c_void_p(ptr), C.byref(base)))
+            b = int(base.value or 0)
+            empty = (plan.nnzs[rank] == 0 and a > 0)
+            row += [b if not empty else -1, ptr - b if b else 0]
+        mine = torch.tensor(row, dtype=torch.int64, device=dev)
+        table = torch.empty(6 * world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(table, mine, group=self.group)
+        table = table.view(world, 6).cpu().numpy()  # host read: every rank's shard is complete from here on
+        if (table[:, 0::2] == 0).any():
+            return None  # the same table on every rank: a collective decision
+        bases = table[:, 0::2]
+        current = {(r, int(bases[r, a])) for r in range(world) for a in range(3) if bases[r, a] > 0}
+        if not current <= self.seen:
+            # a block not exchanged before (the allocator hands out a small, recurring set of blocks for equally sized
+            # builds, so this happens in the first steps only): every rank takes this branch together and maps the new
+            # blocks of its peers; mappings are kept (cudaIpcOpenMemHandle costs about a millisecond)
+            ok, why = 1, ""
+            try:
+                if len(self.mapped) > 96:  # deterministic on every rank: start over
+                    for v in self.mapped.values():
+                        lib.fxii_ipc_close(C.c_void_p(v))
+                    self.mapped.clear()
+                    self.seen.clear()
+                hbuf = (C.c_ubyte * 192)()
+                for a in range(3):
+                    if bases[rank, a] > 0:
+                        _lib.check(lib.fxii_ipc_export(C.c_void_p(int(bases[rank, a])), C.cast(C.byref(hbuf, 64 * a), C.c_void_p)))
+                hs = torch.frombuffer(bytearray(hbuf), dtype=torch.uint8).to(dev)
+            except Exception as e:  # noqa: BLE001
+                ok, why = 0, f"{type(e).__name__}: {e}"
+                hs = torch.zeros(192, dtype=torch.uint8, device=dev)
+            allh = torch.empty(192 * world, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, hs, group=self.group)
+            allh = allh.view(world, 192).cpu().numpy()
+            if ok:
+                try:
+                    for r in range(world):
+                        for a in range(3):
+                            b = int(bases[r, a])
+                            if r == rank or b <= 0 or (r, b) in self.mapped:
+                                continue
+                            raw = (C.c_ubyte * 64).from_buffer_copy(allh[r, 64 * a:64 * a + 64].tobytes())
+                            out = C.c_void_p()
+                            _lib.check(lib.fxii_ipc_open(C.cast(raw, C.c_void_p), C.byref(out)))
+                            self.mapped[(r, b)] = int(out.value)
+                except Exception as e:  # noqa: BLE001
+                    ok, why = 0, f"{type(e).__name__}: {e}"
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if int(flag.item()) == 0:  # some rank cannot export or map: every rank falls back, for good
+                self._fail(why if not ok else "a peer rank could not export or map its arrays")
+                return None
+            self.seen |= current
+        g_indptr = torch.empty(plan.n_rows + 1, dtype=torch.int64, device=dev)
+        g_indptr[:1] = 0
+        g_indices = torch.empty(plan.nnz, dtype=torch.int32, device=dev)
+        g_values = torch.empty(plan.nnz, dtype=torch.float64, device=dev)
+        stream = _lib.current_stream()
+        order = [(rank + d) % world for d in range(world)]  # the own shard first, then ring order: spreads the sources
+        for r in order:
+            mr, nr = int(plan.rows[r]), int(plan.nnzs[r])
+            r0, e0 = int(plan.row_off[r]), int(plan.nnz_off[r])
+            src = []
+            for a in range(3):
+                b = int(bases[r, a])
+                src.append((b if r == rank else self.mapped.get((r, b), 0)) + int(table[r, 2 * a + 1]))
+            if mr:
+                _lib.check(lib.fxii_copy_dev_async(C.c_void_p(g_indptr.data_ptr() + 8 * (1 + r0)), C.c_void_p(src[0] + 8), 8 * mr, stream))
+                if e0:
+                    g_indptr[1 + r0:1 + r0 + mr] += e0  # shard-local row ends -> global
+            if nr:
+                _lib.check(lib.fxii_copy_dev_async(C.c_void_p(g_indices.data_ptr() + 4 * e0), C.c_void_p(src[1]), 4 * nr, stream))
+                _lib.check(lib.fxii_copy_dev_async(C.c_void_p(g_values.data_ptr() + 8 * e0), C.c_void_p(src[2]), 8 * nr, stream))
+        fence = torch.zeros(1, dtype=torch.int32, device=dev)
+        dist.all_reduce(fence, group=self.group)  # no rank runs ahead (and frees its shard) before every peer's copies ran
+        return g_indptr, g_indices, g_values
 
 
 def allgatherv_vector(v, group=None):
@@ -247,6 +388,9 @@ class ShardedProducts:
         self.n_dofs, self.diag, self.m = int(n_dofs), diag_dev, m_dev
         self.world, self.rank, self.group = world, rank, group
         self.plan: "ProductPlan | None" = None
+        import os
+
+        self.peer = PeerGather(group) if (world > 1 and os.environ.get("FXII_GATHER", "p2p") == "p2p") else None
 
     def _make_plan(self, pi_local):
         import torch
@@ -283,8 +427,11 @@ class ShardedProducts:
             self.plan = self._make_plan(pi_local)
         mark()
         if self.world > 1:
-            ptr, idx, val = pi_local.device_tensors()
-            g_ptr, g_idx, g_val = allgatherv_csr(ptr, idx, val, group=self.group, plan=self.plan.gather)
+            got = self.peer.gather(pi_local, self.plan.gather) if self.peer is not None else None
+            if got is None:  # NCCL: one padded collective + unpack copies
+                ptr, idx, val = pi_local.device_tensors()
+                got = allgatherv_csr(ptr, idx, val, group=self.group, plan=self.plan.gather)
+            g_ptr, g_idx, g_val = got
             gp = DeviceCSR.wrap_device_arrays(g_ptr, g_idx, g_val, (self.plan.gather.n_rows, self.n_dofs))
         else:
             gp = pi_local

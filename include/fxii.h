@@ -186,6 +186,19 @@ int fxii_csr_wrap_device(int64_t n_rows, int64_t n_cols, int64_t nnz, int64_t* i
  * monotone from 0 to nnz, 0 <= column < n_cols, columns strictly ascending — hence unique — in every row.
  * FXII_E_INVALID otherwise.  Synchronises. */
 int fxii_csr_validate(const fxii_csr* a, void* stream);
+/* Peer-to-peer exchange between the ranks (processes) of one node: the all-gather-v of Π's row shards as direct
+ * NVLink copies out of the peers' own arrays, straight into the gathered CSR (no staging, no padding).
+ * fxii_alloc_base: the allocator block of THIS library that contains dev_ptr (NULL when the pointer is not ours,
+ * e.g. a torch tensor: such arrays cannot be exported); fxii_ipc_export: 64-byte CUDA IPC handle of such a block;
+ * fxii_ipc_open: map a peer's block (enables peer access lazily; keep the mapping and reuse it while the peer's
+ * block is unchanged); fxii_copy_dev_async: stream-ordered copy between any two device pointers of the node
+ * (unified addressing).  The caller orders the exchange: the source must be complete before the copy is
+ * enqueued and must stay alive until it has run. */
+int fxii_alloc_base(const void* dev_ptr, void** base);
+int fxii_ipc_export(const void* base_ptr, unsigned char* handle64);
+int fxii_ipc_open(const unsigned char* handle64, void** dev_ptr);
+int fxii_ipc_close(void* dev_ptr);
+int fxii_copy_dev_async(void* dst_dev, const void* src_dev, int64_t bytes, void* stream);
 int fxii_csr_info(const fxii_csr* a, int64_t* n_rows, int64_t* n_cols, int64_t* nnz);
 int fxii_csr_device_ptrs(const fxii_csr* a, void** indptr_dev, void** indices_dev, void** values_dev);
 int fxii_csr_download(const fxii_csr* a, int64_t* indptr, int32_t* indices, double* values,

@@ -82,6 +82,64 @@ def main():
             res[name] = float(t.item())
         except Exception as e:  # noqa: BLE001
             res[name] = f"failed: {type(e).__name__}: {e}"[:200]
+    # peer-to-peer pulls out of the library's own allocations (CUDA IPC): raw copy rate, no collectives inside the timing
+    try:
+        import ctypes as C
+
+        import numpy as np
+
+        from fenicsx_ii_b200 import _lib
+        from fenicsx_ii_b200.sparse import DeviceCSR
+
+        lib = _lib.load()
+        ptr_t = torch.arange(n + 1, dtype=torch.int64, device="cuda")
+        mat = DeviceCSR.from_device_arrays(ptr_t, idx, val, (n, 1 << 24))  # copies into the library's allocator
+        p = [C.c_void_p(), C.c_void_p(), C.c_void_p()]
+        _lib.check(lib.fxii_csr_device_ptrs(mat._h, C.byref(p[0]), C.byref(p[1]), C.byref(p[2])))
+        hbuf = (C.c_ubyte * 64)()
+        _lib.check(lib.fxii_ipc_export(p[2], C.cast(hbuf, C.c_void_p)))
+        hs = torch.frombuffer(bytearray(hbuf), dtype=torch.uint8).cuda()
+        allh = torch.empty(64 * world, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(allh, hs)
+        allh = allh.view(world, 64).cpu().numpy()
+        peer = (rank + 1) % world
+        raw = (C.c_ubyte * 64).from_buffer_copy(allh[peer].tobytes())
+        mapped = C.c_void_p()
+        _lib.check(lib.fxii_ipc_open(C.cast(raw, C.c_void_p), C.byref(mapped)))
+        nbytes = 8 * min(sizes)
+        dst = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        stream = _lib.current_stream()
+
+        def pull_kernel():
+            _lib.check(lib.fxii_copy_dev_async(C.c_void_p(dst.data_ptr()), mapped, nbytes, stream))
+
+        def pull_memcpy():
+            torch.cuda.synchronize()  # (cudaMemcpyAsync through the runtime: use torch's peer-agnostic path)
+            C.CDLL("libcudart.so").cudaMemcpyAsync(C.c_void_p(dst.data_ptr()), mapped, C.c_size_t(nbytes), 4, C.c_void_p(stream))
+
+        def local_copy():
+            _lib.check(lib.fxii_copy_dev_async(C.c_void_p(dst.data_ptr()), p[2], nbytes, stream))
+
+        for name, fn in (("p2p_pull_sm_kernel", pull_kernel), ("p2p_pull_cudaMemcpyAsync", pull_memcpy), ("local_copy_sm_kernel", local_copy)):
+            try:
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                dist.barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(5):
+                    fn()
+                b.record()
+                torch.cuda.synchronize()
+                t = torch.tensor([a.elapsed_time(b) / 5], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                res[name] = f"{float(t.item()):8.3f} ms  {nbytes / 1e9 / (float(t.item()) * 1e-3):7.1f} GB/s (one peer, {nbytes / 1e6:.0f} MB)"
+            except Exception as e:  # noqa: BLE001
+                res[name] = f"failed: {type(e).__name__}: {e}"[:200]
+        dist.barrier()
+    except Exception as e:  # noqa: BLE001
+        res["p2p"] = f"failed: {type(e).__name__}: {e}"[:300]
     # correctness of the in-place variant
     uneven()
     chk = torch.tensor([float(g_val[off[rank]:off[rank + 1]].sum() - val.sum())], device="cuda")
