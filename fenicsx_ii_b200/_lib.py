@@ -112,6 +112,7 @@ SIGNATURES = {
     "fxii_csr_info": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "fxii_csr_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "fxii_csr_download": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "fxii_csr_download_async": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "fxii_csr_destroy": (C.c_int, [_vp]),
     "fxii_csr_transpose": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "fxii_csr_transpose_window": (C.c_int, [_vp, _i64, _i64, _vp, C.POINTER(_vp)]),

@@ -68,6 +68,21 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def build_variant(out_path, source: str, defines: list[str]) -> Path:
+    """A variant of the library with ONE source recompiled with extra -D flags, linked against the other objects of the
+    normal build (tests only: e.g. a tiny traversal stack to trip the overflow check).  Load it with FXII_LIB=<path>."""
+    build()
+    nvcc = _nvcc()
+    out_path = Path(out_path)
+    obj = out_path.with_suffix(".o")
+    cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", *EXTRA.get(source, []),
+           *defines, "-c", str(HERE / source), "-o", str(obj)]
+    subprocess.run(cmd, check=True)
+    others = [str(HERE / (src[:-3] + ".o")) for src in SOURCES if src != source]
+    subprocess.run([nvcc, "-shared", *ARCH, "-o", str(out_path), str(obj), *others, "-lcudart"], check=True)
+    return out_path
+
+
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(path)

@@ -705,6 +705,16 @@ int fxii_csr_download(const fxii_csr* a, int64_t* indptr, int32_t* indices, doub
   });
 }
 
+int fxii_csr_download_async(const fxii_csr* a, int64_t* indptr, int32_t* indices, double* values, void* stream) {
+  return guarded([&] {
+    FXII_CHECK(a, "null csr");
+    cudaStream_t s = S(stream);
+    if (indptr) FXII_CUDA(cudaMemcpyAsync(indptr, a->indptr.p, sizeof(int64_t) * (size_t)(a->n_rows + 1), cudaMemcpyDeviceToHost, s));
+    if (indices && a->nnz) FXII_CUDA(cudaMemcpyAsync(indices, a->indices.p, sizeof(int32_t) * (size_t)a->nnz, cudaMemcpyDeviceToHost, s));
+    if (values && a->nnz) FXII_CUDA(cudaMemcpyAsync(values, a->values.p, sizeof(double) * (size_t)a->nnz, cudaMemcpyDeviceToHost, s));
+  });
+}
+
 int fxii_csr_destroy(fxii_csr* a) {
   return guarded([&] { delete a; });
 }

@@ -20,7 +20,14 @@
 
 namespace fxii {
 
-constexpr int kStack = 96;          // LBVH depth bound: 63-bit Morton key + 32-bit index tie-break
+#ifndef FXII_KSTACK
+#define FXII_KSTACK 96
+#endif
+// Traversal stack: the 4-wide walk pushes at most three siblings per wide level; the binary LBVH is at most 95 levels
+// deep (63-bit Morton key + 32-bit index tie-break), i.e. 48 wide levels.  Real meshes need 30-45 entries (config 5:
+// binary depth 27).  A walk that would need more reports it (PiCounters::stack_overflow -> FXII_E_UNSUPPORTED) instead
+// of dropping the subtree.  (-DFXII_KSTACK=n builds a variant with a small stack for the test that trips the check.)
+constexpr int kStack = FXII_KSTACK;
 constexpr double kCollisionD2 = 10.0 * 2.220446049250313e-16;  // dolfinx: d^2 < 10*eps
 
 // frame layout (16 doubles = 128 B per point row):

@@ -96,10 +96,12 @@ class DeviceCSR:
                                                  _lib.current_stream()))
         return indptr, indices, data
 
-    def to_host_into(self, indptr, indices, data):
-        """Download into caller-provided (e.g. pinned) buffers."""
-        _lib.check(_lib.load().fxii_csr_download(self._h, indptr.ctypes.data, indices.ctypes.data, data.ctypes.data,
-                                                 _lib.current_stream()))
+    def to_host_into(self, indptr, indices, data, sync: bool = True):
+        """Download into caller-provided (e.g. pinned) buffers on torch's current stream.  ``sync=False``: the copies
+        are only enqueued — synchronise the stream before reading the buffers and keep this matrix alive until then
+        (with pinned buffers on a side stream the download overlaps the kernels of the main stream)."""
+        fn = _lib.load().fxii_csr_download if sync else _lib.load().fxii_csr_download_async
+        _lib.check(fn(self._h, indptr.ctypes.data, indices.ctypes.data, data.ctypes.data, _lib.current_stream()))
 
     def to_scipy(self):
         import scipy.sparse as sp

@@ -203,6 +203,11 @@ int fxii_csr_info(const fxii_csr* a, int64_t* n_rows, int64_t* n_cols, int64_t* 
 int fxii_csr_device_ptrs(const fxii_csr* a, void** indptr_dev, void** indices_dev, void** values_dev);
 int fxii_csr_download(const fxii_csr* a, int64_t* indptr, int32_t* indices, double* values,
                       void* stream);
+/* The same without the final synchronisation: the copies are enqueued on `stream` (pinned destinations overlap with
+ * kernels of other streams, e.g. the download of Π with the block products); the caller synchronises the stream and
+ * keeps the matrix alive until then. */
+int fxii_csr_download_async(const fxii_csr* a, int64_t* indptr, int32_t* indices, double* values,
+                            void* stream);
 int fxii_csr_destroy(fxii_csr* a);
 
 /* Mat.transpose (matrix_assembler.py:184,236): rows of the result keep the source row order */

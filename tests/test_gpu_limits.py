@@ -1,0 +1,64 @@
+"""GPU: the limits of the path fail LOUDLY: a traversal that runs out of stack, a matrix row of the
+general path that collects more COO entries than its sort can hold, products whose operands break the CSR contract."""
+
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r'''
+import sys
+sys.path.insert(0, %(root)r)
+import numpy as np
+from fenicsx_ii_b200 import PointwiseTrace, create_interpolation_matrix
+from fenicsx_ii_b200 import synthetic as sy
+from fenicsx_ii_b200._lib import FXII_E_UNSUPPORTED, FxiiError
+from fenicsx_ii_b200.mesh import functionspace
+mesh = sy.kuhn_box(8, 8, 8)
+V = functionspace(mesh, ("Lagrange", 1))
+gamma = sy.straight_line(9)   # on mesh edges: every point collides with many cells, the walk needs its stack
+K = functionspace(gamma, ("DG", 1))
+for materialize in (False, True):
+    try:
+        create_interpolation_matrix(V, K, PointwiseTrace(gamma), materialize_coo=materialize)
+    except FxiiError as e:
+        assert e.code == FXII_E_UNSUPPORTED and "stack" in str(e), e
+    else:
+        raise SystemExit("a traversal with a 2-entry stack did not report the overflow")
+print("overflow reported")
+'''
+
+
+def test_traversal_stack_overflow_is_reported(cuda, tmp_path):
+    """A variant of the library with a 2-entry traversal stack (-DFXII_KSTACK=2): the walk cannot hold the siblings of
+    its path, and the build returns FXII_E_UNSUPPORTED instead of silently dropping subtrees."""
+    from fenicsx_ii_b200.csrc.build import build_variant
+
+    lib = build_variant(tmp_path / "libfxii_kstack2.so", "pi_assemble.cu", ["-DFXII_KSTACK=2"])
+    env = dict(os.environ, FXII_LIB=str(lib))
+    out = subprocess.run([sys.executable, "-c", SCRIPT % dict(root=ROOT)], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "overflow reported" in out.stdout, out.stdout + out.stderr
+
+
+def test_general_path_row_cap_is_an_error(cuda):
+    """A K dof shared by so many point rows that its matrix row would collect more than 16384 COO entries is refused
+    (general path: the row is sorted in shared memory), not truncated."""
+    from fenicsx_ii_b200 import Disk, create_interpolation_matrix
+    from fenicsx_ii_b200 import synthetic as sy
+    from fenicsx_ii_b200._lib import FxiiError
+    from fenicsx_ii_b200.mesh import FunctionSpace, DofMap, Element, functionspace
+
+    mesh = sy.kuhn_box(4, 4, 4)
+    V = functionspace(mesh, ("Lagrange", 1))
+    gamma = sy.polyline_network(120, 0.05, n_lines=1, lo=0.3, hi=0.7)
+    base = functionspace(gamma, ("DG", 0))
+    # one K dof for ALL cells: 120 point rows x 49 disk points x 4 dofs = 23520 entries in one matrix row
+    K = FunctionSpace(gamma, Element("DG", 0, base.element.interpolation_points), DofMap(np.zeros((120, 1), dtype=np.int32), 1))
+    with pytest.raises(FxiiError) as ei:
+        create_interpolation_matrix(V, K, Disk(gamma, 0.05, degree=7))
+    assert "16384" in str(ei.value)
