@@ -241,8 +241,11 @@ def run_ours(args):
         csr, st, out = step()
         torch.cuda.synchronize()
     barrier()
-    sampler = ClockSampler(local_rank, period=float(os.environ.get("BENCH_CLOCK_PERIOD", "0.02")))
-    sampler.start()
+    # one NVML poller per box, at 50 ms: eight pollers at 20 ms contended for the driver and cost every rank
+    # milliseconds per step on an 8-GPU run; it keeps sampling through the end-to-end loop below
+    sampler = ClockSampler(local_rank, period=float(os.environ.get("BENCH_CLOCK_PERIOD", "0.05")))
+    if rank == 0 or os.environ.get("BENCH_SAMPLE_ALL_RANKS"):  # one NVML poller per box: eight of them contend for the driver
+        sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     pi_keys = ("ms_frames", "ms_locate", "ms_csr", "ms_csr_count", "ms_csr_fill")
     prod_keys = ("allgather_ms", "transpose_ms", "spgemm_ms", "spgemm_mp_ms")
@@ -277,7 +280,6 @@ def run_ours(args):
         else:
             stage["pi_ms"] += a.elapsed_time(b)
     barrier()
-    clocks = sampler.stop()
     total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
     nnz_local = int(csr.nnz)
     Np, E = int(st["n_points"]), int(st["n_entries"])
@@ -294,8 +296,8 @@ def run_ours(args):
         allr = torch.empty(world * mine.numel(), device="cuda", dtype=torch.float64)
         dist.all_gather_into_tensor(allr, mine)
         allr = allr.view(world, -1).cpu().numpy()
-        names = ("pi_ms", "allgather_ms", "spgemm_ms", "transpose_ms", "nnz_pi", "nnz_c", "ip_c", "gather_pack_ms", "gather_nccl_ms",
-                 "gather_unpack_ms")
+        names = ("pi_ms", "allgather_ms", "spgemm_ms", "transpose_ms", "nnz_pi", "nnz_c", "ip_c", "gather_pack_or_handshake_ms",
+                 "gather_nccl_or_copies_ms", "gather_unpack_or_fence_ms")
         per_rank = {n: [round(float(v), 3) for v in allr[:, i]] for i, n in enumerate(names)}
     # max over ranks of the times; sum over ranks of the work
     keys = sorted(stage)
@@ -359,6 +361,7 @@ def run_ours(args):
         e2e_step()
         b.record()
     barrier()
+    clocks = sampler.stop()
     e2e_ms = float(sum(a.elapsed_time(b) for a, b in e_ev)) / e2e_steps
     e_all = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
     if world > 1:

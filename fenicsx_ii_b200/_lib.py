@@ -104,11 +104,14 @@ SIGNATURES = {
     "fxii_rows_download_coo": (C.c_int, [_vp, _vp, _vp, _vp]),
     "fxii_csr_upload": (C.c_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "fxii_csr_from_device": (C.c_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "fxii_device_alloc": (C.c_int, [_i64, _vp, C.POINTER(_vp)]),
+    "fxii_device_free": (C.c_int, [_vp, _vp]),
     "fxii_alloc_base": (C.c_int, [_vp, C.POINTER(_vp)]),
     "fxii_ipc_export": (C.c_int, [_vp, _vp]),
     "fxii_ipc_open": (C.c_int, [_vp, C.POINTER(_vp)]),
     "fxii_ipc_close": (C.c_int, [_vp]),
     "fxii_copy_dev_async": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "fxii_copy_segments_async": (C.c_int, [_i32, _vp, _vp, _vp, _vp, _vp]),
     "fxii_csr_info": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "fxii_csr_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "fxii_csr_download": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),

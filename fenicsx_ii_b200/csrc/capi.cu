@@ -1,5 +1,6 @@
 // extern "C" boundary (include/fxii.h).  No exceptions cross it: every entry point catches,
 // records a thread-local message and returns a negative status.
+#include <algorithm>
 #include <cstring>
 
 #include "common.cuh"
@@ -206,6 +207,53 @@ __global__ void __launch_bounds__(256) peer_copy_kernel(T* __restrict__ dst, con
     dst[i + 3 * stride] = d;
   }
   for (; i < n; i += stride) dst[i] = src[i];
+}
+}  // namespace fxii
+
+namespace fxii {
+// All segments of one exchange in ONE launch (8 ranks x 3 arrays would otherwise be 24 copy launches plus 8 pointer
+// shifts per step: on a box whose host cores are shared by eight ranks the launch overhead rivals the transfer).
+constexpr int kMaxSegments = 32;
+struct CopySegments {
+  void* dst[kMaxSegments];
+  const void* src[kMaxSegments];
+  long long bytes[kMaxSegments];
+  long long add[kMaxSegments];  // != 0: the segment is int64 data and `add` is added to every element (row-pointer shift)
+  int n;
+};
+
+template <typename T>
+__device__ __forceinline__ void copy_span(T* __restrict__ dst, const T* __restrict__ src, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    const T a = src[i], b = src[i + stride], c = src[i + 2 * stride], d = src[i + 3 * stride];
+    dst[i] = a;
+    dst[i + stride] = b;
+    dst[i + 2 * stride] = c;
+    dst[i + 3 * stride] = d;
+  }
+  for (; i < n; i += stride) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(256) copy_segments_kernel(const CopySegments seg) {
+  for (int k = 0; k < seg.n; ++k) {
+    const long long bytes = seg.bytes[k];
+    if (bytes <= 0) continue;
+    if (seg.add[k] != 0) {
+      long long* d = static_cast<long long*>(seg.dst[k]);
+      const long long* s = static_cast<const long long*>(seg.src[k]);
+      const long long add = seg.add[k];
+      for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < bytes / 8; i += (long long)gridDim.x * blockDim.x)
+        d[i] = s[i] + add;
+      continue;
+    }
+    const uintptr_t al = (uintptr_t)seg.dst[k] | (uintptr_t)seg.src[k] | (uintptr_t)bytes;
+    if ((al & 15) == 0) copy_span(static_cast<uint4*>(seg.dst[k]), static_cast<const uint4*>(seg.src[k]), bytes / 16);
+    else if ((al & 7) == 0) copy_span(static_cast<uint2*>(seg.dst[k]), static_cast<const uint2*>(seg.src[k]), bytes / 8);
+    else if ((al & 3) == 0) copy_span(static_cast<uint32_t*>(seg.dst[k]), static_cast<const uint32_t*>(seg.src[k]), bytes / 4);
+    else copy_span(static_cast<unsigned char*>(seg.dst[k]), static_cast<const unsigned char*>(seg.src[k]), bytes);
+  }
 }
 }  // namespace fxii
 
@@ -617,6 +665,19 @@ int fxii_csr_validate(const fxii_csr* a, void* stream) {
 
 // ---- peer-to-peer exchange of device arrays between the ranks of one node (CUDA IPC over NVLink) ---------------
 
+int fxii_device_alloc(int64_t bytes, void* stream, void** dev_ptr) {
+  return guarded([&] {
+    FXII_CHECK(dev_ptr && bytes >= 0, "bad argument");
+    *dev_ptr = bytes ? fxii::cached_alloc((size_t)bytes, S(stream)) : nullptr;
+  });
+}
+
+int fxii_device_free(void* dev_ptr, void* stream) {
+  return guarded([&] {
+    if (dev_ptr) fxii::cached_free(dev_ptr, S(stream));
+  });
+}
+
 int fxii_alloc_base(const void* dev_ptr, void** base) {
   return guarded([&] {
     FXII_CHECK(base, "null argument");
@@ -673,6 +734,29 @@ int fxii_copy_dev_async(void* dst_dev, const void* src_dev, int64_t bytes, void*
       FXII_CUDA(cudaMemcpyAsync(dst_dev, src_dev, (size_t)bytes, cudaMemcpyDefault, S(stream)));
     }
     FXII_CUDA(cudaGetLastError());
+  });
+}
+
+int fxii_copy_segments_async(int32_t n, void* const* dst_dev, const void* const* src_dev, const int64_t* bytes,
+                             const int64_t* add_i64, void* stream) {
+  return guarded([&] {
+    FXII_CHECK(n >= 0 && (n == 0 || (dst_dev && src_dev && bytes)), "bad argument");
+    for (int32_t k0 = 0; k0 < n; k0 += fxii::kMaxSegments) {
+      fxii::CopySegments seg;
+      seg.n = std::min<int32_t>(fxii::kMaxSegments, n - k0);
+      for (int k = 0; k < seg.n; ++k) {
+        seg.dst[k] = dst_dev[k0 + k];
+        seg.src[k] = src_dev[k0 + k];
+        seg.bytes[k] = bytes[k0 + k];
+        seg.add[k] = add_i64 ? add_i64[k0 + k] : 0;
+        FXII_CHECK(seg.bytes[k] >= 0 && (seg.bytes[k] == 0 || (seg.dst[k] && seg.src[k])), "bad segment");
+        FXII_CHECK(seg.add[k] == 0 || (seg.bytes[k] % 8 == 0 && ((uintptr_t)seg.dst[k] % 8) == 0 && ((uintptr_t)seg.src[k] % 8) == 0),
+                   "shifted segments must be int64 arrays");
+      }
+      fxii::copy_segments_kernel<<<fxii::num_sms() * 8, 256, 0, S(stream)>>>(seg);
+      FXII_LAUNCHED(1);
+      FXII_CUDA(cudaGetLastError());
+    }
   });
 }
 

@@ -165,20 +165,31 @@ def allgatherv_csr(indptr, indices, values, group=None, packed: "bool | None" = 
 class PeerGather:
     """All-gather-v of the row shards of a ``DeviceCSR`` as direct peer-to-peer copies over NVLink (one node).
 
-    Every rank exports CUDA IPC handles of its three CSR arrays; the peers map them once (re-mapping only when a
-    pointer changes — the library's allocator hands the same blocks back to equally sized builds) and then PULL every
-    shard straight into its slice of the gathered arrays with ``cudaMemcpyAsync``: no padding, no staging copies, the
-    copy engines at NVLink rate (770 GB/s peer copy measured on this pool against ~430-475 GB/s for the NCCL all-gather
-    plus its pack/unpack copies).  Ordering: a rank enters after its own build has synchronised, so once the (tiny)
-    pointer all-gather has been read on the host every peer's shard is complete; a closing all-reduce on the stream keeps
-    any rank from releasing its shard before all peers have copied it.  Any failure (IPC not permitted, no peer access)
-    disables the path for the process and the caller falls back to the NCCL exchange."""
+    Set-up, once per ``GatherPlan`` (collective): every rank allocates persistent SEND buffers for its shard in the
+    library's allocator, exports their CUDA IPC handles, maps the peers' buffers, and allocates the persistent gathered
+    arrays.  Every exchange then runs WITHOUT host synchronisation, allocation or pointer exchange, in four launches:
+
+      1. one kernel copies the local shard into the send buffers (row pointers shifted to their global values);
+      2. a one-element NCCL all-reduce on the stream: when it completes every rank's send buffers are complete;
+      3. one kernel PULLS all shards — peers' over NVLink, the own one locally — straight into their slices of the
+         gathered CSR (no padding, no staging: the SMs' loads keep the links full, 570-650 GB/s per peer measured);
+      4. a second one-element all-reduce: no rank refills its send buffers before every peer has read them.
+
+    Why not NCCL's all-gather: it needs equal sizes, i.e. a padded record plus unpack copies (2.35 ms for the 0.885 GB a
+    rank receives on 8 GPUs, profiles/r02_gather_variants_n8.txt), and its uneven variants are slower still (3.2-3.6 ms).
+    A first peer-to-peer version that exchanged the current pointers through a host-read all-gather every step spent
+    1.7-3.5 ms per exchange in that handshake on an 8-rank box.  The gathered arrays belong to this object and are
+    overwritten by the next exchange.  Any failure of the set-up (IPC not permitted, no peer access) disables the path
+    on every rank and the caller uses the NCCL exchange."""
 
     def __init__(self, group=None):
         self.group = group
         self.enabled = True
-        self.seen = set()       # (rank, block base) whose handle has been exchanged (the same set on every rank)
-        self.mapped = {}        # (peer rank, block base on the peer) -> local mapping
+        self.plan = None
+        self.send = None      # local send buffers (device pointers: indptr, indices, values)
+        self.peer = None      # [world][3] mapped pointers of every rank's send buffers (own rank: the local pointers)
+        self.out = None       # persistent gathered tensors
+        self.fence = None
 
     def _fail(self, why):
         import warnings
@@ -186,10 +197,25 @@ class PeerGather:
         self.enabled = False
         warnings.warn(f"peer-to-peer gather disabled, using NCCL: {why}")
 
-    def gather(self, pi_local, plan: GatherPlan):
-        """Returns (g_indptr, g_indices, g_values) torch tensors, or None when the path is unavailable (disabled, or
-        some rank's arrays do not live in blocks of the library's allocator, e.g. torch tensors: this call then goes
-        through NCCL)."""
+    def _release(self):
+        import ctypes as C
+
+        from . import _lib
+
+        lib = _lib.load()
+        if self.peer is not None:
+            for r, ptrs in enumerate(self.peer):
+                if r != self.plan.rank:
+                    for v in ptrs:
+                        if v:
+                            lib.fxii_ipc_close(C.c_void_p(v))
+        if self.send is not None:
+            for v in self.send:
+                if v:
+                    lib.fxii_device_free(C.c_void_p(v), _lib.current_stream())
+        self.send = self.peer = self.out = self.plan = None
+
+    def _setup(self, plan: GatherPlan) -> bool:
         import ctypes as C
 
         import torch
@@ -197,94 +223,103 @@ class PeerGather:
 
         from . import _lib
 
-        if not self.enabled:
-            return None
         lib = _lib.load()
         world, rank = plan.world, plan.rank
         dev = torch.device("cuda", torch.cuda.current_device())
-        p = [C.c_void_p(), C.c_void_p(), C.c_void_p()]
-        _lib.check(lib.fxii_csr_device_ptrs(pi_local._h, C.byref(p[0]), C.byref(p[1]), C.byref(p[2])))
-        row = []
-        for a, v in enumerate(p):  # (block base, offset) per array; base 0: not exportable
-            ptr = int(v.value or 0)
-            base = C.c_void_p()
-            if ptr:
-                _lib.check(lib.fxii_alloc_base(C.c_void_p(ptr), C.byref(base)))
-            b = int(base.value or 0)
-            empty = (plan.nnzs[rank] == 0 and a > 0)
-            row += [b if not empty else -1, ptr - b if b else 0]
-        mine = torch.tensor(row, dtype=torch.int64, device=dev)
-        table = torch.empty(6 * world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(table, mine, group=self.group)
-        table = table.view(world, 6).cpu().numpy()  # host read: every rank's shard is complete from here on
-        if (table[:, 0::2] == 0).any():
-            return None  # the same table on every rank: a collective decision
-        bases = table[:, 0::2]
-        current = {(r, int(bases[r, a])) for r in range(world) for a in range(3) if bases[r, a] > 0}
-        if not current <= self.seen:
-            # a block not exchanged before (the allocator hands out a small, recurring set of blocks for equally sized
-            # builds, so this happens in the first steps only): every rank takes this branch together and maps the new
-            # blocks of its peers; mappings are kept (cudaIpcOpenMemHandle costs about a millisecond)
-            ok, why = 1, ""
+        torch.cuda.synchronize()
+        if self.plan is not None:
+            dist.barrier(group=self.group)  # nobody still reads the old send buffers
+            self._release()
+        self.plan = plan
+        m, n = int(plan.rows[rank]), int(plan.nnzs[rank])
+        sizes = [8 * max(m, 1), 4 * max(n, 1), 8 * max(n, 1)]
+        ok, why = 1, ""
+        hbuf = (C.c_ubyte * 192)()
+        try:
+            self.send = []
+            for a, nb in enumerate(sizes):
+                p = C.c_void_p()
+                _lib.check(lib.fxii_device_alloc(nb, _lib.current_stream(), C.byref(p)))
+                self.send.append(int(p.value))
+                _lib.check(lib.fxii_ipc_export(p, C.cast(C.byref(hbuf, 64 * a), C.c_void_p)))
+        except Exception as e:  # noqa: BLE001
+            ok, why = 0, f"{type(e).__name__}: {e}"
+        hs = torch.frombuffer(bytearray(hbuf), dtype=torch.uint8).to(dev)
+        allh = torch.empty(192 * world, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, hs, group=self.group)
+        allh = allh.view(world, 192).cpu().numpy()
+        self.peer = [[0, 0, 0] for _ in range(world)]
+        if ok:
             try:
-                if len(self.mapped) > 96:  # deterministic on every rank: start over
-                    for v in self.mapped.values():
-                        lib.fxii_ipc_close(C.c_void_p(v))
-                    self.mapped.clear()
-                    self.seen.clear()
-                hbuf = (C.c_ubyte * 192)()
-                for a in range(3):
-                    if bases[rank, a] > 0:
-                        _lib.check(lib.fxii_ipc_export(C.c_void_p(int(bases[rank, a])), C.cast(C.byref(hbuf, 64 * a), C.c_void_p)))
-                hs = torch.frombuffer(bytearray(hbuf), dtype=torch.uint8).to(dev)
-            except Exception as e:  # noqa: BLE001
-                ok, why = 0, f"{type(e).__name__}: {e}"
-                hs = torch.zeros(192, dtype=torch.uint8, device=dev)
-            allh = torch.empty(192 * world, dtype=torch.uint8, device=dev)
-            dist.all_gather_into_tensor(allh, hs, group=self.group)
-            allh = allh.view(world, 192).cpu().numpy()
-            if ok:
-                try:
-                    for r in range(world):
-                        for a in range(3):
-                            b = int(bases[r, a])
-                            if r == rank or b <= 0 or (r, b) in self.mapped:
-                                continue
+                for r in range(world):
+                    for a in range(3):
+                        if r == rank:
+                            self.peer[r][a] = self.send[a]
+                        else:
                             raw = (C.c_ubyte * 64).from_buffer_copy(allh[r, 64 * a:64 * a + 64].tobytes())
                             out = C.c_void_p()
                             _lib.check(lib.fxii_ipc_open(C.cast(raw, C.c_void_p), C.byref(out)))
-                            self.mapped[(r, b)] = int(out.value)
-                except Exception as e:  # noqa: BLE001
-                    ok, why = 0, f"{type(e).__name__}: {e}"
-            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-            if int(flag.item()) == 0:  # some rank cannot export or map: every rank falls back, for good
-                self._fail(why if not ok else "a peer rank could not export or map its arrays")
-                return None
-            self.seen |= current
+                            self.peer[r][a] = int(out.value)
+            except Exception as e:  # noqa: BLE001
+                ok, why = 0, f"{type(e).__name__}: {e}"
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:  # some rank cannot export or map: every rank falls back, for good
+            self._fail(why if not ok else "a peer rank could not export or map its send buffers")
+            return False
         g_indptr = torch.empty(plan.n_rows + 1, dtype=torch.int64, device=dev)
         g_indptr[:1] = 0
-        g_indices = torch.empty(plan.nnz, dtype=torch.int32, device=dev)
-        g_values = torch.empty(plan.nnz, dtype=torch.float64, device=dev)
-        stream = _lib.current_stream()
-        order = [(rank + d) % world for d in range(world)]  # the own shard first, then ring order: spreads the sources
-        for r in order:
+        self.out = (g_indptr, torch.empty(plan.nnz, dtype=torch.int32, device=dev), torch.empty(plan.nnz, dtype=torch.float64, device=dev))
+        self.fence = torch.zeros(1, dtype=torch.int32, device=dev)
+        # the pull: every shard from its owner's send buffers into its slice (own shard first, then ring order)
+        dst, src, nbytes = [], [], []
+        for d in range(world):
+            r = (rank + d) % world
             mr, nr = int(plan.rows[r]), int(plan.nnzs[r])
             r0, e0 = int(plan.row_off[r]), int(plan.nnz_off[r])
-            src = []
-            for a in range(3):
-                b = int(bases[r, a])
-                src.append((b if r == rank else self.mapped.get((r, b), 0)) + int(table[r, 2 * a + 1]))
             if mr:
-                _lib.check(lib.fxii_copy_dev_async(C.c_void_p(g_indptr.data_ptr() + 8 * (1 + r0)), C.c_void_p(src[0] + 8), 8 * mr, stream))
-                if e0:
-                    g_indptr[1 + r0:1 + r0 + mr] += e0  # shard-local row ends -> global
+                dst.append(g_indptr.data_ptr() + 8 * (1 + r0)), src.append(self.peer[r][0]), nbytes.append(8 * mr)
             if nr:
-                _lib.check(lib.fxii_copy_dev_async(C.c_void_p(g_indices.data_ptr() + 4 * e0), C.c_void_p(src[1]), 4 * nr, stream))
-                _lib.check(lib.fxii_copy_dev_async(C.c_void_p(g_values.data_ptr() + 8 * e0), C.c_void_p(src[2]), 8 * nr, stream))
-        fence = torch.zeros(1, dtype=torch.int32, device=dev)
-        dist.all_reduce(fence, group=self.group)  # no rank runs ahead (and frees its shard) before every peer's copies ran
-        return g_indptr, g_indices, g_values
+                dst.append(self.out[1].data_ptr() + 4 * e0), src.append(self.peer[r][1]), nbytes.append(4 * nr)
+                dst.append(self.out[2].data_ptr() + 8 * e0), src.append(self.peer[r][2]), nbytes.append(8 * nr)
+        k = len(dst)
+        self.pull = (k, (C.c_void_p * k)(*dst), (C.c_void_p * k)(*src), (C.c_int64 * k)(*nbytes))
+        return True
+
+    def gather(self, pi_local, plan: GatherPlan):
+        """Returns (g_indptr, g_indices, g_values) — persistent tensors owned by this object, overwritten by the next
+        call — or None when the path is unavailable."""
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        from . import _lib
+
+        if not self.enabled:
+            return None
+        if plan is not self.plan and not self._setup(plan):
+            return None
+        lib = _lib.load()
+        rank = plan.rank
+        m, n = int(plan.rows[rank]), int(plan.nnzs[rank])
+        p = [C.c_void_p(), C.c_void_p(), C.c_void_p()]
+        _lib.check(lib.fxii_csr_device_ptrs(pi_local._h, C.byref(p[0]), C.byref(p[1]), C.byref(p[2])))
+        stream = _lib.current_stream()
+        # 1. local shard -> send buffers; row pointers become global row ends (shard-local ends + entry offset)
+        e0 = int(plan.nnz_off[rank])
+        segs = [(self.send[0], int(p[0].value or 0) + 8, 8 * m, e0), (self.send[1], int(p[1].value or 0), 4 * n, 0),
+                (self.send[2], int(p[2].value or 0), 8 * n, 0)]
+        segs = [s for s in segs if s[2] > 0]
+        k = len(segs)
+        if k:
+            _lib.check(lib.fxii_copy_segments_async(k, (C.c_void_p * k)(*[s[0] for s in segs]), (C.c_void_p * k)(*[s[1] for s in segs]),
+                                                    (C.c_int64 * k)(*[s[2] for s in segs]), (C.c_int64 * k)(*[s[3] for s in segs]), stream))
+        dist.all_reduce(self.fence, group=self.group)  # 2. every rank's send buffers are complete
+        kp, dst, src, nbytes = self.pull
+        if kp:
+            _lib.check(lib.fxii_copy_segments_async(kp, dst, src, nbytes, None, stream))  # 3. pull all shards into place
+        dist.all_reduce(self.fence, group=self.group)  # 4. nobody refills its send buffers before everyone has read them
+        return self.out
 
 
 def allgatherv_vector(v, group=None):

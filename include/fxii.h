@@ -194,11 +194,19 @@ int fxii_csr_validate(const fxii_csr* a, void* stream);
  * block is unchanged); fxii_copy_dev_async: stream-ordered copy between any two device pointers of the node
  * (unified addressing).  The caller orders the exchange: the source must be complete before the copy is
  * enqueued and must stay alive until it has run. */
+/* a block of the library's allocator (exportable with fxii_ipc_export): the persistent send buffers of the exchange */
+int fxii_device_alloc(int64_t bytes, void* stream, void** dev_ptr);
+int fxii_device_free(void* dev_ptr, void* stream);
 int fxii_alloc_base(const void* dev_ptr, void** base);
 int fxii_ipc_export(const void* base_ptr, unsigned char* handle64);
 int fxii_ipc_open(const unsigned char* handle64, void** dev_ptr);
 int fxii_ipc_close(void* dev_ptr);
 int fxii_copy_dev_async(void* dst_dev, const void* src_dev, int64_t bytes, void* stream);
+/* n copies (HOST arrays of device pointers and sizes) in one kernel launch; add_i64 (may be NULL): a segment with a
+ * nonzero entry is int64 data and gets that value added to every element while it is copied (the row pointers of a
+ * shard shifted to their place in the gathered matrix). */
+int fxii_copy_segments_async(int32_t n, void* const* dst_dev, const void* const* src_dev, const int64_t* bytes,
+                             const int64_t* add_i64, void* stream);
 int fxii_csr_info(const fxii_csr* a, int64_t* n_rows, int64_t* n_cols, int64_t* nnz);
 int fxii_csr_device_ptrs(const fxii_csr* a, void** indptr_dev, void** indices_dev, void** values_dev);
 int fxii_csr_download(const fxii_csr* a, int64_t* indptr, int32_t* indices, double* values,

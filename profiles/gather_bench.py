@@ -62,8 +62,24 @@ def main():
         dist.all_gather_into_tensor(rec_i, pad_i)
         dist.all_gather_into_tensor(rec_v, pad_v)
 
+    tiny = torch.zeros(6, dtype=torch.int64, device="cuda")
+    tiny_all = torch.empty(6 * world, dtype=torch.int64, device="cuda")
+
+    def tiny_gather_host():
+        dist.all_gather_into_tensor(tiny_all, tiny)
+        return tiny_all.cpu()
+
+    def tiny_allreduce_stream():
+        dist.all_reduce(tiny)
+
+    def tiny_from_list():
+        t = torch.tensor([1, 2, 3, 4, 5, 6], dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(tiny_all, t)
+        return tiny_all.cpu()
+
     res = {}
-    for name, fn in (("uneven_all_gather", uneven), ("batch_isend_irecv", p2p), ("padded_all_gather+unpack", padded),
+    for name, fn in (("tiny_all_gather+host_read", tiny_gather_host), ("tiny_all_reduce_stream_ordered", tiny_allreduce_stream),
+                     ("tiny_from_list+all_gather+host_read", tiny_from_list), ("uneven_all_gather", uneven), ("batch_isend_irecv", p2p), ("padded_all_gather+unpack", padded),
                      ("padded_all_gather_only", padded_only)):
         try:
             for _ in range(3):
