@@ -198,6 +198,26 @@ def test_transpose_random(cuda, m, n, density):
     assert T.shape == (n, m)
 
 
+def test_transpose_long_columns_and_windows(cuda):
+    """Very long columns (thousands of entries), short columns and empty column windows: the transpose and its
+    windows give MatTranspose's order bit for bit."""
+    rng = np.random.default_rng(9)
+    A = sp.random(6000, 40, density=0.85, random_state=4, format="csr")  # columns of ~5100 entries
+    B = sp.random(3000, 500, density=0.01, random_state=5, format="csr")  # short columns
+    for M in (A, B):
+        M.sort_indices()
+        a = as_host(M)
+        d = DeviceCSR.from_host(*a, M.shape)
+        ref = orc.csr_transpose(*a, M.shape[1])
+        check(d.transpose(), ref, rtol=0)
+        for c0, c1 in ((0, M.shape[1] // 3), (M.shape[1] // 3, M.shape[1]), (5, 5)):
+            Tw = d.transpose(c0, c1).to_host()
+            np.testing.assert_array_equal(Tw[0], ref[0][c0:c1 + 1] - ref[0][c0])
+            np.testing.assert_array_equal(Tw[1], ref[1][ref[0][c0]:ref[0][c1]])
+            assert Tw[2].tobytes() == ref[2][ref[0][c0]:ref[0][c1]].tobytes()
+    assert rng is not None
+
+
 def test_block_products_of_the_demo(cuda):
     """demos/coupled_poisson.py:107-121,164-177 on the scaled config-1 geometry:
     C = A10 T, Pt = P^T, Z = Pt (M_Γ T), D = Pt A01 — all against the oracle."""
