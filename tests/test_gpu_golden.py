@@ -1,5 +1,10 @@
 """GPU path against the golden fixtures produced by the reference's own interpolation.py
-(tests/golden/pi_*.npz): bit-exact pattern and ownership, values to 1e-12 of the row scale."""
+(tests/golden/pi_*.npz): bit-exact pattern and ownership, values to 1e-12 of the row scale.
+
+What the fixtures pin: everything the reference itself implements (point ordering, operator quadrature, pattern,
+weights/scales arithmetic, first-visit-wins, accumulation order).  What they cannot pin: point location and basis
+tabulation — the dolfinx shim the reference ran on takes both from oracle/pi_oracle.py (its `determine_point_ownership`
+IS the oracle's GridLocator), so the `cell` arrays compared here are GPU-vs-oracle, not GPU-vs-dolfinx."""
 
 import numpy as np
 import pytest
