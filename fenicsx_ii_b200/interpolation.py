@@ -400,7 +400,8 @@ def create_interpolation_matrix(V, K, red_op, tol: float = 1.0e-8, use_petsc: bo
         tol: Tolerance (box padding) for determining point ownership.
         use_petsc: Return a PETSc AIJ matrix (requires petsc4py) instead of a ``MatrixCSR``.
         cells_K: Optional subset of the cells of K to process.
-        complex_dtype: Not supported on the device path.
+        complex_dtype: Return a matrix whose host values are complex128 (the entries of Π are real: the imaginary part
+            is zero; the device arithmetic is float64 either way).
         materialize_coo: (extension) force the unfused COO path, e.g. to inspect the COO.
         cache: (extension) reuse the matrix of an earlier call with the same `V`, `K`, `red_op`,
             `tol` and `cells_K` objects (see ``clear_interpolation_cache``).
@@ -411,13 +412,18 @@ def create_interpolation_matrix(V, K, red_op, tol: float = 1.0e-8, use_petsc: bo
     Returns:
         ``(A, imap_K, imap_V)``: the matrix and the (serial: unchanged) index maps of K and V.
     """
-    if complex_dtype:
-        raise NotImplementedError("complex matrices are not supported on the device path")
+    # scalar type of the returned matrix (interpolation.py:175-203): complex when asked for, else the mesh's real type
+    geom_dtype = np.asarray(V.mesh.geometry.x).dtype
+    out_dtype = np.complex128 if complex_dtype else (np.float32 if geom_dtype == np.float32 else np.float64)
+    if complex_dtype and geom_dtype == np.float32:
+        out_dtype = np.complex64
     imap_K, imap_V = K.dofmap.index_map, V.dofmap.index_map
     key = _cache_key(V, K, red_op, tol, cells_K) if cache and not materialize_coo else None
     if key is not None and key in _PI_CACHE:
         A = _PI_CACHE.pop(key)[0]
         _PI_CACHE[key] = (A, V, K, red_op)  # most recently used last
+        if A.dtype != np.dtype(out_dtype):  # same device matrix, another host scalar type
+            A = MatrixCSR(A.device, stats=A.stats, rows=A.rows, dtype=out_dtype)
         return (A.to_petsc() if use_petsc else A), imap_K, imap_V
     bs = int(getattr(V.dofmap, "bs", 1))
     if bs != int(getattr(K.dofmap, "bs", 1)):
@@ -434,7 +440,7 @@ def create_interpolation_matrix(V, K, red_op, tol: float = 1.0e-8, use_petsc: bo
             hints[hkey] = nnz
             n_rows = rows.n_rows_total
             A = MatrixCSR(None, stats=stats, rows=rows, host=(indptr_h[: n_rows + 1], indices_h[:nnz], values_h[:nnz]),
-                          shape=(n_rows, dspace.n_dofs))
+                          shape=(n_rows, dspace.n_dofs), dtype=out_dtype)
             return A, imap_K, imap_V
     rows = device_rows(K, red_op, cells_K)
     if materialize_coo:
@@ -451,7 +457,7 @@ def create_interpolation_matrix(V, K, red_op, tol: float = 1.0e-8, use_petsc: bo
         hints[hkey] = nnz
         n_rows = rows.n_rows_total
         A = MatrixCSR(None, stats=stats, rows=rows, host=(indptr_h[: n_rows + 1], indices_h[:nnz], values_h[:nnz]),
-                      shape=(n_rows, dspace.n_dofs))
+                      shape=(n_rows, dspace.n_dofs), dtype=out_dtype)
         return A, imap_K, imap_V
     general = K.__dict__.get("_fxii_general_path", False) if hasattr(K, "__dict__") else False
     if general and not materialize_coo:
@@ -462,7 +468,7 @@ def create_interpolation_matrix(V, K, red_op, tol: float = 1.0e-8, use_petsc: bo
     hints[hkey] = csr.nnz
     if bs > 1:
         csr = csr.expand_blocks(bs)  # device kernel: bs x bs blocks, explicit zeros off the diagonal
-    A = MatrixCSR(csr, stats=stats, rows=rows)
+    A = MatrixCSR(csr, stats=stats, rows=rows, dtype=out_dtype)
     if key is not None:
         _PI_CACHE[key] = (A, V, K, red_op)
         while len(_PI_CACHE) > _PI_CACHE_SIZE:

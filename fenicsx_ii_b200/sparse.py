@@ -236,7 +236,8 @@ class MatrixCSR:
     ``dolfinx.la.MatrixCSR`` the callers use (``indptr``, ``indices``, ``data``, ``to_scipy``,
     ``to_dense``) over a device-resident matrix.  Host arrays are downloaded on first access."""
 
-    def __init__(self, device: "DeviceCSR | None", stats=None, rows=None, host=None, shape=None):
+    def __init__(self, device: "DeviceCSR | None", stats=None, rows=None, host=None, shape=None, dtype=np.float64):
+        self.dtype = np.dtype(dtype)  # scalar type of `data` on the host (the device arithmetic is always float64)
         self._device = device
         self.stats = stats
         self.rows = rows  # DeviceRows of the build (per-point diagnostics), may be None
@@ -271,18 +272,24 @@ class MatrixCSR:
 
     @property
     def data(self):
-        return self._arrays()[2]
+        """Values in the matrix' scalar type: float64 as computed, or cast on the host (complex128 with a zero imaginary
+        part for ``complex_dtype=True``; the mesh's float32 for single-precision meshes — computed in float64, rounded once)."""
+        v = self._arrays()[2]
+        return v if self.dtype == np.float64 else v.astype(self.dtype)
 
     def to_scipy(self):
         import scipy.sparse as sp
 
-        a, b, c = self._arrays()
-        return sp.csr_matrix((c, b, a), shape=self.shape)
+        a, b, _ = self._arrays()
+        return sp.csr_matrix((self.data, b, a), shape=self.shape)
 
     def to_dense(self):
         return self.to_scipy().toarray()
 
     def mult(self, u):
+        u = np.asarray(u)
+        if np.iscomplexobj(u):  # a real matrix acting on a complex vector: real and imaginary parts separately
+            return self.device.mult(np.ascontiguousarray(u.real)) + 1j * self.device.mult(np.ascontiguousarray(u.imag))
         return self.device.mult(u)
 
     def scatter_reverse(self):  # serial: nothing to accumulate
@@ -304,7 +311,8 @@ class MatrixCSR:
             from petsc4py import PETSc
         except ImportError as e:
             raise RuntimeError("use_petsc=True needs petsc4py, which is not installed") from e
-        a, b, c = self._arrays()
+        a, b, _ = self._arrays()
+        c = self.data
         if b.shape[0] >= 2**31 and PETSc.IntType().itemsize == 4:
             raise RuntimeError("matrix needs 64-bit PETSc indices")
         A = PETSc.Mat().createAIJ(size=self.shape, csr=(a.astype(PETSc.IntType), b.astype(PETSc.IntType), c))

@@ -182,3 +182,26 @@ def test_overridden_plugin_contract_is_honoured(cuda, problem):
     r2 = (x[:, 0] - 0.5) ** 2 + (x[:, 1] - 0.5) ** 2
     # the P1 interpolant of r^2 averaged over the smaller circle is clearly smaller than over the stock one
     assert np.all(A.mult(r2) < stock.mult(r2) - 1e-3)
+
+
+def test_scalar_type_of_the_returned_matrix(cuda, problem):
+    """interpolation.py:175-203: ``complex_dtype=True`` returns a complex matrix (Π is real: zero imaginary part), a
+    single-precision mesh a float32 one; the device arithmetic is float64 in every case, the cast happens once on the host."""
+    from fenicsx_ii_b200.mesh import Mesh
+
+    V, W = problem["V"], problem["W"]
+    A = create_interpolation_matrix(V, W, problem["circle"])[0]
+    Ac = create_interpolation_matrix(V, W, problem["circle"], complex_dtype=True)[0]
+    assert A.data.dtype == np.float64 and Ac.data.dtype == np.complex128
+    np.testing.assert_array_equal(Ac.indices, A.indices)
+    np.testing.assert_array_equal(Ac.data.real, A.data)
+    assert not Ac.data.imag.any() and Ac.to_scipy().dtype == np.complex128
+    u = np.random.default_rng(0).normal(size=V.num_dofs) + 1j * np.random.default_rng(1).normal(size=V.num_dofs)
+    np.testing.assert_allclose(Ac.mult(u), problem["T"] @ u, rtol=1e-12, atol=1e-13)
+    m32 = Mesh(problem["mesh"].geometry.x.astype(np.float32), problem["mesh"].geometry.dofmap, tdim=3)
+    m32.geometry.x = m32.geometry.x.astype(np.float32)  # the stand-in stores float64: make the mesh single precision
+    V32 = functionspace(m32, ("Lagrange", 1))
+    A32 = create_interpolation_matrix(V32, W, problem["circle"])[0]
+    assert A32.data.dtype == np.float32
+    np.testing.assert_array_equal(A32.indices, A.indices)  # the box mesh is exactly representable in float32
+    np.testing.assert_allclose(A32.data, A.data, rtol=0, atol=1e-6)
