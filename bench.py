@@ -326,27 +326,31 @@ def run_ours(args):
 
     copy_stream = torch.cuda.Stream()
 
-    def download(mat, bufs):
-        """Enqueue the download of a finished matrix on the copy stream (it overlaps the kernels that follow on the main
-        stream); returns the matrix so that it stays alive until the final synchronisation."""
-        done = torch.cuda.Event()
-        done.record()
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(done)
-            mat.to_host_into(*bufs, sync=False)
-        return mat
+    from fenicsx_ii_b200.distributed import assemble_blocks_to_host
 
-    def e2e_step():
-        A, _, _ = create_interpolation_matrix(V, K, op, cells_K=None if world == 1 else my_cells)
-        pi_local = A.device if world == 1 else A.device.row_slice(r0, r1)
-        keep = [A, download(pi_local, host["pi"])]
+    def e2e_step(marks=None):
+        """One end-to-end block assembly through the public API: pinned host Γ arrays in, pinned host CSR blocks out.
+        Π is built in `--e2e-pi-pieces` blocks of Γ cells and C in `--e2e-pieces` row pieces; every finished block is
+        downloaded on the copy stream while the next one is computed (the D2H link bounds the step)."""
+        if marks is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            marks.append(("start", e0))
         if prod is not None:
-            c, mp = prod(pi_local)[:2]
-            keep.append(download(c, host["c"]))
-            if mp is not None:
-                keep.append(download(mp, host["mp"]))
+            keep = assemble_blocks_to_host(V, K, op, prod, host["pi"], host["c"], host.get("mp"), cells_K=None if world == 1 else my_cells,
+                                           pi_pieces=args.e2e_pi_pieces, c_pieces=args.e2e_pieces, copy_stream=copy_stream, marks=marks)
+        else:
+            A, _, _ = create_interpolation_matrix(V, K, op, cells_K=None if world == 1 else my_cells)
+            pi_local = A.device if world == 1 else A.device.row_slice(r0, r1)
+            done = torch.cuda.Event()
+            done.record()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                pi_local.to_host_into(*host["pi"], sync=False)
+            keep = [A, pi_local]
         copy_stream.synchronize()  # all blocks are in the host arrays
         torch.cuda.current_stream().wait_stream(copy_stream)
+        del keep
 
     e2e_steps = max(2, min(args.steps, 5))
     e2e_step()
@@ -362,15 +366,29 @@ def run_ours(args):
         b.record()
     barrier()
     clocks = sampler.stop()
+    # where one end-to-end step spends its time: device timestamps (ms after the start event) of the main-stream and
+    # copy-stream milestones of ONE extra, untimed step
+    marks = []
+    flush.zero_()
+    torch.cuda.synchronize()
+    e2e_step(marks)
+    torch.cuda.synchronize()
+    e_start = marks[0][1]
+    e2e_timeline = {}
+    for name, m in marks[1:]:
+        e2e_timeline[name] = round(1e3 * m, 3) if isinstance(m, float) else round(e_start.elapsed_time(m), 3)
     e2e_ms = float(sum(a.elapsed_time(b) for a, b in e_ev)) / e2e_steps
     e_all = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e_all, op=dist.ReduceOp.MAX)
     e2e_ms = float(e_all.item())
     gx, gc = gamma.geometry.x, gamma.geometry.dofmap
-    h2d = gx.nbytes + gc.nbytes + 8 * nip + (0 if world == 1 else 4 * (c1 - c0))
+    # every create_interpolation_matrix call (one per block of Γ cells) uploads Γ's geometry and the operator tables;
+    # cells_K and the per-cell radii of the blocks add up to this rank's cells
+    n_calls = args.e2e_pi_pieces if products_on else 1
+    h2d = n_calls * (gx.nbytes + gc.nbytes + 8 * nip) + (0 if (world == 1 and n_calls == 1) else 4 * (c1 - c0))
     if cfg["op"] != "trace":
-        h2d += 32 * op.num_points + (8 * (c1 - c0) * nip if seg_r is not None else 8)
+        h2d += n_calls * 32 * op.num_points + (8 * (c1 - c0) if seg_r is not None else 8 * n_calls)
     d2h = sum(a.nbytes + 4 * b.shape[0] + 8 * c.shape[0] for a, b, c in host.values())
 
     # ---- roofline: every stage of the step with its algorithmic bytes, the dominant one named ---------
@@ -436,9 +454,11 @@ def run_ours(args):
                           "spgemm_s": stage_ms["spgemm_ms"] * 1e-3, "m_pi_s": stage_ms["spgemm_mp_ms"] * 1e-3,
                           "plan_setup_ms": prod.plan.setup_ms if prod.plan else None} if products_on else None),
             "e2e": {"value": nnz_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms,
-                    "note": "create_interpolation_matrix(V,K,op[,cells_K]) from pinned host Γ arrays + products + download of Π, "
-                            "C and MΠ into pinned host CSR arrays, every step; Ω handle (upload + LBVH) cached"},
+                    "ms_per_step": e2e_ms, "timeline_ms": e2e_timeline,
+                    "note": "assemble_blocks_to_host: create_interpolation_matrix(V,K,op,cells_K=block) from pinned host Γ arrays for "
+                            f"{args.e2e_pi_pieces} blocks of Γ cells + ShardedProducts.to_host (MΠ first, C in {args.e2e_pieces} row pieces); "
+                            "Π, C and MΠ land in pinned host CSR arrays every step, every block downloaded while the next is "
+                            "computed; Ω handle (upload + LBVH) cached"},
             "e2e_cold": {"value": nnz_cold / cold_s if world == 1 else None, "unit": UNIT, "s": cold_s, "mesh_build_s": mesh_build_s,
                          "note": "FIRST call on a fresh mesh: Ω upload + LBVH build + Γ upload + Π build + CSR download (Π only); "
                                  "the reference rebuilds its tree on every call"},
@@ -627,6 +647,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--e2e-pieces", type=int, default=4, help="row pieces of C whose downloads overlap the remaining products (e2e)")
+    ap.add_argument("--e2e-pi-pieces", type=int, default=2, help="blocks of Γ cells Π is built in, each downloaded while the next is built (e2e)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

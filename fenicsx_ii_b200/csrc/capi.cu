@@ -9,6 +9,7 @@ namespace fxii {
 void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* cell_nodes, int64_t n_cells, int npc,
                 double padding, cudaStream_t s);
 void device_iota(int32_t* a, int64_t n, cudaStream_t s);
+void check_index_range(const int32_t* a, int64_t n, int64_t hi, cudaStream_t s, const char* what);
 void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr* out, fxii_pi_stats* stats,
                  bool keep_points);
 void csr_transpose(const fxii_csr* a, int64_t c0, int64_t c1, cudaStream_t s, fxii_csr* out);
@@ -25,6 +26,7 @@ static thread_local std::string g_last_error;
 #include <cstdlib>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 namespace fxii {
@@ -180,6 +182,148 @@ void cache_trim() {
 }  // namespace fxii
 
 namespace fxii {
+// ---- small device -> host reads through a mapped pinned page (common.cuh: d2h_small / stream_sync) -----------------
+namespace {
+constexpr size_t kFetchPage = 4096;
+struct FetchState {
+  unsigned char* page = nullptr;  // pinned; under unified addressing the device stores through the same pointer
+  size_t used = 0;
+  struct Item { void* host; size_t off, bytes; };
+  std::vector<Item> items;
+};
+thread_local FetchState g_fetch;
+__global__ void fetch_kernel(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src, int bytes) {
+  for (int i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+}
+}  // namespace
+
+void d2h_small(void* host, const void* dev, size_t bytes, cudaStream_t s) {
+  FetchState& f = g_fetch;
+  if (!f.page) FXII_CUDA(cudaHostAlloc((void**)&f.page, kFetchPage, cudaHostAllocPortable | cudaHostAllocMapped));
+  const size_t need = (bytes + 15) / 16 * 16;
+  if (bytes > kFetchPage || f.used + need > kFetchPage) {  // does not happen on the path; keep the semantics anyway
+    FXII_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, s));
+    return;
+  }
+  fetch_kernel<<<1, 64, 0, s>>>(f.page + f.used, static_cast<const unsigned char*>(dev), (int)bytes);
+  FXII_CUDA(cudaGetLastError());
+  f.items.push_back({host, f.used, bytes});
+  f.used += need;
+}
+
+// an error unwound the caller before its stream_sync: forget the pending destinations (they were its locals)
+void d2h_small_abandon() {
+  g_fetch.items.clear();
+  g_fetch.used = 0;
+}
+
+void stream_sync(cudaStream_t s) {
+  FXII_CUDA(cudaStreamSynchronize(s));
+  FetchState& f = g_fetch;
+  for (const auto& it : f.items) memcpy(it.host, f.page + it.off, it.bytes);
+  f.items.clear();
+  f.used = 0;
+}
+}  // namespace fxii
+
+namespace fxii {
+// ---- pipelined upload of large pageable host arrays ----------------------------------------------------------
+// A first call on numpy arrays uploads 3.6 GB for config 5's Ω (coordinates, cells, dofmap).  cudaMemcpyAsync from
+// pageable memory goes through the driver's single-threaded staging copy: 11 GB/s measured on the B200 boxes, while
+// the link moves 55 GB/s from pinned memory and eight host threads copy 69 GB/s into pinned memory
+// (profiles/r02_pcie_probe.txt).  Here T worker threads each own two pinned 4 MiB buffers and a stream: a worker
+// copies its next chunk into one buffer while the copy engine drains the other.  The buffers live for the process.
+namespace {
+constexpr size_t kStageChunk = (size_t)4 << 20;
+constexpr size_t kStageMin = (size_t)32 << 20;  // below this the plain copy is as fast
+constexpr int kStageMaxThreads = 8;
+struct StageWorker {
+  unsigned char* buf[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaStream_t stream = nullptr;
+};
+std::mutex g_stage_mutex;
+std::map<int, std::vector<StageWorker>> g_stage;  // per device
+int stage_threads() {
+  static int n = [] {
+    if (const char* e = getenv("FXII_UPLOAD_THREADS")) return std::max(0, std::min(atoi(e), kStageMaxThreads));
+    const unsigned hc = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min<unsigned>(hc / 2, kStageMaxThreads));
+  }();
+  return n;
+}
+}  // namespace
+
+void staged_upload(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  if (bytes == 0) return;
+  const int T = stage_threads();
+  bool plain = bytes < kStageMin || T == 0;
+  if (!plain) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, src) != cudaSuccess) {
+      cudaGetLastError();
+      plain = true;
+    } else if (attr.type != cudaMemoryTypeUnregistered) {
+      plain = true;  // pinned, registered, managed or device memory: the copy engine reads it directly
+    }
+  }
+  if (plain) {
+    FXII_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s));
+    return;
+  }
+  int dev = 0;
+  FXII_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_stage_mutex);
+  std::vector<StageWorker>& ws = g_stage[dev];
+  if ((int)ws.size() < T) {
+    const size_t have = ws.size();
+    ws.resize(T);
+    for (size_t t = have; t < ws.size(); ++t) {
+      FXII_CUDA(cudaStreamCreateWithFlags(&ws[t].stream, cudaStreamNonBlocking));
+      for (int b = 0; b < 2; ++b) {
+        FXII_CUDA(cudaHostAlloc((void**)&ws[t].buf[b], kStageChunk, cudaHostAllocDefault));
+        FXII_CUDA(cudaEventCreateWithFlags(&ws[t].ev[b], cudaEventDisableTiming));
+      }
+    }
+  }
+  // the destination may still be in use by work queued on s (a recycled block): the worker streams start after it
+  cudaEvent_t start = event_acquire();
+  FXII_CUDA(cudaEventRecord(start, s));
+  const size_t n_chunks = (bytes + kStageChunk - 1) / kStageChunk;
+  std::vector<cudaError_t> err(T, cudaSuccess);
+  std::vector<std::thread> threads;
+  threads.reserve(T);
+  for (int t = 0; t < T; ++t) {
+    threads.emplace_back([&, t] {
+      StageWorker& w = ws[t];
+      cudaError_t e = cudaSetDevice(dev);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(w.stream, start, 0);
+      int b = 0;
+      for (size_t c = (size_t)t; c < n_chunks && e == cudaSuccess; c += (size_t)T, b ^= 1) {
+        const size_t off = c * kStageChunk;
+        const size_t n = std::min(kStageChunk, bytes - off);
+        e = cudaEventSynchronize(w.ev[b]);  // the previous copy out of this buffer has finished (no-op the first time)
+        if (e != cudaSuccess) break;
+        memcpy(w.buf[b], static_cast<const unsigned char*>(src) + off, n);
+        e = cudaMemcpyAsync(static_cast<unsigned char*>(dst) + off, w.buf[b], n, cudaMemcpyHostToDevice, w.stream);
+        if (e == cudaSuccess) e = cudaEventRecord(w.ev[b], w.stream);
+      }
+      err[t] = e;
+    });
+  }
+  for (auto& th : threads) th.join();  // the host array has been consumed; the last device copies may be in flight
+  event_release(start);
+  for (int t = 0; t < T; ++t) {
+    // s continues after every worker's last copy (both buffers' events cover them)
+    for (int b = 0; b < 2; ++b) FXII_CUDA(cudaStreamWaitEvent(s, ws[t].ev[b], 0));
+  }
+  for (int t = 0; t < T; ++t)
+    if (err[t] != cudaSuccess) throw Error(FXII_E_CUDA, std::string("staged upload: ") + cudaGetErrorString(err[t]));
+}
+}  // namespace fxii
+
+namespace fxii {
 // the live block of the library's allocator that contains p (nullptr: not ours)
 void* alloc_base_of(const void* p) {
   std::lock_guard<std::mutex> lock(g_mem_mutex);
@@ -263,12 +407,15 @@ static int guarded(F&& f) {
     f();
     return FXII_OK;
   } catch (const fxii::Error& e) {
+    fxii::d2h_small_abandon();
     g_last_error = e.what();
     return e.code;
   } catch (const std::exception& e) {
+    fxii::d2h_small_abandon();
     g_last_error = e.what();
     return FXII_E_INVALID;
   } catch (...) {
+    fxii::d2h_small_abandon();
     g_last_error = "unknown error";
     return FXII_E_INVALID;
   }
@@ -356,7 +503,7 @@ int fxii_space_create(fxii_mesh* mesh, const int32_t* dofmap, int32_t nd, int32_
     s->n_dofs = n_dofs;
     try {
       s->dofmap.upload(dofmap, (int64_t)nd * mesh->n_cells, S(stream));
-      FXII_CUDA(cudaStreamSynchronize(S(stream)));
+      fxii::check_index_range(s->dofmap.p, (int64_t)nd * mesh->n_cells, n_dofs, S(stream), "dof index");  // synchronises
     } catch (...) {
       delete s;
       throw;
@@ -422,7 +569,7 @@ static fxii_rows* make_rows(const fxii_rows_desc& d, cudaStream_t s, bool sync) 
     if (d.kind != FXII_OP_TRACE) {
       r->table.upload(d.table, 3 * (int64_t)nq, s);
       r->w.upload(d.w, nq, s);
-      r->radius.upload(d.radius, d.radius_per_row ? d.n_cells_k * d.nip : 1, s);
+      r->radius.upload(d.radius, d.radius_per_row == 1 ? d.n_cells_k * d.nip : (d.radius_per_row == 2 ? d.n_cells_k : 1), s);
     }
     if (sync) FXII_CUDA(cudaStreamSynchronize(s));
   } catch (...) {
@@ -607,10 +754,15 @@ static fxii_csr* csr_from(int64_t n_rows, int64_t n_cols, int64_t nnz, const int
     c->indptr.alloc(n_rows + 1, s);
     c->indices.alloc(nnz, s);
     c->values.alloc(nnz, s);
-    FXII_CUDA(cudaMemcpyAsync(c->indptr.p, indptr, sizeof(int64_t) * (size_t)(n_rows + 1), kind, s));
+    // host sources: large pageable arrays take the pipelined staging copy (staged_upload)
+    auto put = [&](void* dst, const void* src, size_t bytes) {
+      if (kind == cudaMemcpyHostToDevice) fxii::staged_upload(dst, src, bytes, s);
+      else FXII_CUDA(cudaMemcpyAsync(dst, src, bytes, kind, s));
+    };
+    put(c->indptr.p, indptr, sizeof(int64_t) * (size_t)(n_rows + 1));
     if (nnz) {
-      FXII_CUDA(cudaMemcpyAsync(c->indices.p, indices, sizeof(int32_t) * (size_t)nnz, kind, s));
-      FXII_CUDA(cudaMemcpyAsync(c->values.p, values, sizeof(double) * (size_t)nnz, kind, s));
+      put(c->indices.p, indices, sizeof(int32_t) * (size_t)nnz);
+      put(c->values.p, values, sizeof(double) * (size_t)nnz);
     }
     FXII_CUDA(cudaStreamSynchronize(s));
   } catch (...) {

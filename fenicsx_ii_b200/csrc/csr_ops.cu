@@ -124,8 +124,8 @@ void csr_transpose(const fxii_csr* a, int64_t c0, int64_t c1, cudaStream_t s, fx
       DevBuf<uint8_t> tmp;
       tmp.alloc((int64_t)tb, s);
       FXII_CUDA(cub::DeviceSelect::If(tmp.p, tb, positions, sel.p, n_sel_dev.p, nnz, pred, s));
-      FXII_CUDA(cudaMemcpyAsync(&n_sel, n_sel_dev.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-      FXII_CUDA(cudaStreamSynchronize(s));
+      d2h_small(&n_sel, n_sel_dev.p, sizeof(int64_t), s);
+      stream_sync(s);
     } else {
       row_of.alloc(nnz, s);
       iota.alloc(nnz, s);
@@ -865,8 +865,8 @@ static void bin_rows(const int64_t* size, int64_t m, const BinThresholds& thr, c
   tmp.alloc((int64_t)tb, s);
   FXII_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, bin_of.p, bin_sorted.p, rows.p, rb.sorted_rows.p, m, 0, 4, s));
   unsigned long long h[kNumBins + 1];
-  FXII_CUDA(cudaMemcpyAsync(h, counts.p, sizeof(h), cudaMemcpyDeviceToHost, s));
-  FXII_CUDA(cudaStreamSynchronize(s));
+  d2h_small(h, counts.p, sizeof(h), s);
+  stream_sync(s);
   int64_t off = 0;
   for (int b = 0; b <= kNumBins; ++b) {
     rb.count[b] = (int64_t)h[b];
@@ -947,7 +947,7 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, const double* b_scale, int64_t
     FXII_CUDA(cub::DeviceReduce::Sum(tmp.p, tb, ub.p, ip_dev.p, m, s));
   }
   int64_t h_ip = 0;
-  FXII_CUDA(cudaMemcpyAsync(&h_ip, ip_dev.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  d2h_small(&h_ip, ip_dev.p, sizeof(int64_t), s);
   DevBuf<int> overflow;
   overflow.alloc(1, s);
 
@@ -969,8 +969,8 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, const double* b_scale, int64_t
       { global_table_sizes_kernel<<<grid_for(nl + 1, 256, 8), 256, 0, s>>>(list, nl, size, b->n_cols, g_sizes.p); FXII_LAUNCHED(1); }
       exclusive_scan_i64((const long long*)g_sizes.p, (long long*)g_off.p, nl + 1, s);
       int64_t total = 0;
-      FXII_CUDA(cudaMemcpyAsync(&total, g_off.p + nl, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-      FXII_CUDA(cudaStreamSynchronize(s));
+      d2h_small(&total, g_off.p + nl, sizeof(int64_t), s);
+      stream_sync(s);
       FXII_CHECK(total < ((int64_t)1 << 33), "spgemm: rows too long for the global-table fallback (shard the product)");
       g_keys.alloc(total, s);
       if (numeric) {
@@ -995,7 +995,7 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, const double* b_scale, int64_t
     else if (!block && numeric) FXII_SPGEMM_LAUNCH(false, true);
     else FXII_SPGEMM_LAUNCH(false, false);
 #undef FXII_SPGEMM_LAUNCH
-    if (global) FXII_CUDA(cudaStreamSynchronize(s));  // tables are freed when this scope ends
+    if (global) stream_sync(s);  // tables are freed when this scope ends
   };
 
   // lean warp-per-row kernel (short rows of B): G lanes per row of B from B's mean row length
@@ -1068,8 +1068,8 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, const double* b_scale, int64_t
   DevBuf<int64_t> n_retry;
   auto select_overflowed = [&]() -> int64_t {
     int h_over = 0;
-    FXII_CUDA(cudaMemcpyAsync(&h_over, overflow.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    FXII_CUDA(cudaStreamSynchronize(s));
+    d2h_small(&h_over, overflow.p, sizeof(int), s);
+    stream_sync(s);
     if (!h_over) return 0;
     if (!iota.p) {
       iota.alloc(m, s);
@@ -1084,9 +1084,9 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, const double* b_scale, int64_t
     tmp.alloc((int64_t)tb, s);
     FXII_CUDA(cub::DeviceSelect::If(tmp.p, tb, iota.p, retry.p, n_retry.p, m, pred, s));
     int64_t h_n = 0;
-    FXII_CUDA(cudaMemcpyAsync(&h_n, n_retry.p, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    d2h_small(&h_n, n_retry.p, sizeof(int64_t), s);
     FXII_CUDA(cudaMemsetAsync(overflow.p, 0, sizeof(int), s));
-    FXII_CUDA(cudaStreamSynchronize(s));
+    stream_sync(s);
     return h_n;
   };
 
@@ -1129,7 +1129,7 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, const double* b_scale, int64_t
   tr.mark("symbolic long rows");
   exclusive_scan_i64((const long long*)row_nnz.p, (long long*)out->indptr.p, m + 1, s);
   int64_t nnz = 0;
-  FXII_CUDA(cudaMemcpyAsync(&nnz, out->indptr.p + m, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  d2h_small(&nnz, out->indptr.p + m, sizeof(int64_t), s);
   // ---- numeric ---------------------------------------------------------------------------------
   // bins 0..7: shared-memory tables of 64..8192 slots; bin 8: exact-size tables in global memory.
   // Lean kernel: bins 0..5 (64..2048 slots, 12 B per slot) hold nnz <= LF*cap; round-1 kernels: nnz <= cap/2.
@@ -1249,7 +1249,7 @@ void csr_scale_rows(fxii_csr* a, const double* d_any, cudaStream_t s) {
   }
   if (a->n_rows > 0) { scale_rows_kernel<<<grid_for(a->n_rows * 32, 256, 8), 256, 0, s>>>(a->indptr.p, a->n_rows, dp, a->values.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
-  if (!on_device) FXII_CUDA(cudaStreamSynchronize(s));
+  if (!on_device) stream_sync(s);
 }
 
 // one warp per row; lanes stride the row, partial sums combined by a fixed shuffle tree
@@ -1276,7 +1276,7 @@ void csr_spmv(const fxii_csr* a, const double* u_host, double* y_host, cudaStrea
     FXII_CUDA(cudaGetLastError());
     FXII_CUDA(cudaMemcpyAsync(y_host, y.p, sizeof(double) * (size_t)a->n_rows, cudaMemcpyDeviceToHost, s));
   }
-  FXII_CUDA(cudaStreamSynchronize(s));
+  stream_sync(s);
 }
 
 // ---- validation of caller-supplied matrices ---------------------------------------------------------
@@ -1311,8 +1311,8 @@ void csr_validate(const fxii_csr* a, cudaStream_t s) {
     FXII_CUDA(cudaGetLastError());
   }
   int h = 0;
-  FXII_CUDA(cudaMemcpyAsync(&h, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-  FXII_CUDA(cudaStreamSynchronize(s));
+  d2h_small(&h, bad.p, sizeof(int), s);
+  stream_sync(s);
   FXII_CHECK(a->n_rows > 0 || a->nnz == 0, "CSR: entries without rows");
   FXII_CHECK(h != 1, "CSR: indptr must rise monotonically from 0 to nnz");
   FXII_CHECK(h != 2, "CSR: column index out of range");

@@ -34,6 +34,18 @@ __host__ __device__ __forceinline__ double dec_ordered(unsigned long long e) {
 #endif
 }
 
+// any a[i] outside [0, hi)?  (index arrays are validated on the device: two numpy reductions over config 5's 1.6 GB
+// cell array cost 0.25 s on the host, this pass 0.3 ms)
+__global__ void __launch_bounds__(256) index_range_kernel(const int32_t* __restrict__ a, int64_t n, int32_t hi,
+                                                          int32_t* __restrict__ bad) {
+  bool b = false;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t v = a[i];
+    b = b || v < 0 || v >= hi;
+  }
+  if (__any_sync(0xffffffffu, b) && (threadIdx.x & 31) == 0) *bad = 1;
+}
+
 // bounds[0..2] = encoded min, bounds[3..5] = encoded max
 __global__ void __launch_bounds__(256) scene_bounds_kernel(const double* __restrict__ x, int64_t n_nodes,
                                                            unsigned long long* __restrict__ bounds) {
@@ -403,6 +415,21 @@ static void finish_wide(fxii_mesh* m, DevBuf<BvhNode>& bnodes, DevBuf<unsigned l
   FXII_CUDA(cudaStreamSynchronize(s));
 }
 
+// throws FXII_E_INVALID when an entry of the device array a[0..n) lies outside [0, hi); synchronises s
+void check_index_range(const int32_t* a, int64_t n, int64_t hi, cudaStream_t s, const char* what) {
+  if (n <= 0) return;
+  DevBuf<int32_t> bad;
+  bad.alloc(1, s);
+  FXII_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int32_t), s));
+  const int32_t hi32 = hi > 0x7fffffff ? 0x7fffffff : (int32_t)hi;
+  { index_range_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(a, n, hi32, bad.p); FXII_LAUNCHED(1); }
+  FXII_CUDA(cudaGetLastError());
+  int32_t h = 0;
+  FXII_CUDA(cudaMemcpyAsync(&h, bad.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  FXII_CUDA(cudaStreamSynchronize(s));
+  if (h) throw Error(FXII_E_INVALID, std::string(what) + " out of range");
+}
+
 void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* cell_nodes, int64_t n_cells, int npc,
                 double padding, cudaStream_t s) {
   FXII_CHECK(npc == 4 || npc == 8, "cells must have 4 (tetrahedron) or 8 (hexahedron) geometry nodes");
@@ -412,8 +439,11 @@ void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* c
   m->n_nodes = n_nodes;
   m->npc = npc;
   m->padding = padding;
+  Trace tr("mesh_build", s);
   m->x.upload(x, 3 * n_nodes, s);
   m->cell_nodes.upload(cell_nodes, (int64_t)npc * n_cells, s);
+  tr.mark("upload x + cells");
+  check_index_range(m->cell_nodes.p, (int64_t)npc * n_cells, n_nodes, s, "cell node index");
   m->cellgeo.alloc((npc == 4 ? 12 : 24) * n_cells, s);
   const int n = (int)n_cells;
   const int n_internal = n > 1 ? n - 1 : 1;
@@ -440,6 +470,7 @@ void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* c
   ids_sorted.alloc(n, s);
   leaf_parent.alloc(n, s);
   flags.alloc(n_internal, s);
+  tr.mark("allocations");
   if (npc == 4) {
     { cell_geom_morton_kernel<<<grid_for(n_cells, 256, 8), 256, 0, s>>>(
         m->x.p, reinterpret_cast<const int4*>(m->cell_nodes.p), n_cells, bounds.p, m->cellgeo.p, keys.p, ids.p); FXII_LAUNCHED(1); }
@@ -453,7 +484,9 @@ void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* c
   FXII_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.p, keys_sorted.p, ids.p, ids_sorted.p, n, 0, 63, s));
   DevBuf<uint8_t> tmp;
   tmp.alloc((int64_t)tmp_bytes, s);
+  tr.mark("geometry + morton");
   FXII_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys.p, keys_sorted.p, ids.p, ids_sorted.p, n, 0, 63, s));
+  tr.mark("sort");
 
   if (n == 1) {
     // single leaf: a root whose left child is the cell and whose right child box is empty
@@ -479,6 +512,7 @@ void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* c
   { refit_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(m->x.p, m->cell_nodes.p, npc, ids_sorted.p,
                                                    leaf_parent.p, n, padding, bnodes.p, flags.p); FXII_LAUNCHED(1); }
   FXII_CUDA(cudaGetLastError());
+  tr.mark("karras + refit");
   DevBuf<int32_t> depth;
   depth.alloc(1, s);
   FXII_CUDA(cudaMemsetAsync(depth.p, 0, sizeof(int32_t), s));
@@ -489,5 +523,6 @@ void mesh_build(fxii_mesh* m, const double* x, int64_t n_nodes, const int32_t* c
   FXII_CUDA(cudaStreamSynchronize(s));
   m->max_depth = h;
   finish_wide(m, bnodes, bounds, n_internal, s);
+  tr.mark("depth + wide collapse");
 }
 }  // namespace fxii

@@ -95,7 +95,8 @@ __device__ __forceinline__ void compute_frame(const double* __restrict__ gx, con
       const double diag = (p == q) ? ct : 0.0;
       f[4 + 3 * p + q] = (diag + sm[3 * p + q] * st) + (a[p] * a[q]) * omc;
     }
-  const double R = radius_per_row ? radius[r] : radius[0];
+  // radius_per_row: 0 one radius, 1 one per point row, 2 one per processed Γ cell (row r belongs to cell slot i = r / nip)
+  const double R = radius_per_row == 1 ? radius[r] : (radius_per_row == 2 ? radius[i] : radius[0]);
   f[3] = R;
   if (kind == FXII_OP_CIRCLE) {
     const double scale = 2.0 * R * PI;  // restriction_operators.py:203
@@ -1602,6 +1603,16 @@ compact_rows_kernel(const int32_t* __restrict__ src_row, const int64_t* __restri
   }
 }
 
+__global__ void publish_result_kernel(FusedResult* __restrict__ host_result, const int64_t* __restrict__ nnz,
+                                      const int* __restrict__ conflict, const PiCounters* __restrict__ counters) {
+  if (threadIdx.x == 0) {
+    host_result->nnz = *nnz;
+    host_result->conflict = *conflict;
+    host_result->counters = *counters;
+    __threadfence_system();
+  }
+}
+
 // ---- host side of the fused path -------------------------------------------------------------
 struct FusedPlan {
   int team, B, rpb, grid;
@@ -1713,9 +1724,10 @@ static void enqueue_fused(const fxii_space* sp, fxii_rows* rows, const FusedPlan
   size_t tb = p.scan_tmp_bytes;
   FXII_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, tb, (const long long*)row_cnt, (long long*)indptr, (int64_t)(n_rows + 1), s));
   launch_compact(sp, rows, ws, p, indptr, capacity, indices, values, s);
-  FXII_CUDA(cudaMemcpyAsync(&host_result->nnz, indptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-  FXII_CUDA(cudaMemcpyAsync(&host_result->conflict, conflict, sizeof(int), cudaMemcpyDeviceToHost, s));
-  FXII_CUDA(cudaMemcpyAsync(&host_result->counters, counters_dev, sizeof(PiCounters), cudaMemcpyDeviceToHost, s));
+  // the result record goes into the pinned (device-mapped) slot by a store from a kernel, not by the copy engine: a
+  // device-to-host copy of a few bytes queues behind any CSR download still in flight on another stream
+  { publish_result_kernel<<<1, 32, 0, s>>>(host_result, indptr + n_rows, conflict, counters_dev); FXII_LAUNCHED(1); }
+  FXII_CUDA(cudaGetLastError());
   FXII_CUDA(cudaEventRecordWithFlags(ev[3], s, ev_flags));
 }
 

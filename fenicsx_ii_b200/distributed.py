@@ -10,6 +10,7 @@ every shard straight into its slice of the gathered arrays.
 
 from __future__ import annotations
 
+import time
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -483,6 +484,215 @@ class ShardedProducts:
             mp, ip_mp = self.m.matmult(gp, q0, q1, return_ip=True)
         mark()
         return c, mp, ip, pt.nnz, ip_mp
+
+
+    # ---- host delivery: downloads overlapped with the remaining products -----------------------------------------
+    def _sub_windows(self, gp, n_sub: int):
+        """This rank's window of 3D dofs cut into `n_sub` contiguous pieces of equal SpGEMM work (cached in the plan)."""
+        r0, r1 = self.plan.windows[self.rank]
+        key = ("sub", n_sub)
+        cache = self.plan.__dict__.setdefault("_sub", {})
+        if key not in cache:
+            if n_sub <= 1:
+                cache[key] = [(r0, r1)]
+            else:
+                ptr, idx, _ = gp.device_tensors()
+                fine = balanced_dof_windows(idx, self.n_dofs, self.world * n_sub, indptr_t=ptr)
+                mine = fine[self.rank * n_sub:(self.rank + 1) * n_sub]
+                # the fine cuts at multiples of n_sub are the coarse cuts (same formula); pin the ends anyway
+                mine[0] = (r0, mine[0][1])
+                mine[-1] = (mine[-1][0], r1)
+                cache[key] = [(a, max(a, b)) for a, b in mine]
+        return cache[key]
+
+    def to_host(self, pi_local, host_c, host_mp=None, n_sub: int = 4, copy_stream=None, marks=None):
+        """The products of ``__call__`` delivered into caller-owned host CSR arrays ``(indptr int64, indices int32,
+        values float64)``, ideally pinned, with the device→host copies overlapped with the products still to come
+        (what bounds the end-to-end time of a block assembly is the PCIe link: 3 GB for config 5):
+
+          * MΠ is computed first and its download queued on `copy_stream`;
+          * this rank's window of C = Πᵀ(M_ΓΠ) is computed in `n_sub` row pieces of equal work; a piece's row
+            pointers are shifted to the window's entry numbering on the device and its download is queued as soon as
+            it is finished, while the next piece is transposed and multiplied on the main stream.
+
+        The rows, their order and their arithmetic are those of ``__call__`` (the result is bit-identical).
+        Returns ``dict(nnz_c, nnz_mp, rows_c, keep)``; synchronise `copy_stream` before reading the arrays and keep
+        ``keep`` alive until then.  ``ValueError`` if a host array is too small."""
+        import torch
+
+        from .sparse import DeviceCSR
+
+        if copy_stream is None:
+            copy_stream = torch.cuda.Stream()
+        if self.plan is None or (self.plan.gather is not None and not self.plan.gather.matches(pi_local.shape[0], pi_local.nnz)):
+            self.plan = self._make_plan(pi_local)
+        if self.world > 1:
+            got = self.peer.gather(pi_local, self.plan.gather) if self.peer is not None else None
+            if got is None:
+                ptr, idx, val = pi_local.device_tensors()
+                got = allgatherv_csr(ptr, idx, val, group=self.group, plan=self.plan.gather)
+            gp = DeviceCSR.wrap_device_arrays(*got, (self.plan.gather.n_rows, self.n_dofs))
+        else:
+            gp = pi_local
+        keep = [gp]
+
+        def queue_download(mat, bufs, name):
+            done = torch.cuda.Event(enable_timing=marks is not None)
+            done.record()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                if marks is not None:
+                    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    b0.record()
+                mat.to_host_into(*bufs, sync=False)
+                if marks is not None:
+                    b1.record()
+                    marks.extend([(name + " ready (main stream)", done), (name + " D2H begin", b0), (name + " D2H end", b1)])
+            keep.append(mat)
+
+        nnz_mp = 0
+        if self.m is not None and host_mp is not None:
+            q0, q1 = shard_range(self.m.shape[0], self.world, self.rank)
+            mp = self.m.matmult(gp, q0, q1)
+            nnz_mp = mp.nnz
+            if host_mp[0].shape[0] < mp.shape[0] + 1 or host_mp[1].shape[0] < nnz_mp or host_mp[2].shape[0] < nnz_mp:
+                raise ValueError(f"host arrays for MΠ too small: {mp.shape[0]} rows, {nnz_mp} entries")
+            queue_download(mp, (host_mp[0][: mp.shape[0] + 1], host_mp[1][:nnz_mp], host_mp[2][:nnz_mp]), "MPi")
+        r0, r1 = self.plan.windows[self.rank]
+        if host_c[0].shape[0] < r1 - r0 + 1:
+            raise ValueError(f"host row pointers for C too small: {r1 - r0} rows")
+        off = 0
+        for w, (a, b) in enumerate(self._sub_windows(gp, n_sub)):
+            if b <= a:
+                continue
+            pt = gp.transpose(a, b)
+            c = pt.matmult(gp, row_scale=self.diag)
+            del pt
+            if host_c[1].shape[0] < off + c.nnz or host_c[2].shape[0] < off + c.nnz:
+                raise ValueError(f"host arrays for C too small: at least {off + c.nnz} entries")
+            if off:
+                c.device_tensors()[0].add_(off)  # row pointers in the numbering of the whole window
+            # the piece's first pointer equals the previous piece's last one: the one-element overlap is consistent
+            queue_download(c, (host_c[0][a - r0:b - r0 + 1], host_c[1][off:off + c.nnz], host_c[2][off:off + c.nnz]), f"C[{w}]")
+            off += c.nnz
+        return dict(nnz_c=off, nnz_mp=nnz_mp, rows_c=r1 - r0, keep=keep, copy_stream=copy_stream)
+
+
+def assemble_blocks_to_host(V, K, red_op, products: ShardedProducts, host_pi, host_c, host_mp=None, cells_K=None,
+                            pi_pieces: int = 2, c_pieces: int = 4, copy_stream=None, marks=None, tol: float = 1.0e-8) -> dict:
+    """One block assembly of the coupled 3D-1D problem delivered into caller-owned host CSR arrays (ideally pinned):
+    Π for `cells_K` (this rank's block of Γ cells; None: all), this rank's rows of C = Πᵀ(M_ΓΠ) and of MΠ.
+
+    What bounds the end-to-end time is the device→host link (config 5: 3.2 GB at ~55 GB/s ≈ 60 ms against 35 ms of
+    kernels), so the copy engine is started as early as possible and never left idle: Π is built in `pi_pieces`
+    contiguous blocks of Γ cells (``create_interpolation_matrix(..., cells_K=block)``) and every block is downloaded
+    while the next one is built; the blocks are concatenated on the device for the products, which
+    ``ShardedProducts.to_host`` delivers piece by piece.  Blocks need K's cell-local dof numbering (Quadrature / DG
+    spaces: the rows of a block of cells are a block of rows) and a contiguous ascending `cells_K`; otherwise Π is
+    built in one piece.  The matrices are bit-identical to the one-shot calls.
+
+    `host_pi` / `host_c` / `host_mp`: ``(indptr int64, indices int32, values float64)`` with room for the rows and
+    entries (``ValueError`` otherwise).  Returns ``dict(nnz_pi, nnz_c, nnz_mp, rows_pi, rows_c, keep, copy_stream)``:
+    synchronise `copy_stream` before reading the arrays and keep the dict alive until then."""
+    import torch
+
+    from .interpolation import _uses_stock_quadrature, create_interpolation_matrix, device_rows_block, device_space
+    from .sparse import DeviceCSR
+
+    if copy_stream is None:
+        copy_stream = torch.cuda.Stream()
+    k_list = np.asarray(K.dofmap.list)
+    nip = k_list.shape[1]
+    n_cells = k_list.shape[0]
+    cells = np.arange(n_cells, dtype=np.int32) if cells_K is None else np.ascontiguousarray(cells_K, dtype=np.int32)
+    contiguous = cells.size > 0 and int(cells[-1]) - int(cells[0]) + 1 == cells.size and bool(np.all(np.diff(cells) == 1))
+    identity = hasattr(K, "__dict__") and K.__dict__.get("_fxii_identity_dofs")
+    if identity is None:
+        flat = k_list.reshape(-1)
+        identity = bool(np.array_equal(flat, np.arange(flat.shape[0], dtype=flat.dtype)))
+    if not (contiguous and identity and _uses_stock_quadrature(red_op)) or cells.size < pi_pieces:
+        pi_pieces = 1
+    blocks, first_rows = [cells], None
+    if pi_pieces > 1:
+        blocks = np.array_split(cells, pi_pieces)
+        first_rows = device_rows_block(K, red_op, blocks[0], known_contiguous=True)  # None: this K / operator cannot be built block by block
+        if first_rows is None:
+            pi_pieces = 1
+    keep = []
+
+    def mark3(name, done, b0, b1):
+        if marks is not None:
+            marks.extend([(name + " ready (main stream)", done), (name + " D2H begin", b0), (name + " D2H end", b1)])
+
+    def ev():
+        return torch.cuda.Event(enable_timing=marks is not None)
+
+    if pi_pieces == 1:
+        A, _, _ = create_interpolation_matrix(V, K, red_op, tol=tol, cells_K=cells_K)
+        pi_local = A.device
+        if cells_K is not None and contiguous and identity:
+            pi_local = pi_local.row_slice(int(cells[0]) * nip, (int(cells[-1]) + 1) * nip)
+        n_rows, nnz = pi_local.shape[0], pi_local.nnz
+        if host_pi[0].shape[0] < n_rows + 1 or host_pi[1].shape[0] < nnz or host_pi[2].shape[0] < nnz:
+            raise ValueError(f"host arrays for Π too small: {n_rows} rows, {nnz} entries")
+        done, b0, b1 = ev(), ev(), ev()
+        done.record()
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done)
+            b0.record()
+            pi_local.to_host_into(host_pi[0][: n_rows + 1], host_pi[1][:nnz], host_pi[2][:nnz], sync=False)
+            b1.record()
+        mark3("Pi", done, b0, b1)
+        keep += [A, pi_local]
+    else:
+        dspace = device_space(V, tol)
+        n_rows = cells.size * nip
+        if host_pi[0].shape[0] < n_rows + 1:
+            raise ValueError(f"host row pointers for Π too small: {n_rows} rows")
+        host_pi[0][0] = 0
+        h_ptr, h_idx, h_val = (torch.from_numpy(a) for a in host_pi)
+        hints = red_op.__dict__.setdefault("_fxii_nnz_hints", {}) if hasattr(red_op, "__dict__") else {}
+        subs, off, row0 = [], 0, 0
+        for i, blk in enumerate(blocks):
+            # local numbering: the block's Π has blk.size * nip rows
+            t_h0 = time.perf_counter()
+            rows = first_rows if i == 0 else device_rows_block(K, red_op, blk, known_contiguous=True)
+            t_h1 = time.perf_counter()
+            hkey = ("block", id(K), id(V), blk.size, int(blk[0]))
+            if hkey in hints:
+                rows.set_nnz_hint(hints[hkey])
+            sub, st_blk = rows.assemble(dspace)
+            if marks is not None:
+                marks.append((f"host: Pi[{i}] rows handle [host ms]", t_h1 - t_h0))
+                marks.append((f"host: Pi[{i}] assemble call [host ms]", time.perf_counter() - t_h1))
+                marks.append((f"device: Pi[{i}] frames+rows+csr kernels [host ms]", 1e-3 * (st_blk["ms_frames"] + st_blk["ms_locate"] + st_blk["ms_csr"])))
+            hints[hkey] = n = sub.nnz
+            m = sub.shape[0]
+            if h_idx.numel() < off + n or h_val.numel() < off + n:
+                raise ValueError(f"host arrays for Π too small: at least {off + n} entries")
+            ptr, idx, val = sub.device_tensors()
+            if off:
+                ptr[1:].add_(off)  # row ends in the numbering of the concatenated matrix (vstack copies them as they are)
+            done, b0, b1 = ev(), ev(), ev()
+            done.record()
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                b0.record()
+                h_ptr[row0 + 1:row0 + m + 1].copy_(ptr[1:], non_blocking=True)
+                h_idx[off:off + n].copy_(idx, non_blocking=True)
+                h_val[off:off + n].copy_(val, non_blocking=True)
+                b1.record()
+            mark3(f"Pi[{i}]", done, b0, b1)
+            keep += [rows, sub]
+            subs.append(sub)
+            off += n
+            row0 += m
+        pi_local = DeviceCSR.vstack(subs, entry_offsets=[0] * len(subs))  # pointers are already shifted
+        nnz = off
+    out = products.to_host(pi_local, host_c, host_mp, n_sub=c_pieces, copy_stream=copy_stream, marks=marks)
+    out["keep"] = keep + [pi_local] + out["keep"]
+    out.update(nnz_pi=int(nnz), rows_pi=int(n_rows))
+    return out
 
 
 def product_pt_m_p(pi_local, gamma, K, world: int, rank: int, steps: int = 5, flush=None, m_dev=None) -> dict:

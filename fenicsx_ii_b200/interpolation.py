@@ -30,6 +30,16 @@ class PiStats(dict):
     """Counters and per-stage device times of the last assembly (fxii_pi_stats)."""
 
 
+def _check_indices(rc: int):
+    """`_lib.check`, with the device-side index range checks reported as the ValueError the host checks used to raise."""
+    try:
+        _lib.check(rc)
+    except _lib.FxiiError as e:
+        if e.code == _lib.FXII_E_INVALID and "out of range" in str(e):
+            raise ValueError(str(e)) from None
+        raise
+
+
 class DeviceMesh:
     """Ω on the device (affine tetrahedra or Q1 hexahedra): packed cell geometry + LBVH.  Built once per (mesh, tol) and cached on the
     mesh object — the reference rebuilds dolfinx's tree on every call (interpolation.py:66-68)."""
@@ -42,13 +52,12 @@ class DeviceMesh:
             raise ValueError("mesh.geometry.x must have shape (n, 3)")
         if cells.ndim != 2 or cells.shape[1] not in (4, 8):
             raise NotImplementedError("only affine tetrahedra (4 geometry nodes) and Q1 hexahedra (8 geometry nodes) are supported")
-        if cells.size and (cells.min() < 0 or cells.max() >= x.shape[0]):
-            raise ValueError("cell node index out of range")
+        # node indices are range-checked on the device (FXII_E_INVALID -> ValueError)
         self.n_cells, self.n_nodes, self.padding = cells.shape[0], x.shape[0], float(padding)
         out = C.c_void_p()
         s = _lib.current_stream() if stream is None else stream
-        _lib.check(_lib.load().fxii_mesh_create_cells(_lib.ptr(x), x.shape[0], _lib.ptr(cells), cells.shape[0], cells.shape[1],
-                                                      float(padding), s, C.byref(out)))
+        _check_indices(_lib.load().fxii_mesh_create_cells(_lib.ptr(x), x.shape[0], _lib.ptr(cells), cells.shape[0], cells.shape[1],
+                                                          float(padding), s, C.byref(out)))
         self._h = out
 
     def info(self) -> dict:
@@ -72,13 +81,12 @@ class DeviceSpace:
         dofmap = np.ascontiguousarray(dofmap, dtype=np.int32)
         if dofmap.shape[0] != mesh.n_cells:
             raise ValueError("dofmap rows must equal the number of cells")
-        if dofmap.size and (dofmap.min() < 0 or dofmap.max() >= n_dofs):
-            raise ValueError("dof index out of range")
+        # dof indices are range-checked on the device (FXII_E_INVALID -> ValueError)
         self.mesh, self.nd, self.degree, self.n_dofs = mesh, dofmap.shape[1], int(degree), int(n_dofs)
         out = C.c_void_p()
         s = _lib.current_stream() if stream is None else stream
-        _lib.check(_lib.load().fxii_space_create(mesh._h, _lib.ptr(dofmap), dofmap.shape[1], int(degree), int(n_dofs), s,
-                                                 C.byref(out)))
+        _check_indices(_lib.load().fxii_space_create(mesh._h, _lib.ptr(dofmap), dofmap.shape[1], int(degree), int(n_dofs), s,
+                                                     C.byref(out)))
         self._h = out
 
     def __del__(self):
@@ -122,9 +130,14 @@ class DeviceRows:
             table = np.ascontiguousarray(desc["table"], dtype=np.float64)
             w = np.ascontiguousarray(desc["w"], dtype=np.float64)
             if "cell_radius" in desc:
-                cr = desc["cell_radius"] if cells_k is None else desc["cell_radius"][cells_k]
-                radius = np.ascontiguousarray(np.repeat(cr, nip), dtype=np.float64)
-                per_row = 1
+                # one radius per processed cell; the rows of a cell read it on the device (no 6x host expansion)
+                if cells_k is None or desc.get("cell_radius_is_local"):
+                    cr = desc["cell_radius"]  # already the radii of the processed cells, in order
+                else:
+                    cr = desc["cell_radius"][cells_k]
+                radius = np.ascontiguousarray(cr, dtype=np.float64)
+                assert radius.shape[0] == n_cells_k
+                per_row = 2
             else:
                 radius = np.ascontiguousarray(desc["radius"], dtype=np.float64)
                 per_row = 1 if desc.get("radius_per_row") else 0
@@ -371,6 +384,40 @@ def device_rows(K, red_op, cells_K=None, args_only: bool = False):
     return DeviceRows.from_points(q.points, q.weights, q.scales, row_dofs, n_rows_total)
 
 
+def device_rows_block(K, red_op, cells_block: np.ndarray, known_contiguous: bool = False):
+    """A rows handle for a contiguous ascending block of Γ cells with LOCAL row numbering: row r of the block's Π is
+    the dof ``cells_block[0]*nip + r`` of K.  Only for spaces with cell-local dofs (Quadrature / DG: the rows of a block
+    of cells are a block of rows) and the stock operators; returns None otherwise.  Used to build Π block by block
+    (``distributed.assemble_blocks_to_host``) — the block matrices stacked are the matrix of one call."""
+    mesh_to = K.mesh
+    k_list = np.asarray(K.dofmap.list)
+    ref_points = np.asarray(K.element.interpolation_points, dtype=np.float64)
+    cells_block = np.ascontiguousarray(cells_block, dtype=np.int32)
+    if cells_block.size == 0 or k_list.shape[1] != ref_points.shape[0]:
+        return None
+    identity = K.__dict__.get("_fxii_identity_dofs") if hasattr(K, "__dict__") else None
+    if identity is None:
+        flat = k_list.reshape(-1)
+        identity = bool(np.array_equal(flat, np.arange(flat.shape[0], dtype=flat.dtype)))
+        if hasattr(K, "__dict__"):
+            K.__dict__["_fxii_identity_dofs"] = identity
+    contiguous = known_contiguous or (int(cells_block[-1]) - int(cells_block[0]) + 1 == cells_block.size
+                                      and bool(np.all(np.diff(cells_block) == 1)))
+    on_device = _uses_stock_quadrature(red_op) and red_op._mesh is mesh_to and mesh_to.topology.dim == 1 \
+        and np.asarray(mesh_to.geometry.dofmap).shape[1] == 2
+    if not (identity and contiguous and on_device):
+        return None
+    from .restriction_operators import get_physical_points
+
+    desc = dict(red_op.device_descriptor(lambda: get_physical_points(mesh_to, cells_block, ref_points)))
+    if "cell_radius" in desc:  # a contiguous block: its radii are a slice, not a gather
+        desc["cell_radius"] = desc["cell_radius"][int(cells_block[0]):int(cells_block[-1]) + 1]
+        desc["cell_radius_is_local"] = True
+    nip = ref_points.shape[0]
+    return DeviceRows.from_gamma(np.asarray(mesh_to.geometry.x), np.asarray(mesh_to.geometry.dofmap), cells_block, ref_points, None,
+                                 cells_block.size * nip, desc)
+
+
 # Π cache (SURVEY §8f rank 1): the reference rebuilds Π for every integral of every block and twice per
 # assemble (matrix_assembler.py:177,203,229,239,267-294).  Entries hold strong references to their key
 # objects so that `id()` stays unique while an entry lives; least recently used entries are dropped.
@@ -434,7 +481,7 @@ def create_interpolation_matrix(V, K, red_op, tol: float = 1.0e-8, use_petsc: bo
         if gamma_args is not None:
             # host arrays in, host CSR out: ONE C call and one synchronisation
             hints = red_op.__dict__.setdefault("_fxii_nnz_hints", {}) if hasattr(red_op, "__dict__") else {}
-            hkey = (id(K), id(V), None if cells_K is None else len(cells_K))
+            hkey = (id(K), id(V), None if cells_K is None or len(cells_K) == 0 else (len(cells_K), int(cells_K[0]), int(cells_K[-1])))
             indptr_h, indices_h, values_h = host_out
             rows, nnz, stats = DeviceRows.build_to_host(dspace, gamma_args, indptr_h, indices_h, values_h, hints.get(hkey, 0))
             hints[hkey] = nnz
@@ -447,7 +494,7 @@ def create_interpolation_matrix(V, K, red_op, tol: float = 1.0e-8, use_petsc: bo
         rows.set_mode(1)
     # nnz of the previous build with the same (K, operator, cells_K): lets the build allocate up front
     hints = red_op.__dict__.setdefault("_fxii_nnz_hints", {}) if hasattr(red_op, "__dict__") else {}
-    hkey = (id(K), id(V), None if cells_K is None else len(cells_K))
+    hkey = (id(K), id(V), None if cells_K is None or len(cells_K) == 0 else (len(cells_K), int(cells_K[0]), int(cells_K[-1])))
     if hkey in hints:
         rows.set_nnz_hint(hints[hkey])
     if host_out is not None and bs == 1 and not use_petsc:

@@ -71,6 +71,43 @@ class DeviceCSR:
         sub._keepalive = sub._keepalive + (self,)
         return sub
 
+    @classmethod
+    def vstack(cls, blocks, entry_offsets=None) -> "DeviceCSR":
+        """Row-wise concatenation of matrices with the same number of columns, one copy kernel for all arrays (no host
+        synchronisation).  `entry_offsets[i]`: what to add to block i's row pointers on the way — default: the entries
+        of the blocks before it; pass zeros for blocks whose pointers are already in the concatenated numbering."""
+        import torch
+
+        blocks = list(blocks)
+        assert blocks and all(b.shape[1] == blocks[0].shape[1] for b in blocks)
+        assert 3 * len(blocks) <= 32, "at most 10 blocks per concatenation"
+        n_rows, nnz = sum(b.shape[0] for b in blocks), sum(b.nnz for b in blocks)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        ptr = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+        ptr[:1] = 0
+        idx = torch.empty(nnz, dtype=torch.int32, device=dev)
+        val = torch.empty(nnz, dtype=torch.float64, device=dev)
+        dst, src, nbytes, add = [], [], [], []
+        r = e = 0
+        for i, b in enumerate(blocks):
+            p0, p1, p2 = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            _lib.check(_lib.load().fxii_csr_device_ptrs(b._h, C.byref(p0), C.byref(p1), C.byref(p2)))
+            shift = e if entry_offsets is None else int(entry_offsets[i])
+            if b.shape[0]:
+                dst.append(ptr.data_ptr() + 8 * (1 + r)), src.append((p0.value or 0) + 8), nbytes.append(8 * b.shape[0]), add.append(shift)
+            if b.nnz:
+                dst.append(idx.data_ptr() + 4 * e), src.append(p1.value or 0), nbytes.append(4 * b.nnz), add.append(0)
+                dst.append(val.data_ptr() + 8 * e), src.append(p2.value or 0), nbytes.append(8 * b.nnz), add.append(0)
+            r += b.shape[0]
+            e += b.nnz
+        k = len(dst)
+        if k:
+            _lib.check(_lib.load().fxii_copy_segments_async(k, (C.c_void_p * k)(*dst), (C.c_void_p * k)(*src), (C.c_int64 * k)(*nbytes),
+                                                            (C.c_int64 * k)(*add), _lib.current_stream()))
+        out = cls.wrap_device_arrays(ptr, idx, val, (n_rows, blocks[0].shape[1]))
+        out._keepalive = out._keepalive + tuple(blocks)  # the copy is stream-ordered: sources stay alive with the result
+        return out
+
     def validate(self) -> "DeviceCSR":
         """Raise unless indptr is monotone, columns are in range and strictly ascending in every row."""
         _lib.check(_lib.load().fxii_csr_validate(self._h, _lib.current_stream()))

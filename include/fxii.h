@@ -89,7 +89,8 @@ int fxii_space_destroy(fxii_space* s);
  * (cells_K of interpolation.py:47-51).  xref [nip]: reference interpolation points of K (:43).
  * row_dofs [n_cells_k*nip]: K.dofmap.list[cells_K] flattened.  cells_k == NULL: cells 0..n_cells_k-1;
  * row_dofs == NULL: rows 0..n_cells_k*nip-1 (both then need no upload).  table [nq,3], w [nq]: operator
- * tables (NULL for TRACE).  radius: [n_cells_k*nip] when radius_per_row != 0, else [1]. */
+ * tables (NULL for TRACE).  radius: [1] when radius_per_row == 0, [n_cells_k*nip] (one per point row) when 1,
+ * [n_cells_k] (one per processed cell, expanded on the device) when 2. */
 int fxii_rows_create(const double* gx, int64_t n_gnodes, const int32_t* gcells, int64_t n_gcells,
                      const int32_t* cells_k, int64_t n_cells_k, const double* xref, int32_t nip,
                      const int32_t* row_dofs, int64_t n_rows_total, int32_t kind, int32_t nq,

@@ -62,3 +62,47 @@ def test_general_path_row_cap_is_an_error(cuda):
     with pytest.raises(FxiiError) as ei:
         create_interpolation_matrix(V, K, Disk(gamma, 0.05, degree=7))
     assert "16384" in str(ei.value)
+
+
+def test_index_arrays_are_range_checked_on_the_device(cuda):
+    """Cell node indices and dof indices outside their ranges are refused (device-side check, reported as the
+    ValueError the host-side numpy checks used to raise) instead of being dereferenced."""
+    from fenicsx_ii_b200 import synthetic as sy
+    from fenicsx_ii_b200.interpolation import DeviceMesh, DeviceSpace
+
+    mesh = sy.kuhn_box(4, 4, 4)
+    x, cells = np.asarray(mesh.geometry.x), np.asarray(mesh.geometry.dofmap).copy()
+    good = DeviceMesh(x, cells, 1e-8)
+    for bad_value in (-1, x.shape[0]):
+        bad = cells.copy()
+        bad[17, 2] = bad_value
+        with pytest.raises(ValueError, match="cell node index out of range"):
+            DeviceMesh(x, bad, 1e-8)
+    dofmap = cells.copy()
+    DeviceSpace(good, dofmap, 1, x.shape[0])
+    for bad_value in (-3, x.shape[0]):
+        bad = dofmap.copy()
+        bad[-1, 0] = bad_value
+        with pytest.raises(ValueError, match="dof index out of range"):
+            DeviceSpace(good, bad, 1, x.shape[0])
+
+
+def test_large_pageable_uploads_take_the_staged_path_unchanged(cuda):
+    """Host arrays above 32 MiB in pageable memory are uploaded through the threaded pinned staging pipeline
+    (capi.cu: staged_upload); the device copy must equal the source byte for byte — odd sizes, several chunks per
+    worker, and a pinned source (plain copy) beside it."""
+    import torch
+
+    from fenicsx_ii_b200.sparse import DeviceCSR
+
+    rng = np.random.default_rng(7)
+    n_rows, nnz = 1000, (40 << 20) // 8 + 12345  # values: 40 MiB + a ragged tail; indices: 20 MiB (plain path)
+    indptr = np.linspace(0, nnz, n_rows + 1).astype(np.int64)
+    indices = rng.integers(0, 1 << 20, size=nnz, dtype=np.int32)
+    values = rng.standard_normal(nnz)
+    a = DeviceCSR.from_host(indptr, indices, values, (n_rows, 1 << 20))
+    gi, gj, gv = a.to_host()
+    assert np.array_equal(gi, indptr) and np.array_equal(gj, indices) and np.array_equal(gv, values)
+    pinned = torch.from_numpy(values).pin_memory().numpy()
+    b = DeviceCSR.from_host(indptr, indices, pinned, (n_rows, 1 << 20))
+    assert np.array_equal(b.to_host()[2], values)

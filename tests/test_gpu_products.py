@@ -179,6 +179,47 @@ def test_sharded_products_single_rank(cuda):
     check(mp, refm[:3])
 
 
+@pytest.mark.parametrize("n_sub", [1, 3, 4])
+def test_sharded_products_streamed_to_host(cuda, n_sub):
+    """ShardedProducts.to_host — MΠ first, C in `n_sub` row pieces whose downloads overlap the next piece's product —
+    delivers bit for bit the matrices of the one-shot products into the caller's pinned host arrays."""
+    import torch
+
+    from fenicsx_ii_b200.distributed import ShardedProducts, p1_quadrature_coupling
+
+    mesh = sy.kuhn_box(8, 8, 8)
+    V = functionspace(mesh, ("Lagrange", 1))
+    gamma = sy.polyline_network(150, 1 / 8, n_lines=4, lo=0.2, hi=0.8)
+    W = functionspace(gamma, ("Quadrature", 10))
+    Q = functionspace(gamma, ("Lagrange", 1))
+    P, _, _ = create_interpolation_matrix(V, W, Circle(gamma, 0.06, degree=9))
+    diag = quadrature_mass_diagonal(gamma, W)
+    M = p1_quadrature_coupling(gamma, Q, W)
+    prod = ShardedProducts(V.num_dofs, torch.from_numpy(diag).to("cuda"), DeviceCSR.from_scipy(M))
+    c, mp, *_ = prod(P.device)
+    ref_c, ref_mp = c.to_host(), mp.to_host()
+
+    def pinned(n, dtype):
+        return torch.zeros(n, dtype=dtype).pin_memory().numpy()
+
+    host_c = (pinned(V.num_dofs + 1, torch.int64), pinned(c.nnz + 5, torch.int32), pinned(c.nnz + 5, torch.float64))
+    host_mp = (pinned(mp.shape[0] + 1, torch.int64), pinned(mp.nnz, torch.int32), pinned(mp.nnz, torch.float64))
+    for _ in range(2):  # the second call reuses the cached piece boundaries
+        for a in host_c + host_mp:
+            a[:] = 0
+        r = prod.to_host(P.device, host_c, host_mp, n_sub=n_sub)
+        r["copy_stream"].synchronize()
+        assert r["nnz_c"] == c.nnz and r["nnz_mp"] == mp.nnz and r["rows_c"] == V.num_dofs
+        np.testing.assert_array_equal(host_c[0], ref_c[0])
+        np.testing.assert_array_equal(host_c[1][: c.nnz], ref_c[1])
+        np.testing.assert_array_equal(host_c[2][: c.nnz], ref_c[2])
+        for got, ref in zip(host_mp, ref_mp):
+            np.testing.assert_array_equal(got, ref)
+    with pytest.raises(ValueError, match="too small"):
+        prod.to_host(P.device, (host_c[0], host_c[1][:10], host_c[2][:10]), host_mp, n_sub=n_sub)
+    torch.cuda.synchronize()
+
+
 def test_spgemm_keeps_cancellation_and_explicit_zeros(cuda):
     A = sp.csr_matrix(np.array([[1.0, -1.0, 0.0], [0.0, 0.0, 2.0]]))
     B = sp.csr_matrix((np.array([3.0, 3.0, 0.0]), np.array([0, 0, 1]), np.array([0, 1, 2, 3])), shape=(3, 2))
@@ -335,3 +376,47 @@ def test_scale_rows_with_device_diagonal(cuda):
     np.testing.assert_array_equal(a[1], b[1])
     assert a[2].tobytes() == b[2].tobytes()
     np.testing.assert_array_equal(a[2], ref)
+
+
+@pytest.mark.parametrize("pi_pieces,c_pieces,subset", [(1, 1, False), (2, 4, False), (3, 2, True)])
+def test_assemble_blocks_to_host(cuda, pi_pieces, c_pieces, subset):
+    """assemble_blocks_to_host — Π in blocks of Γ cells, each downloaded while the next is built, concatenated on the
+    device for the streamed products — fills the host arrays with exactly the matrices of the one-shot calls."""
+    import torch
+
+    from fenicsx_ii_b200.distributed import ShardedProducts, assemble_blocks_to_host, p1_quadrature_coupling
+
+    mesh = sy.kuhn_box(8, 8, 8)
+    V = functionspace(mesh, ("Lagrange", 1))
+    gamma = sy.polyline_network(150, 1 / 8, n_lines=4, lo=0.2, hi=0.8)
+    W = functionspace(gamma, ("Quadrature", 10))
+    Q = functionspace(gamma, ("Lagrange", 1))
+    nip = W.element.interpolation_points.shape[0]
+    seg_r = np.linspace(0.03, 0.07, 150)
+    op = Circle(gamma, seg_r, degree=9)
+    cells = np.arange(20, 131, dtype=np.int32) if subset else None
+    P, _, _ = create_interpolation_matrix(V, W, op, cells_K=cells)
+    pd = P.device if cells is None else P.device.row_slice(20 * nip, 131 * nip)
+    ref_p = pd.to_host()
+    diag = quadrature_mass_diagonal(gamma, W)
+    M = p1_quadrature_coupling(gamma, Q, W)
+    if subset:  # the products of a sub-block: restrict M_Γ and M to its rows / columns
+        diag = diag[20 * nip:131 * nip]
+        M = M[:, 20 * nip:131 * nip].tocsr()
+    prod = ShardedProducts(V.num_dofs, torch.from_numpy(np.ascontiguousarray(diag)).to("cuda"), DeviceCSR.from_scipy(M))
+    c, mp, *_ = prod(pd)
+    ref_c, ref_mp = c.to_host(), mp.to_host()
+
+    def pinned(n, dtype):
+        return torch.zeros(n, dtype=dtype).pin_memory().numpy()
+
+    def triple(rows, nnz):
+        return pinned(rows + 1, torch.int64), pinned(nnz, torch.int32), pinned(nnz, torch.float64)
+
+    host_pi, host_c, host_mp = triple(pd.shape[0], pd.nnz), triple(V.num_dofs, c.nnz), triple(mp.shape[0], mp.nnz)
+    r = assemble_blocks_to_host(V, W, op, prod, host_pi, host_c, host_mp, cells_K=cells, pi_pieces=pi_pieces, c_pieces=c_pieces)
+    r["copy_stream"].synchronize()
+    assert (r["nnz_pi"], r["nnz_c"], r["nnz_mp"], r["rows_pi"]) == (pd.nnz, c.nnz, mp.nnz, pd.shape[0])
+    for got, ref in ((host_pi, ref_p), (host_c, ref_c), (host_mp, ref_mp)):
+        for g, e in zip(got, ref):
+            np.testing.assert_array_equal(g, e)
