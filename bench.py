@@ -647,9 +647,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--e2e-pieces", type=int, default=4, help="row pieces of C whose downloads overlap the remaining products (e2e)")
-    ap.add_argument("--e2e-pi-pieces", type=int, default=2, help="blocks of Γ cells Π is built in, each downloaded while the next is built (e2e)")
+    ap.add_argument("--e2e-pieces", type=int, default=0, help="row pieces of C whose downloads overlap the remaining products "
+                    "(e2e); 0: by GPU count (4 / 2 / 2 / 1 at 1 / 2 / 4 / 8 GPUs: the fewer bytes a rank downloads, the less there is to hide)")
+    ap.add_argument("--e2e-pi-pieces", type=int, default=0, help="blocks of Γ cells Π is built in, each downloaded while the next is "
+                    "built (e2e); 0: 2 on one GPU, else 1")
     args = ap.parse_args()
+    if args.e2e_pieces <= 0:
+        args.e2e_pieces = {1: 4, 2: 2, 4: 2}.get(args.gpus, 1)
+    if args.e2e_pi_pieces <= 0:
+        args.e2e_pi_pieces = 2 if args.gpus == 1 else 1
     if args.impl == "reference":
         run_reference(args)
     else:

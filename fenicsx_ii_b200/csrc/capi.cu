@@ -321,6 +321,80 @@ void staged_upload(void* dst, const void* src, size_t bytes, cudaStream_t s) {
   for (int t = 0; t < T; ++t)
     if (err[t] != cudaSuccess) throw Error(FXII_E_CUDA, std::string("staged upload: ") + cudaGetErrorString(err[t]));
 }
+
+// The mirror image: a synchronous download into a large PAGEABLE host array (what `MatrixCSR.data` / `.indices` hand to
+// scipy or PETSc: 1 GB for config 5's Π).  Every worker lets the copy engine fill one of its pinned buffers while it
+// copies the other one out to the destination.  Returns after the last byte has reached `dst`.
+void staged_download(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  if (bytes == 0) return;
+  const int T = stage_threads();
+  bool plain = bytes < kStageMin || T == 0;
+  if (!plain) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, dst) != cudaSuccess) {
+      cudaGetLastError();
+      plain = true;
+    } else if (attr.type != cudaMemoryTypeUnregistered) {
+      plain = true;
+    }
+  }
+  if (plain) {
+    FXII_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, s));
+    FXII_CUDA(cudaStreamSynchronize(s));
+    return;
+  }
+  int dev = 0;
+  FXII_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_stage_mutex);
+  std::vector<StageWorker>& ws = g_stage[dev];
+  if ((int)ws.size() < T) {
+    const size_t have = ws.size();
+    ws.resize(T);
+    for (size_t t = have; t < ws.size(); ++t) {
+      FXII_CUDA(cudaStreamCreateWithFlags(&ws[t].stream, cudaStreamNonBlocking));
+      for (int b = 0; b < 2; ++b) {
+        FXII_CUDA(cudaHostAlloc((void**)&ws[t].buf[b], kStageChunk, cudaHostAllocDefault));
+        FXII_CUDA(cudaEventCreateWithFlags(&ws[t].ev[b], cudaEventDisableTiming));
+      }
+    }
+  }
+  FXII_CUDA(cudaStreamSynchronize(s));  // the source is complete
+  const size_t n_chunks = (bytes + kStageChunk - 1) / kStageChunk;
+  std::vector<cudaError_t> err(T, cudaSuccess);
+  std::vector<std::thread> threads;
+  threads.reserve(T);
+  for (int t = 0; t < T; ++t) {
+    threads.emplace_back([&, t] {
+      StageWorker& w = ws[t];
+      cudaError_t e = cudaSetDevice(dev);
+      for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaEventSynchronize(w.ev[b]);  // buffers free of earlier uploads
+      auto issue = [&](size_t c, int b) {
+        const size_t off = c * kStageChunk;
+        const size_t n = std::min(kStageChunk, bytes - off);
+        cudaError_t r = cudaMemcpyAsync(w.buf[b], static_cast<const unsigned char*>(src) + off, n, cudaMemcpyDeviceToHost, w.stream);
+        if (r == cudaSuccess) r = cudaEventRecord(w.ev[b], w.stream);
+        return r;
+      };
+      int b = 0;
+      size_t c = (size_t)t;
+      if (c < n_chunks && e == cudaSuccess) e = issue(c, b);
+      for (; c < n_chunks && e == cudaSuccess; c += (size_t)T, b ^= 1) {
+        const size_t next = c + (size_t)T;
+        if (next < n_chunks) e = issue(next, b ^ 1);  // the copy engine fills the other buffer meanwhile
+        if (e != cudaSuccess) break;
+        e = cudaEventSynchronize(w.ev[b]);
+        if (e != cudaSuccess) break;
+        const size_t off = c * kStageChunk;
+        memcpy(static_cast<unsigned char*>(dst) + off, w.buf[b], std::min(kStageChunk, bytes - off));
+      }
+      if (e != cudaSuccess) cudaStreamSynchronize(w.stream);
+      err[t] = e;
+    });
+  }
+  for (auto& th : threads) th.join();
+  for (int t = 0; t < T; ++t)
+    if (err[t] != cudaSuccess) throw Error(FXII_E_CUDA, std::string("staged download: ") + cudaGetErrorString(err[t]));
+}
 }  // namespace fxii
 
 namespace fxii {
@@ -934,9 +1008,10 @@ int fxii_csr_download(const fxii_csr* a, int64_t* indptr, int32_t* indices, doub
   return guarded([&] {
     FXII_CHECK(a, "null csr");
     cudaStream_t s = S(stream);
-    if (indptr) FXII_CUDA(cudaMemcpyAsync(indptr, a->indptr.p, sizeof(int64_t) * (size_t)(a->n_rows + 1), cudaMemcpyDeviceToHost, s));
-    if (indices && a->nnz) FXII_CUDA(cudaMemcpyAsync(indices, a->indices.p, sizeof(int32_t) * (size_t)a->nnz, cudaMemcpyDeviceToHost, s));
-    if (values && a->nnz) FXII_CUDA(cudaMemcpyAsync(values, a->values.p, sizeof(double) * (size_t)a->nnz, cudaMemcpyDeviceToHost, s));
+    // large pageable destinations take the pipelined staging copy (each call returns with its array complete)
+    if (indptr) fxii::staged_download(indptr, a->indptr.p, sizeof(int64_t) * (size_t)(a->n_rows + 1), s);
+    if (indices && a->nnz) fxii::staged_download(indices, a->indices.p, sizeof(int32_t) * (size_t)a->nnz, s);
+    if (values && a->nnz) fxii::staged_download(values, a->values.p, sizeof(double) * (size_t)a->nnz, s);
     FXII_CUDA(cudaStreamSynchronize(s));
   });
 }

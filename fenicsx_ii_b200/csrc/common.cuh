@@ -64,6 +64,8 @@ void event_release(cudaEvent_t e);
 void cache_trim();  // return all cached blocks to the driver
 // host -> device copy ordered on s; large pageable sources go through a threaded, pipelined pinned staging copy
 void staged_upload(void* dst, const void* src, size_t bytes, cudaStream_t s);
+// device -> host copy that has COMPLETED on return; large pageable destinations go through the same staging buffers
+void staged_download(void* dst, const void* src, size_t bytes, cudaStream_t s);
 
 // Device -> host reads of a few bytes WITHOUT the copy engine.  A cudaMemcpyAsync(DeviceToHost) of 8 bytes queues behind
 // every download in flight on any stream (one D2H engine): with a 1 GB CSR download running on a side stream each of

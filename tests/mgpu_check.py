@@ -50,6 +50,26 @@ def main():
     c_w, mp_w, ip, nnz_a, ip_mp = prod(pi_local)
     c_w2 = prod(pi_local)[0]  # second call: cached plan, no size exchange
     assert c_w2.to_host()[2].tobytes() == c_w.to_host()[2].tobytes()
+    # the same blocks through the host-delivery path (Π in blocks of Γ cells, C in row pieces, overlapped downloads):
+    # every rank's host arrays must hold exactly its device results
+    from fenicsx_ii_b200.distributed import assemble_blocks_to_host
+
+    def pinned(n, dtype):
+        return torch.zeros(max(int(n), 1), dtype=dtype).pin_memory().numpy()
+
+    def triple(rows, nnz):
+        return pinned(rows + 1, torch.int64), pinned(nnz, torch.int32), pinned(nnz, torch.float64)
+
+    h_pi, h_c, h_mp = triple(pi_local.shape[0], pi_local.nnz), triple(c_w.shape[0], c_w.nnz), triple(mp_w.shape[0], mp_w.nnz)
+    r = assemble_blocks_to_host(V, K, op, prod, h_pi, h_c, h_mp, cells_K=np.arange(c0, c1, dtype=np.int32), pi_pieces=2, c_pieces=3)
+    r["copy_stream"].synchronize()
+    host_ok = True
+    for name, got, mat in (("Pi", h_pi, pi_local), ("C", h_c, c_w), ("MPi", h_mp, mp_w)):
+        for g, e, what in zip(got, mat.to_host(), ("indptr", "indices", "values")):
+            if g.shape != e.shape or g.tobytes() != e.tobytes():
+                host_ok = False
+                print(f"rank {rank}: host delivery MISMATCH {name}.{what}", flush=True)
+    del r
     # gather the windows (they are row shards of C and of MΠ)
     gc = allgatherv_csr(*c_w.device_tensors(), packed=False)
     gm = allgatherv_csr(*mp_w.device_tensors(), packed=False)
@@ -67,6 +87,10 @@ def main():
         print(f"world={world} scale={scale} nnz(Pi)={full.nnz} nnz(C)={ref_c.nnz} nnz(MPi)={ref_mp.nnz} windows={prod.plan.windows}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
+    hflag = torch.tensor([1 if host_ok else 0], device="cuda")
+    dist.all_reduce(hflag, op=dist.ReduceOp.MIN)
+    flag = torch.minimum(flag, hflag)
+    ok = ok and int(hflag.item()) == 1
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
