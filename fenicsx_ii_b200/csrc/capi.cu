@@ -565,11 +565,11 @@ int fxii_space_create(fxii_mesh* mesh, const int32_t* dofmap, int32_t nd, int32_
                       fxii_space** out) {
   return guarded([&] {
     FXII_CHECK(mesh && dofmap && out, "null argument");
-    const bool tet_ok = mesh->npc == 4 && ((degree == 1 && nd == 4) || (degree == 2 && nd == 10));
+    const bool tet_ok = mesh->npc == 4 && ((degree == 1 && nd == 4) || (degree == 2 && nd == 10) || (degree == 3 && nd == 20));
     const bool hex_ok = mesh->npc == 8 && degree == 1 && nd == 8;
     if (!(tet_ok || hex_ok))
       throw fxii::Error(FXII_E_UNSUPPORTED,
-                        "supported spaces: Lagrange P1 (nd=4) / P2 (nd=10) on affine tetrahedra, Q1 (nd=8) on hexahedra");
+                        "supported spaces: Lagrange P1 (nd=4) / P2 (nd=10) / P3 (nd=20) on affine tetrahedra, Q1 (nd=8) on hexahedra");
     auto* s = new fxii_space();
     s->mesh = mesh;
     s->nd = nd;

@@ -576,6 +576,82 @@ __device__ __forceinline__ void make_point(int kind, const double* __restrict__ 
   S = f[14];
 }
 
+// ---- P3 (Lagrange degree 3 on tetrahedra, basix's default gll_warped variant) ---------------------------------------
+// phi_i = sum_k c_p3[i][k] * m_k, m_k the 20 barycentric monomials l0^a l1^b l2^c l3^d (a+b+c+d = 3, a outermost, then
+// b, then c).  The nodal basis is dual to point evaluation at: the vertices; on every edge (2,3),(1,3),(1,2),(0,3),
+// (0,2),(0,1) the two Gauss-Lobatto-Legendre abscissae (1 -+ 1/sqrt 5)/2 measured from the edge's first vertex; the
+// centroids of the faces (1,2,3),(0,2,3),(0,1,3),(0,1,2).  Lagrange elements need no dof transformation at tabulation
+// time (they are permutations dolfinx applies to the dofmap), so the reference basis is used as is.  The table is a
+// constant of the element: computed once on the host (Gaussian elimination of the 20x20 collocation matrix).
+__constant__ double c_p3[20 * 20];
+
+static void p3_exponents(int (*ex)[4]) {
+  int k = 0;
+  for (int a = 0; a < 4; ++a)
+    for (int b = 0; b < 4 - a; ++b)
+      for (int c = 0; c < 4 - a - b; ++c) {
+        ex[k][0] = a; ex[k][1] = b; ex[k][2] = c; ex[k][3] = 3 - a - b - c;
+        ++k;
+      }
+}
+
+static void ensure_p3_table() {
+  static int ready_dev = -1;
+  int dev = 0;
+  FXII_CUDA(cudaGetDevice(&dev));
+  if (ready_dev == dev) return;
+  static const int edges[6][2] = {{2, 3}, {1, 3}, {1, 2}, {0, 3}, {0, 2}, {0, 1}};
+  static const int faces[4][3] = {{1, 2, 3}, {0, 2, 3}, {0, 1, 3}, {0, 1, 2}};
+  double node[20][4] = {};
+  int n = 0;
+  for (int v = 0; v < 4; ++v) node[n++][v] = 1.0;
+  const double t[2] = {0.5 - 0.5 / sqrt(5.0), 0.5 + 0.5 / sqrt(5.0)};
+  for (int e = 0; e < 6; ++e)
+    for (int k = 0; k < 2; ++k) {
+      node[n][edges[e][0]] = 1.0 - t[k];
+      node[n][edges[e][1]] = t[k];
+      ++n;
+    }
+  for (int f = 0; f < 4; ++f) {
+    for (int k = 0; k < 3; ++k) node[n][faces[f][k]] = 1.0 / 3.0;
+    ++n;
+  }
+  int ex[20][4];
+  p3_exponents(ex);
+  // A[j][k] = m_k(node_j); solve A X = I: column i of X holds the monomial coefficients of phi_i
+  double A[20][40];
+  for (int j = 0; j < 20; ++j) {
+    for (int k = 0; k < 20; ++k) {
+      double m = 1.0;
+      for (int d = 0; d < 4; ++d)
+        for (int q = 0; q < ex[k][d]; ++q) m *= node[j][d];
+      A[j][k] = m;
+    }
+    for (int k = 0; k < 20; ++k) A[j][20 + k] = (j == k) ? 1.0 : 0.0;
+  }
+  for (int c = 0; c < 20; ++c) {  // Gauss-Jordan with partial pivoting (condition number ~40)
+    int piv = c;
+    for (int r = c + 1; r < 20; ++r)
+      if (fabs(A[r][c]) > fabs(A[piv][c])) piv = r;
+    FXII_CHECK(fabs(A[piv][c]) > 1e-12, "P3 collocation matrix is singular");
+    if (piv != c)
+      for (int k = 0; k < 40; ++k) std::swap(A[piv][k], A[c][k]);
+    const double inv = 1.0 / A[c][c];
+    for (int k = 0; k < 40; ++k) A[c][k] *= inv;
+    for (int r = 0; r < 20; ++r) {
+      if (r == c) continue;
+      const double f = A[r][c];
+      if (f != 0.0)
+        for (int k = 0; k < 40; ++k) A[r][k] -= f * A[c][k];
+    }
+  }
+  double coef[400];
+  for (int i = 0; i < 20; ++i)
+    for (int k = 0; k < 20; ++k) coef[20 * i + k] = A[k][20 + i];
+  FXII_CUDA(cudaMemcpyToSymbol(c_p3, coef, sizeof(coef)));
+  ready_dev = dev;
+}
+
 // basis values of the owning cell at the point, scaled: (phi*W)/S  (interpolation.py:234-238)
 template <int ND>
 __device__ __forceinline__ void tabulate_vals(const double* __restrict__ cellgeo, int cell, const double* p, double W,
@@ -595,6 +671,31 @@ __device__ __forceinline__ void tabulate_vals(const double* __restrict__ cellgeo
   double X[3];
   pull_back(g, p, X);
   const double lam[4] = {((1.0 - X[0]) - X[1]) - X[2], X[0], X[1], X[2]};
+  if (ND == 20) {  // P3: table-driven (c_p3), monomials in the order of p3_exponents
+    double pw[4][4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      pw[d][0] = 1.0;
+      pw[d][1] = lam[d];
+      pw[d][2] = lam[d] * lam[d];
+      pw[d][3] = pw[d][2] * lam[d];
+    }
+    double m[20];
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4 - a; ++b)
+#pragma unroll
+        for (int c = 0; c < 4 - a - b; ++c) m[k++] = ((pw[0][a] * pw[1][b]) * pw[2][c]) * pw[3][3 - a - b - c];
+    for (int i = 0; i < 20; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < 20; ++q) acc += c_p3[20 * i + q] * m[q];
+      vals[i % ND] = (acc * W) / S;
+    }
+    return;
+  }
   double phi[ND];
   if (ND == 4) {
 #pragma unroll
@@ -2129,7 +2230,9 @@ void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr
   float ms_count = 0.f, ms_fill = 0.f, ms_fr_f = 0.f, ms_loc_f = 0.f, ms_csr_f = 0.f;
   bool fused = false;
   // a handle whose rows were found not to be cell-local (continuous K) goes straight to the COO path from then on
-  if (rows->mode != 1 && !rows->not_cell_local) {
+  if (nd == 20) ensure_p3_table();
+  // (P3 takes the general path: its 20-entry point records do not fit the fused kernel's per-team sort budget)
+  if (rows->mode != 1 && !rows->not_cell_local && nd != 20) {
     fused = pi_assemble_fused(sp, rows, s, out, &h, &ms_fr_f, &ms_loc_f, &ms_csr_f);
     if (!fused && rows->host_result && static_cast<FusedResult*>(rows->host_result)->conflict == 1) rows->not_cell_local = true;
   }
@@ -2155,6 +2258,11 @@ void pi_assemble(const fxii_space* sp, fxii_rows* rows, cudaStream_t s, fxii_csr
             rows->coo_cols.p, rows->coo_vals.p, counters.p); FXII_LAUNCHED(1); }
       else if (nd == 8)
         { pi_locate_tabulate_kernel<8><<<grid, threads, smem, s>>>(
+            m->wnodes.p, m->grid, m->cellgeo.p, m->x.p, cn, m->padding, sp->dofmap.p, rows->frames.p, rows->table.p, rows->w.p,
+            rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, nq, (rows->kind != FXII_OP_POINTS) ? packet_mode() : 0, Np, rows->cell.p, rows->ncoll.p, rows->points.p,
+            rows->coo_cols.p, rows->coo_vals.p, counters.p); FXII_LAUNCHED(1); }
+      else if (nd == 20)
+        { pi_locate_tabulate_kernel<20><<<grid, threads, smem, s>>>(
             m->wnodes.p, m->grid, m->cellgeo.p, m->x.p, cn, m->padding, sp->dofmap.p, rows->frames.p, rows->table.p, rows->w.p,
             rows->pts_in.p, rows->w_in.p, rows->s_in.p, rows->kind, nq, (rows->kind != FXII_OP_POINTS) ? packet_mode() : 0, Np, rows->cell.p, rows->ncoll.p, rows->points.p,
             rows->coo_cols.p, rows->coo_vals.p, counters.p); FXII_LAUNCHED(1); }

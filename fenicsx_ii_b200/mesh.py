@@ -134,10 +134,43 @@ def _tet_p2_dofmap(cells: np.ndarray, n_nodes: int) -> tuple[np.ndarray, int]:
     return dof_list, n_nodes + uniq.shape[0]
 
 
+_TET_FACES = ((1, 2, 3), (0, 2, 3), (0, 1, 3), (0, 1, 2))  # basix reference tetrahedron
+
+
+def _tet_p3_dofmap(cells: np.ndarray, n_nodes: int) -> tuple[np.ndarray, int]:
+    """Vertex dofs, two dofs per mesh edge, one per mesh face; cell-local order = basix P3 order (vertices, edges,
+    faces).  The two dofs of an edge are numbered along its REFERENCE direction, from the vertex with the lower global
+    index to the higher one — the permutation dolfinx applies to the dofmap of a cell that sees the edge reversed — so
+    cells sharing an edge agree on which dof sits near which vertex (the space is conforming)."""
+    cells64 = cells.astype(np.int64)
+    ekeys, flipped = [], []
+    for a, b in _TET_EDGES:
+        va, vb = cells64[:, a], cells64[:, b]
+        ekeys.append(np.minimum(va, vb) * n_nodes + np.maximum(va, vb))
+        flipped.append(va > vb)  # the cell's local direction a -> b runs against the reference direction
+    ekeys = np.stack(ekeys, axis=1)
+    flipped = np.stack(flipped, axis=1)
+    uniq_e, inv_e = np.unique(ekeys.reshape(-1), return_inverse=True)
+    edge_id = inv_e.reshape(ekeys.shape)
+    n_edges = uniq_e.shape[0]
+    first = n_nodes + 2 * edge_id + flipped   # local dof 0 (nearer local vertex a)
+    second = n_nodes + 2 * edge_id + (~flipped)
+    ftri = np.stack([np.sort(cells64[:, list(f)], axis=1) for f in _TET_FACES], axis=1)  # [cells, 4, 3] sorted vertices
+    if n_nodes < 2_000_000:  # the packed key fits 63 bits
+        fkeys = (ftri[:, :, 0] * n_nodes + ftri[:, :, 1]) * n_nodes + ftri[:, :, 2]
+        uniq_f, inv_f = np.unique(fkeys.reshape(-1), return_inverse=True)
+    else:
+        uniq_f, inv_f = np.unique(ftri.reshape(-1, 3), axis=0, return_inverse=True)
+    face_dofs = n_nodes + 2 * n_edges + np.asarray(inv_f).reshape(cells.shape[0], 4)
+    edge_dofs = np.stack([first, second], axis=2).reshape(cells.shape[0], 12)
+    dof_list = np.concatenate([cells64, edge_dofs, face_dofs], axis=1).astype(np.int32)
+    return dof_list, n_nodes + 2 * n_edges + uniq_f.shape[0]
+
+
 def functionspace(mesh: Mesh, element, dof_list: np.ndarray | None = None, n_dofs: int | None = None) -> FunctionSpace:
     """``dolfinx.fem.functionspace`` for the element families the hot path supports.
 
-    3D (tetrahedra): ("Lagrange", 1|2).  1D (intervals): ("Quadrature", q) — the ``(q+2)//2``
+    3D (tetrahedra): ("Lagrange", 1|2|3).  1D (intervals): ("Quadrature", q) — the ``(q+2)//2``
     Gauss points per cell, cell-local dofs; ("DG", k) k=0,1,2; ("Lagrange", 1|2).
     A precomputed ``dof_list`` (e.g. the closed-form P2 numbering of a structured mesh) may be given."""
     bs = 1
@@ -157,13 +190,15 @@ def functionspace(mesh: Mesh, element, dof_list: np.ndarray | None = None, n_dof
             raise NotImplementedError("hexahedra: Lagrange degree 1 (Q1)")
         return FunctionSpace(mesh, Element("Lagrange", 1, np.zeros((0, 3))), DofMap(cells.copy(), n_nodes))
     if tdim == 3:
-        if family != "Lagrange" or degree not in (1, 2):
-            raise NotImplementedError("3D spaces: Lagrange degree 1 or 2 on affine tetrahedra")
+        if family != "Lagrange" or degree not in (1, 2, 3):
+            raise NotImplementedError("3D spaces: Lagrange degree 1, 2 or 3 on affine tetrahedra")
         if dof_list is None:
             if degree == 1:
                 dof_list, n_dofs = cells.copy(), n_nodes
-            else:
+            elif degree == 2:
                 dof_list, n_dofs = _tet_p2_dofmap(cells, n_nodes)
+            else:
+                dof_list, n_dofs = _tet_p3_dofmap(cells, n_nodes)
         pts = np.zeros((0, 3))
         return FunctionSpace(mesh, Element("Lagrange", degree, pts), DofMap(dof_list, int(n_dofs)))
     if tdim != 1:

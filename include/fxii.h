@@ -79,7 +79,9 @@ int fxii_mesh_info(const fxii_mesh* m, int64_t* n_cells, int64_t* n_nodes, int64
 int fxii_mesh_destroy(fxii_mesh* m);
 
 /* ---- V space ----------------------------------------------------------------------------- */
-/* dofmap: [n_cells, nd] i32, basix dof order: tetrahedra nd = 4 (degree 1) or 10 (degree 2); hexahedra nd = 8 (Q1). */
+/* dofmap: [n_cells, nd] i32, basix dof order: tetrahedra nd = 4 (degree 1), 10 (degree 2) or 20 (degree 3, basix's default
+ * gll_warped variant; the orientation of shared edges is in the dofmap, as dolfinx builds it); hexahedra nd = 8 (Q1).
+ * Indices outside [0, n_dofs) are refused (FXII_E_INVALID, checked on the device). */
 int fxii_space_create(fxii_mesh* mesh, const int32_t* dofmap, int32_t nd, int32_t degree,
                       int64_t n_dofs, void* stream, fxii_space** out);
 int fxii_space_destroy(fxii_space* s);

@@ -124,6 +124,10 @@ CASES = {
     "circle_hex_tapered_dg1": dict(n=(5, 5, 5), p=1, hex=0.3, gamma=("network", 40, 1 / 5, 2), K=("DG", 1), op=("circle", 0.05, 7)),
     "disk_hex_tapered_p1k_firstvisit": dict(n=(5, 6, 4), p=1, hex=-0.2, gamma=("network", 40, 1 / 5, 2), K=("Lagrange", 1),
                                             op=("disk", 0.04, 3)),
+    # P3 on tetrahedra (tests/test_interpolation_matrix.py:181 builds V = ("Lagrange", 3)): 20 dofs per cell, edge dofs
+    # oriented by the dofmap
+    "circle_p3v_quadrature": dict(n=(3, 3, 4), p=3, gamma=("network", 24, 1 / 3, 2), K=("Quadrature", 3), op=("circle", 0.07, 6)),
+    "trace_p3v_p1k_firstvisit": dict(n=(3, 3, 3), p=3, gamma=("network", 20, 1 / 3, 2), K=("Lagrange", 1), op=("trace",)),
 }
 
 
@@ -139,7 +143,7 @@ def build_case(spec):
     elif bs > 1:
         V = functionspace(mesh, ("Lagrange", spec["p"], (bs,)))
     else:
-        V = functionspace(mesh, ("Lagrange", 1)) if spec["p"] == 1 else sy.kuhn_p2_space(mesh)
+        V = functionspace(mesh, ("Lagrange", spec["p"])) if spec["p"] in (1, 3) else sy.kuhn_p2_space(mesh)
     g = spec["gamma"]
     if g[0] == "line":
         gamma = sy.straight_line(g[1])
@@ -149,8 +153,10 @@ def build_case(spec):
     return mesh, V, gamma, K
 
 
-def pi_fixtures():
+def pi_fixtures(only=None):
     for name, spec in CASES.items():
+        if only and name not in only:
+            continue
         mesh, V, gamma, K = build_case(spec)
         m3, m1, Vs, Ks = shim_spaces(mesh, V, gamma, K)
         op = spec["op"]
@@ -178,5 +184,7 @@ def pi_fixtures():
 
 
 if __name__ == "__main__":
-    quadrature_fixture()
-    pi_fixtures()
+    only = set(sys.argv[1:])  # case names: regenerate just these Π fixtures
+    if not only:
+        quadrature_fixture()
+    pi_fixtures(only)

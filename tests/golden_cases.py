@@ -34,6 +34,10 @@ CASES = {
     "circle_hex_tapered_dg1": dict(n=(5, 5, 5), p=1, hex=0.3, gamma=("network", 40, 1 / 5, 2), K=("DG", 1), op=("circle", 0.05, 7)),
     "disk_hex_tapered_p1k_firstvisit": dict(n=(5, 6, 4), p=1, hex=-0.2, gamma=("network", 40, 1 / 5, 2), K=("Lagrange", 1),
                                             op=("disk", 0.04, 3)),
+    # P3 on tetrahedra (tests/test_interpolation_matrix.py:181 builds V = ("Lagrange", 3)): 20 dofs per cell, edge dofs
+    # oriented by the dofmap
+    "circle_p3v_quadrature": dict(n=(3, 3, 4), p=3, gamma=("network", 24, 1 / 3, 2), K=("Quadrature", 3), op=("circle", 0.07, 6)),
+    "trace_p3v_p1k_firstvisit": dict(n=(3, 3, 3), p=3, gamma=("network", 20, 1 / 3, 2), K=("Lagrange", 1), op=("trace",)),
 }
 
 
@@ -58,7 +62,7 @@ def load_case(name):
     elif bs > 1:
         V = functionspace(mesh, ("Lagrange", spec["p"], (bs,)))
     else:
-        V = functionspace(mesh, ("Lagrange", 1)) if spec["p"] == 1 else sy.kuhn_p2_space(mesh)
+        V = functionspace(mesh, ("Lagrange", spec["p"])) if spec["p"] in (1, 3) else sy.kuhn_p2_space(mesh)
     from fenicsx_ii_b200.mesh import Mesh
 
     gamma = Mesh(fx["gamma_x"], fx["gamma_cells"], tdim=1, name="gamma")

@@ -9,6 +9,7 @@ import pytest
 from fenicsx_ii_b200 import create_interpolation_matrix
 from fenicsx_ii_b200 import synthetic as sy
 from fenicsx_ii_b200.mesh import functionspace
+from oracle import pi_oracle as orc
 from tests.helpers import assert_csr_parity, make_operator, oracle_pi, small_cfg
 
 pytestmark = pytest.mark.gpu
@@ -408,3 +409,57 @@ def test_continuous_k_remembers_the_general_path(cuda):
     assert A1.data.tobytes() == A2.data.tobytes() == out[0][2].tobytes()
     ref = oracle_pi(V, K, gamma, "circle", 0.05, 7)
     assert_csr_parity((A2.indptr, A2.indices, A2.data), ref)
+
+
+# ---- P3 (tests/test_interpolation_matrix.py:174-247 of the reference: V = ("Lagrange", 3)) -------------------------------
+def _p3_dof_coordinates(V):
+    mesh = V.mesh
+    P = np.einsum("nv,cvd->cnd", orc.p3_nodes(), mesh.geometry.x[mesh.geometry.dofmap])
+    coords = np.zeros((V.num_dofs, 3))
+    coords[V.dofmap.list.reshape(-1)] = P.reshape(-1, 3)
+    return coords
+
+
+@pytest.mark.parametrize("op_name", ["trace", "circle", "disk"])
+def test_p3_parity_with_oracle(cuda, op_name):
+    mesh = sy.kuhn_box(4, 3, 5)
+    V = functionspace(mesh, ("Lagrange", 3))
+    gamma = sy.polyline_network(40, 0.2, n_lines=3, lo=0.3, hi=0.7)
+    K = functionspace(gamma, ("Quadrature", 4))
+    radius, degree = (None, None) if op_name == "trace" else ((0.06, 7) if op_name == "circle" else (0.05, 3))
+    op = make_operator(op_name, gamma, radius, degree)
+    A, _, _ = create_interpolation_matrix(V, K, op)
+    ref = oracle_pi(V, K, gamma, op_name, radius, degree)
+    cell, ncoll = A.rows.diagnostics()
+    np.testing.assert_array_equal(cell, ref["cell"])
+    assert_csr_parity((A.indptr, A.indices, A.data), ref)
+
+
+@pytest.mark.parametrize("case", [1, 2, 3])
+@pytest.mark.parametrize("family,degree", [("Lagrange", 2), ("DG", 2), ("Quadrature", 3)])
+def test_p3_circle_trace_of_polynomials(cuda, family, degree, case):
+    """The reference's own `test_circle_trace` (tests/test_interpolation_matrix.py:174-247), cases with a polynomial f:
+    V = P3 represents f exactly, so Π applied to the nodal interpolant of f equals the interpolant of the circle
+    average of f in K — x2 -> x2, x0²+x1² -> R², x2(x0²+x1²) -> x2 R² for a line along x2 through the origin."""
+    from fenicsx_ii_b200 import Circle
+    from fenicsx_ii_b200.mesh import Mesh
+
+    mesh = sy.kuhn_box(4, 4, 4)
+    mesh = Mesh(mesh.geometry.x * 2.0 - np.array([1.0, 1.0, 0.0]), mesh.geometry.dofmap, tdim=3)  # [-1,1]^2 x [0,2]
+    V = functionspace(mesh, ("Lagrange", 3))
+    nodes = np.zeros((9, 3))
+    nodes[:, 2] = np.linspace(0.1, 1.9, 9)
+    gamma = sy.line_mesh(nodes)
+    K = functionspace(gamma, (family, degree))
+    R = 0.53
+    f = {1: lambda x: x[:, 2], 2: lambda x: x[:, 0] ** 2 + x[:, 1] ** 2, 3: lambda x: x[:, 2] * (x[:, 0] ** 2 + x[:, 1] ** 2)}[case]
+    pif = {1: lambda z: z, 2: lambda z: np.full_like(z, R * R), 3: lambda z: z * R * R}[case]
+    A, _, _ = create_interpolation_matrix(V, K, Circle(gamma, R, degree=6))
+    u = f(_p3_dof_coordinates(V))
+    b = A.to_scipy() @ u
+    # K's interpolation points in physical space (cell-local dofs for DG / Quadrature; shared for Lagrange)
+    xr = np.asarray(K.element.interpolation_points).reshape(-1)
+    z = nodes[gamma.geometry.dofmap[:, 0], 2][:, None] * (1 - xr)[None, :] + nodes[gamma.geometry.dofmap[:, 1], 2][:, None] * xr[None, :]
+    expect = np.zeros(K.num_dofs)
+    expect[K.dofmap.list.reshape(-1)] = pif(z.reshape(-1))
+    np.testing.assert_allclose(b, expect, rtol=1e-12, atol=1e-12)

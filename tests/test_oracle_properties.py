@@ -242,3 +242,41 @@ def test_hex_oracle_newton_and_ownership():
     u = 0.3 * x[:, 0] - 1.7 * x[:, 1] + 0.5 * x[:, 2] + 2.0
     np.testing.assert_allclose(np.einsum("nv,nv->n", phi, u[cells[c]]), 0.3 * pts[:, 0] - 1.7 * pts[:, 1] + 0.5 * pts[:, 2] + 2.0,
                                rtol=0, atol=1e-13)
+
+
+# ---- P3 (gll_warped) on tetrahedra ------------------------------------------------------------------------------------
+def test_p3_basis_is_nodal_and_reproduces_cubics():
+    """φ_i(node_j) = δ_ij at the gll_warped nodes, Σφ = 1, and Σ f(node_i) φ_i = f for every cubic f."""
+    nodes = orc.p3_nodes()
+    assert nodes.shape == (20, 4) and np.allclose(nodes.sum(axis=1), 1.0)
+    t = nodes[4:16].reshape(6, 2, 4)
+    for e, (a, b) in enumerate(orc.P2_EDGES):  # edge nodes: GLL abscissae measured from the edge's first vertex
+        np.testing.assert_allclose(t[e, :, b], [0.5 - 0.5 / np.sqrt(5), 0.5 + 0.5 / np.sqrt(5)], atol=1e-15)
+        np.testing.assert_allclose(t[e, :, a] + t[e, :, b], 1.0, atol=1e-15)
+    np.testing.assert_allclose(orc.tabulate(3, nodes[:, 1:]), np.eye(20), atol=1e-14)
+    rng = np.random.default_rng(3)
+    X = rng.dirichlet(np.ones(4), size=200)[:, 1:]
+    phi = orc.tabulate(3, X)
+    np.testing.assert_allclose(phi.sum(axis=1), 1.0, atol=1e-14)
+    for f in (lambda x: x[:, 0] ** 3 - 2 * x[:, 0] * x[:, 1] * x[:, 2] + x[:, 2] ** 2, lambda x: (x[:, 0] + 2 * x[:, 1] - x[:, 2]) ** 3):
+        np.testing.assert_allclose(phi @ f(nodes[:, 1:]), f(X), atol=1e-13)
+
+
+def test_p3_dofmap_is_conforming():
+    """The P3 dofmap of fenicsx_ii_b200.mesh (vertex, 2 per edge oriented low -> high global vertex, 1 per face): every
+    dof has ONE physical location whichever cell it is seen from, and the counts are those of the mesh entities."""
+    from fenicsx_ii_b200 import synthetic as sy
+    from fenicsx_ii_b200.mesh import functionspace
+
+    mesh = sy.kuhn_box(3, 2, 2)
+    V = functionspace(mesh, ("Lagrange", 3))
+    x, cells, dl = mesh.geometry.x, mesh.geometry.dofmap, V.dofmap.list
+    assert dl.shape == (cells.shape[0], 20) and np.array_equal(dl[:, :4], cells)
+    P = np.einsum("nv,cvd->cnd", orc.p3_nodes(), x[cells])  # [cells, 20, 3]
+    coords = np.full((V.num_dofs, 3), np.nan)
+    for c in range(cells.shape[0]):
+        seen = ~np.isnan(coords[dl[c], 0])
+        np.testing.assert_allclose(coords[dl[c]][seen], P[c][seen], atol=1e-14)
+        coords[dl[c]] = P[c]
+    assert not np.isnan(coords).any() and np.unique(dl).shape[0] == V.num_dofs
+    assert np.unique(np.round(coords, 12), axis=0).shape[0] == V.num_dofs  # distinct dofs sit at distinct points
