@@ -207,6 +207,7 @@ void d2h_small(void* host, const void* dev, size_t bytes, cudaStream_t s) {
     return;
   }
   fetch_kernel<<<1, 64, 0, s>>>(f.page + f.used, static_cast<const unsigned char*>(dev), (int)bytes);
+  FXII_LAUNCHED(1);
   FXII_CUDA(cudaGetLastError());
   f.items.push_back({host, f.used, bytes});
   f.used += need;

@@ -573,8 +573,25 @@ __device__ __forceinline__ void warp_sort_regs(uint64_t (&key)[R], int lane) {
 // registers per step, 64-bit address arithmetic, a max-reduction per step for rows of B longer than G.  Now the loads
 // of S steps are issued together into registers (no pipeline moves, S*2 loads in flight per lane), the steps are
 // unrolled, and only the rows of B that are longer than G take a second pass for their tails.
+// Resident blocks per SM the compiler must leave room for (0: no constraint), per register-sort width R.  Round 2 A/B
+// on config 5 (profiles/r02_spgemm_occupancy_ab.txt): the two widest numeric bins were latency bound at low occupancy —
+// R = 16 (80 registers, 3 blocks/SM, 37 % warps active, 46 % issue active) and R = 8 (64 registers, 4 blocks/SM);
+// capping them at 64 and 48 registers (no spills / 8 bytes) gives 4 and 5 blocks/SM: 17.38 -> 16.29 ms for
+// C = Pi^T (M_Gamma Pi).  The narrower bins are issue bound: more resident warps changed nothing (R = 4, 2 at 6 blocks).
+#ifndef FXII_R16_MINBLOCKS
+#define FXII_R16_MINBLOCKS 4
+#endif
+#ifndef FXII_R8_MINBLOCKS
+#define FXII_R8_MINBLOCKS 5
+#endif
+#ifndef FXII_R4_MINBLOCKS
+#define FXII_R4_MINBLOCKS 0
+#endif
+#ifndef FXII_R2_MINBLOCKS
+#define FXII_R2_MINBLOCKS 0
+#endif
 template <int G, int R, bool NUMERIC, bool SCALE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (R == 16) ? FXII_R16_MINBLOCKS : ((R == 8) ? FXII_R8_MINBLOCKS : ((R == 4) ? FXII_R4_MINBLOCKS : ((R == 2) ? FXII_R2_MINBLOCKS : 0))))
 spgemm_warp_kernel(const int64_t* __restrict__ a_ptr, const int32_t* __restrict__ a_idx, const double* __restrict__ a_val,
                    const int64_t* __restrict__ b_ptr, const int32_t* __restrict__ b_idx, const double* __restrict__ b_val,
                    const double* __restrict__ b_scale, int64_t row_begin, const int32_t* __restrict__ row_list,
