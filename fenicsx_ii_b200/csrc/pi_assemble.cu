@@ -461,15 +461,19 @@ __device__ LocateResult locate_point(const WideNode* __restrict__ nodes, const S
     const WideHit h = load_test_node(nodes, node, q);
     const int kids[4] = {h.child.x, h.child.y, h.child.z, h.child.w};
     const bool hit[4] = {(h.m01 & 0xffffu) != 0, (h.m01 >> 16) != 0, (h.m23 & 0xffffu) != 0, (h.m23 >> 16) != 0};
-    // Memory-level parallelism: everything this node leads to is requested before anything is
-    // used — the hit children and the (up to four) candidate cells are otherwise a chain of
-    // dependent cold misses.
+    // Memory-level parallelism: the hit internal children are requested before anything is used (the ones that go
+    // on the stack are otherwise cold misses when they are popped).  Prefetching the candidate cells' records as well
+    // was measured slightly slower on config 5 (row kernel 9.59 ms with both, 9.39 ms with internal children only,
+    // 9.54 ms with none, 10.08 ms with cells only): the records are used a few instructions later anyway.
+#ifndef FXII_WALK_PREFETCH
+#define FXII_WALK_PREFETCH 1  // bit 0: hit internal children, bit 1: candidate cells
+#endif
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (!hit[k]) continue;
       if (kids[k] >= 0) {
-        prefetch_l1(nodes + kids[k]);
-      } else {
+        if (FXII_WALK_PREFETCH & 1) prefetch_l1(nodes + kids[k]);
+      } else if (FXII_WALK_PREFETCH & 2) {
         const double* g = cellgeo + (HEX ? 24 : 12) * (int64_t)(~kids[k]);
         prefetch_l1(g);
         prefetch_l1(g + 11);
