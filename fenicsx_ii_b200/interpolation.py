@@ -297,14 +297,17 @@ def device_space(V, tol: float = 1.0e-8) -> DeviceSpace:
     mesh = V.mesh
     if _comm_size(mesh) > 1:
         raise NotImplementedError("distributed 3D meshes are not supported on the device path (no CPU fallback)")
+    # one handle per tol, rebuilt when the coordinates were moved (fingerprint of ~64 samples, see _geometry_token)
+    token = _geometry_token(mesh)
     cache = mesh.__dict__.setdefault("_fxii_meshes", {})
-    dmesh = cache.get(float(tol))
-    if dmesh is None:
+    dmesh, seen = cache.get(float(tol), (None, None))
+    if dmesh is None or seen != token:
         x = np.asarray(mesh.geometry.x)
-        dmesh = cache[float(tol)] = DeviceMesh(x, np.asarray(mesh.geometry.dofmap), tol)
+        dmesh = DeviceMesh(x, np.asarray(mesh.geometry.dofmap), tol)
+        cache[float(tol)] = (dmesh, token)
     spaces = V.__dict__.setdefault("_fxii_spaces", {})
     dspace = spaces.get(float(tol))
-    if dspace is None:
+    if dspace is None or dspace.mesh is not dmesh:
         n_dofs = V.dofmap.index_map.size_local + V.dofmap.index_map.num_ghosts
         dspace = spaces[float(tol)] = DeviceSpace(dmesh, np.asarray(V.dofmap.list), _element_degree(V), n_dofs)
     return dspace
@@ -429,9 +432,18 @@ def clear_interpolation_cache():
     _PI_CACHE.clear()
 
 
+def _geometry_token(mesh):
+    """A cheap fingerprint of a mesh's coordinates (address, shape and the sum of ~64 strided samples): a cached Π is
+    not reused after the mesh was moved in place.  Not a hash: changes it cannot see (and changed radius
+    functions) need ``clear_interpolation_cache``."""
+    x = np.asarray(mesh.geometry.x)
+    flat = x.reshape(-1)
+    return (x.__array_interface__["data"][0], x.shape, float(flat[:: max(1, flat.size // 64)].sum()))
+
+
 def _cache_key(V, K, red_op, tol, cells_K):
     ck = None if cells_K is None else np.ascontiguousarray(cells_K, dtype=np.int32).tobytes()
-    return (id(V), id(K), id(red_op), float(tol), ck)
+    return (id(V), id(K), id(red_op), float(tol), ck, _geometry_token(V.mesh), _geometry_token(K.mesh))
 
 
 def create_interpolation_matrix(V, K, red_op, tol: float = 1.0e-8, use_petsc: bool = False, cells_K=None,

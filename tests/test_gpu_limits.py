@@ -106,3 +106,28 @@ def test_large_pageable_uploads_take_the_staged_path_unchanged(cuda):
     pinned = torch.from_numpy(values).pin_memory().numpy()
     b = DeviceCSR.from_host(indptr, indices, pinned, (n_rows, 1 << 20))
     assert np.array_equal(b.to_host()[2], values)
+
+
+def test_moved_mesh_is_not_served_from_the_caches(cuda):
+    """the Ω handle (LBVH) and the Π cache are keyed on a fingerprint of the coordinates — after the mesh is
+    moved in place, a cached build must not be reused."""
+    from fenicsx_ii_b200 import PointwiseTrace, clear_interpolation_cache, create_interpolation_matrix
+    from fenicsx_ii_b200 import synthetic as sy
+    from fenicsx_ii_b200._lib import PointsNotFound
+    from fenicsx_ii_b200.mesh import functionspace
+
+    clear_interpolation_cache()
+    mesh = sy.kuhn_box(4, 4, 4)
+    V = functionspace(mesh, ("Lagrange", 1))
+    gamma = sy.straight_line(5)  # x = y = 0.5, inside the unit cube
+    K = functionspace(gamma, ("DG", 0))
+    op = PointwiseTrace(gamma)
+    A0, _, _ = create_interpolation_matrix(V, K, op, cache=True)
+    assert A0.device.nnz > 0
+    mesh.geometry.x[:, 0] += 10.0  # the line now lies outside the mesh
+    with pytest.raises(PointsNotFound):
+        create_interpolation_matrix(V, K, op, cache=True)
+    mesh.geometry.x[:, 0] -= 10.0
+    A1, _, _ = create_interpolation_matrix(V, K, op, cache=True)
+    assert np.array_equal(A1.indices, A0.indices) and np.array_equal(A1.data, A0.data)
+    clear_interpolation_cache()

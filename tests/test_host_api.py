@@ -63,8 +63,10 @@ def test_functionspace_standins():
     gamma = sy.straight_line(5)
     assert functionspace(gamma, ("Quadrature", 10)).element.interpolation_points.shape == (6, 1)
     assert functionspace(gamma, ("Lagrange", 2)).num_dofs == 5 + 4
+    V3 = functionspace(mesh, ("Lagrange", 3))
+    assert V3.dofmap.list.shape == (162, 20) and V3.num_dofs == 10**3  # vertices + 2 per edge + 1 per face
     with pytest.raises(NotImplementedError):
-        functionspace(mesh, ("Lagrange", 3))
+        functionspace(mesh, ("Lagrange", 4))
 
 
 def test_gamma_description_skips_identity_arrays():
