@@ -610,14 +610,17 @@ def assemble_blocks_to_host(V, K, red_op, products: ShardedProducts, host_pi, ho
     if identity is None:
         flat = k_list.reshape(-1)
         identity = bool(np.array_equal(flat, np.arange(flat.shape[0], dtype=flat.dtype)))
-    if not (contiguous and identity and _uses_stock_quadrature(red_op)) or cells.size < pi_pieces:
-        pi_pieces = 1
+    # the block path (local row numbering, no explicit row-dof list, no full-height row pointers) also serves a single
+    # block of cells — a rank's shard; only a K / operator that cannot be built block by block takes the general call
+    pi_pieces = max(1, min(int(pi_pieces), int(cells.size)))
     blocks, first_rows = [cells], None
-    if pi_pieces > 1:
+    use_blocks = bool(contiguous and identity and _uses_stock_quadrature(red_op))
+    if use_blocks:
         blocks = np.array_split(cells, pi_pieces)
-        first_rows = device_rows_block(K, red_op, blocks[0], known_contiguous=True)  # None: this K / operator cannot be built block by block
-        if first_rows is None:
-            pi_pieces = 1
+        first_rows = device_rows_block(K, red_op, blocks[0], known_contiguous=True)
+        use_blocks = first_rows is not None
+    if not use_blocks:
+        pi_pieces, blocks = 1, [cells]
     keep = []
 
     def mark3(name, done, b0, b1):
@@ -627,7 +630,7 @@ def assemble_blocks_to_host(V, K, red_op, products: ShardedProducts, host_pi, ho
     def ev():
         return torch.cuda.Event(enable_timing=marks is not None)
 
-    if pi_pieces == 1:
+    if not use_blocks:
         A, _, _ = create_interpolation_matrix(V, K, red_op, tol=tol, cells_K=cells_K)
         pi_local = A.device
         if cells_K is not None and contiguous and identity:
@@ -687,7 +690,8 @@ def assemble_blocks_to_host(V, K, red_op, products: ShardedProducts, host_pi, ho
             subs.append(sub)
             off += n
             row0 += m
-        pi_local = DeviceCSR.vstack(subs, entry_offsets=[0] * len(subs))  # pointers are already shifted
+        # (pointers are already shifted; a single block is used as it is)
+        pi_local = subs[0] if len(subs) == 1 else DeviceCSR.vstack(subs, entry_offsets=[0] * len(subs))
         nnz = off
     out = products.to_host(pi_local, host_c, host_mp, n_sub=c_pieces, copy_stream=copy_stream, marks=marks)
     out["keep"] = keep + [pi_local] + out["keep"]

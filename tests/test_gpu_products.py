@@ -378,7 +378,7 @@ def test_scale_rows_with_device_diagonal(cuda):
     np.testing.assert_array_equal(a[2], ref)
 
 
-@pytest.mark.parametrize("pi_pieces,c_pieces,subset", [(1, 1, False), (2, 4, False), (3, 2, True)])
+@pytest.mark.parametrize("pi_pieces,c_pieces,subset", [(1, 1, False), (2, 4, False), (3, 2, True), (1, 2, True)])
 def test_assemble_blocks_to_host(cuda, pi_pieces, c_pieces, subset):
     """assemble_blocks_to_host — Π in blocks of Γ cells, each downloaded while the next is built, concatenated on the
     device for the streamed products — fills the host arrays with exactly the matrices of the one-shot calls."""
