@@ -481,6 +481,10 @@ __device__ LocateResult locate_point(const WideNode* __restrict__ nodes, const S
       }
     }
     int next = -1;
+    // (Round 2, tried and rejected: sorting out the hit children first and testing the candidate cells of the node in ONE
+    // loop body — a warp runs up to four inlined copies of the leaf test below with 8-14 of its 32 lanes active in each,
+    // because which slots are leaves differs between lanes.  The converged loop spilled three times as much (592 vs 212
+    // bytes at the 64-register cap) and lost the overlap of the four copies' loads: 11.42 vs 9.41 ms on config 5.)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (!hit[k]) continue;
@@ -814,14 +818,14 @@ __device__ __forceinline__ uint32_t next_pow2(uint32_t v) {
   return v <= 1 ? 1u : 1u << (32 - __clz(v - 1));
 }
 
-// Shared body: loads the keys of matrix row `rho`, sorts, returns the number of entries.
-// smem: keys[cap]
+// Shared body: loads the n keys of matrix row `rho` into keys[] (shared memory, or a per-block buffer in global memory
+// for rows beyond the shared-memory budget), padded to the next power of two, and sorts them.
 template <bool BLOCK>
-__device__ uint32_t load_sort_row(const int64_t* __restrict__ seg_ptr, const int32_t* __restrict__ seg_rows,
-                                  const int32_t* __restrict__ coo_cols, int seg, int64_t rho, uint64_t* keys,
-                                  uint32_t cap, int tid, int nthreads) {
-  const int64_t s0 = seg_ptr[rho], s1 = seg_ptr[rho + 1];
-  const uint32_t n = (uint32_t)((s1 - s0) * seg);
+__device__ void load_sort_row(const int64_t* __restrict__ seg_ptr, const int32_t* __restrict__ seg_rows,
+                              const int32_t* __restrict__ coo_cols, int seg, int64_t rho, uint32_t n, uint64_t* keys,
+                              int tid, int nthreads) {
+  const int64_t s0 = seg_ptr[rho];
+  const uint32_t cap = n <= 2 ? 2u : next_pow2(n);  // the row's own sort size, not the launch's maximum
   for (uint32_t e = tid; e < cap; e += nthreads) {
     uint64_t key = ~0ULL;
     if (e < n) {
@@ -835,24 +839,33 @@ __device__ uint32_t load_sort_row(const int64_t* __restrict__ seg_ptr, const int
   }
   group_sync<BLOCK>();
   bitonic_sort_u64<BLOCK>(keys, cap, tid, nthreads);
-  return n;
+}
+
+// entries of matrix row rho; rows outside (n_lo, n_hi] belong to the other launch (shared- vs global-memory keys)
+__device__ __forceinline__ bool row_in_class(const int64_t* __restrict__ seg_ptr, int seg, int64_t rho, int64_t n_lo, int64_t n_hi,
+                                             uint32_t& n) {
+  const int64_t cnt = (seg_ptr[rho + 1] - seg_ptr[rho]) * seg;
+  n = (uint32_t)cnt;
+  return cnt > n_lo && cnt <= n_hi;
 }
 
 // pass 1: nnz per matrix row.  BLOCK=false: one warp per row; BLOCK=true: one block per row.
 template <bool BLOCK>
 __global__ void rows_count_kernel(const int64_t* __restrict__ seg_ptr, const int32_t* __restrict__ seg_rows,
                                   const int32_t* __restrict__ coo_cols, int seg, int64_t n_rows, uint32_t cap,
-                                  int64_t* __restrict__ row_nnz) {
+                                  uint64_t* __restrict__ g_keys, int64_t n_lo, int64_t n_hi, int64_t* __restrict__ row_nnz) {
   extern __shared__ uint64_t s_keys[];
   const int nthreads = BLOCK ? blockDim.x : 32;
   const int tid = BLOCK ? threadIdx.x : (threadIdx.x & 31);
   const int groups_per_block = BLOCK ? 1 : blockDim.x / 32;
   const int gid = BLOCK ? 0 : threadIdx.x / 32;
-  uint64_t* keys = s_keys + (size_t)gid * cap;
+  uint64_t* keys = g_keys ? g_keys + (size_t)blockIdx.x * cap : s_keys + (size_t)gid * cap;
   __shared__ int s_count;
   for (int64_t rho = (int64_t)blockIdx.x * groups_per_block + gid; rho < n_rows;
        rho += (int64_t)gridDim.x * groups_per_block) {
-    const uint32_t n = load_sort_row<BLOCK>(seg_ptr, seg_rows, coo_cols, seg, rho, keys, cap, tid, nthreads);
+    uint32_t n;
+    if (!row_in_class(seg_ptr, seg, rho, n_lo, n_hi, n)) continue;  // uniform over the group
+    load_sort_row<BLOCK>(seg_ptr, seg_rows, coo_cols, seg, rho, n, keys, tid, nthreads);
     int local = 0;
     for (uint32_t e = tid; e < n; e += nthreads) {
       const uint32_t col = (uint32_t)(keys[e] >> 32);
@@ -877,18 +890,20 @@ __global__ void rows_count_kernel(const int64_t* __restrict__ seg_ptr, const int
 template <bool BLOCK>
 __global__ void rows_fill_kernel(const int64_t* __restrict__ seg_ptr, const int32_t* __restrict__ seg_rows,
                                  const int32_t* __restrict__ coo_cols, const double* __restrict__ coo_vals, int seg,
-                                 int64_t n_rows, uint32_t cap, const int64_t* __restrict__ indptr,
-                                 int32_t* __restrict__ indices, double* __restrict__ values) {
+                                 int64_t n_rows, uint32_t cap, uint64_t* __restrict__ g_keys, int64_t n_lo, int64_t n_hi,
+                                 const int64_t* __restrict__ indptr, int32_t* __restrict__ indices, double* __restrict__ values) {
   extern __shared__ uint64_t s_keys[];
   const int nthreads = BLOCK ? blockDim.x : 32;
   const int tid = BLOCK ? threadIdx.x : (threadIdx.x & 31);
   const int groups_per_block = BLOCK ? 1 : blockDim.x / 32;
   const int gid = BLOCK ? 0 : threadIdx.x / 32;
-  uint64_t* keys = s_keys + (size_t)gid * cap;
+  uint64_t* keys = g_keys ? g_keys + (size_t)blockIdx.x * cap : s_keys + (size_t)gid * cap;
   __shared__ int s_warp_heads[32];
   for (int64_t rho = (int64_t)blockIdx.x * groups_per_block + gid; rho < n_rows;
        rho += (int64_t)gridDim.x * groups_per_block) {
-    const uint32_t n = load_sort_row<BLOCK>(seg_ptr, seg_rows, coo_cols, seg, rho, keys, cap, tid, nthreads);
+    uint32_t n;
+    if (!row_in_class(seg_ptr, seg, rho, n_lo, n_hi, n)) continue;  // uniform over the group
+    load_sort_row<BLOCK>(seg_ptr, seg_rows, coo_cols, seg, rho, n, keys, tid, nthreads);
     const int64_t s0 = seg_ptr[rho];
     const int64_t out0 = indptr[rho];
     // heads are processed in chunks of nthreads sorted positions; running head count kept uniform
@@ -1046,10 +1061,24 @@ void coo_segments_to_csr(const int32_t* row_dofs, int64_t n_point_rows, int64_t 
   FXII_CUDA(cudaStreamSynchronize(s));
   FXII_CHECK(h_bad[0] == 0, "row_dofs out of range [0, n_rows_total)");
   const uint64_t max_entries = h_max_seg * (uint64_t)seg;
-  FXII_CHECK(max_entries <= 16384, "a matrix row collects more than 16384 COO entries (unsupported)");
+  // Rows of up to kSmemRowEntries COO entries are sorted in shared memory.  Longer rows (a K dof shared by hundreds of
+  // point rows) take the same kernels with their keys in a per-block buffer in GLOBAL memory — slower, never truncated.
+  constexpr uint64_t kSmemRowEntries = 16384;
+  FXII_CHECK(max_entries < ((uint64_t)1 << 31), "a matrix row collects 2^31 or more COO entries");
   uint32_t cap = 1;
-  while (cap < max_entries) cap <<= 1;
+  while (cap < std::min(max_entries, kSmemRowEntries)) cap <<= 1;
   if (cap < 2) cap = 2;
+  const int64_t n_hi_smem = (int64_t)kSmemRowEntries;
+  uint32_t g_cap = 0;
+  int g_grid = 0;
+  DevBuf<uint64_t> g_keys;
+  if (max_entries > kSmemRowEntries) {
+    g_cap = 1;
+    while (g_cap < max_entries) g_cap <<= 1;
+    // one buffer per block; at most 2 GiB of keys in total
+    g_grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)num_sms(), ((int64_t)1 << 28) / (int64_t)g_cap));
+    g_keys.alloc((int64_t)g_grid * g_cap, s);
+  }
 
   DevBuf<int64_t> row_nnz;
   row_nnz.alloc(n_rows_total + 1, s);
@@ -1075,9 +1104,11 @@ void coo_segments_to_csr(const int32_t* row_dofs, int64_t n_point_rows, int64_t 
   FXII_CUDA(cudaEventRecord(ke[0], s));
   if (n_rows_total > 0) {
     if (block_mode)
-      { rows_count_kernel<true><<<grid, threads, smem, s>>>(seg_ptr.p, seg_rows.p, coo_cols, seg, n_rows_total, cap, row_nnz.p); FXII_LAUNCHED(1); }
+      { rows_count_kernel<true><<<grid, threads, smem, s>>>(seg_ptr.p, seg_rows.p, coo_cols, seg, n_rows_total, cap, nullptr, -1, n_hi_smem, row_nnz.p); FXII_LAUNCHED(1); }
     else
-      { rows_count_kernel<false><<<grid, threads, smem, s>>>(seg_ptr.p, seg_rows.p, coo_cols, seg, n_rows_total, cap, row_nnz.p); FXII_LAUNCHED(1); }
+      { rows_count_kernel<false><<<grid, threads, smem, s>>>(seg_ptr.p, seg_rows.p, coo_cols, seg, n_rows_total, cap, nullptr, -1, n_hi_smem, row_nnz.p); FXII_LAUNCHED(1); }
+    if (g_cap)
+      { rows_count_kernel<true><<<g_grid, 256, 0, s>>>(seg_ptr.p, seg_rows.p, coo_cols, seg, n_rows_total, g_cap, g_keys.p, n_hi_smem, INT64_MAX, row_nnz.p); FXII_LAUNCHED(1); }
     FXII_CUDA(cudaGetLastError());
   }
   FXII_CUDA(cudaEventRecord(ke[1], s));
@@ -1099,11 +1130,14 @@ void coo_segments_to_csr(const int32_t* row_dofs, int64_t n_point_rows, int64_t 
   FXII_CUDA(cudaEventRecord(ke[2], s));
   if (n_rows_total > 0 && nnz > 0) {
     if (block_mode)
-      { rows_fill_kernel<true><<<grid, threads, smem, s>>>(seg_ptr.p, seg_rows.p, coo_cols, coo_vals, seg, n_rows_total, cap,
-                                                         out->indptr.p, out->indices.p, out->values.p); FXII_LAUNCHED(1); }
+      { rows_fill_kernel<true><<<grid, threads, smem, s>>>(seg_ptr.p, seg_rows.p, coo_cols, coo_vals, seg, n_rows_total, cap, nullptr, -1,
+                                                         n_hi_smem, out->indptr.p, out->indices.p, out->values.p); FXII_LAUNCHED(1); }
     else
-      { rows_fill_kernel<false><<<grid, threads, smem, s>>>(seg_ptr.p, seg_rows.p, coo_cols, coo_vals, seg, n_rows_total, cap,
-                                                          out->indptr.p, out->indices.p, out->values.p); FXII_LAUNCHED(1); }
+      { rows_fill_kernel<false><<<grid, threads, smem, s>>>(seg_ptr.p, seg_rows.p, coo_cols, coo_vals, seg, n_rows_total, cap, nullptr, -1,
+                                                          n_hi_smem, out->indptr.p, out->indices.p, out->values.p); FXII_LAUNCHED(1); }
+    if (g_cap)
+      { rows_fill_kernel<true><<<g_grid, 256, 0, s>>>(seg_ptr.p, seg_rows.p, coo_cols, coo_vals, seg, n_rows_total, g_cap, g_keys.p,
+                                                     n_hi_smem, INT64_MAX, out->indptr.p, out->indices.p, out->values.p); FXII_LAUNCHED(1); }
     FXII_CUDA(cudaGetLastError());
   }
   FXII_CUDA(cudaEventRecord(ke[3], s));
