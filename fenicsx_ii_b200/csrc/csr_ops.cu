@@ -918,7 +918,7 @@ static bool lean_enabled() {
 static int lean_load_factor_pct() {
   static const int lf = [] {
     const char* e = getenv("FXII_SPGEMM_LF");
-    const int v = e ? atoi(e) : 70;
+    const int v = e ? atoi(e) : 50;  // config 5, after the register caps: 30/40/45/50/60/70/80 % -> 18.3/16.1/15.7/15.5/16.0/16.3/16.5 ms
     return v < 30 ? 30 : (v > 85 ? 85 : v);
   }();
   return lf;
