@@ -112,3 +112,27 @@ def test_balanced_dof_windows_by_intermediate_products():
         by_count = balanced_dof_windows(idx, n_cols, world)
         loads_c = np.array([work[a:b].sum() for a, b in by_count])
         assert loads.max() <= loads_c.max() + 1e-9
+
+
+@pytest.mark.parametrize("world,n_sub", [(1, 4), (2, 2), (4, 3), (8, 2)])
+def test_row_pieces_refine_the_rank_windows(world, n_sub):
+    """ShardedProducts.to_host cuts a rank's window of 3D dofs into `n_sub` pieces of equal work by asking for
+    world*n_sub windows: every n_sub-th cut of the fine partition must be a cut of the coarse one (same formula), so the
+    pieces of rank r tile exactly the window of rank r."""
+    from fenicsx_ii_b200.distributed import balanced_dof_windows
+
+    rng = np.random.default_rng(world * 10 + n_sub)
+    n_rows, n_cols = 4000, 900
+    lens = rng.integers(1, 12, size=n_rows)
+    indptr = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64))
+    cols = np.concatenate([np.sort(rng.choice(n_cols, size=k, replace=False)) for k in lens]).astype(np.int32)
+    # an uneven column distribution: the work is concentrated in a third of the dofs
+    cols = (cols.astype(np.int64) ** 2 // n_cols).astype(np.int32)
+    idx = torch.from_numpy(cols)
+    coarse = balanced_dof_windows(idx, n_cols, world, indptr_t=indptr)
+    fine = balanced_dof_windows(idx, n_cols, world * n_sub, indptr_t=indptr)
+    assert fine[0][0] == 0 and fine[-1][1] == n_cols
+    assert all(fine[i][1] == fine[i + 1][0] for i in range(len(fine) - 1))
+    for r in range(world):
+        mine = fine[r * n_sub:(r + 1) * n_sub]
+        assert (mine[0][0], mine[-1][1]) == coarse[r]
