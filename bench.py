@@ -339,9 +339,12 @@ def run_ours(args):
         if prod is not None:
             keep = assemble_blocks_to_host(V, K, op, prod, host["pi"], host["c"], host.get("mp"), cells_K=None if world == 1 else my_cells,
                                            pi_pieces=args.e2e_pi_pieces, c_pieces=args.e2e_pieces, copy_stream=copy_stream, marks=marks)
+        elif world == 1:
+            # Π only: host arrays in, host CSR out in ONE C call (the download rides behind the kernel, one synchronisation)
+            keep = create_interpolation_matrix(V, K, op, host_out=host["pi"])
         else:
-            A, _, _ = create_interpolation_matrix(V, K, op, cells_K=None if world == 1 else my_cells)
-            pi_local = A.device if world == 1 else A.device.row_slice(r0, r1)
+            A, _, _ = create_interpolation_matrix(V, K, op, cells_K=my_cells)
+            pi_local = A.device.row_slice(r0, r1)
             done = torch.cuda.Event()
             done.record()
             with torch.cuda.stream(copy_stream):
@@ -455,10 +458,12 @@ def run_ours(args):
                           "plan_setup_ms": prod.plan.setup_ms if prod.plan else None} if products_on else None),
             "e2e": {"value": nnz_total / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms, "timeline_ms": e2e_timeline,
-                    "note": "assemble_blocks_to_host: create_interpolation_matrix(V,K,op,cells_K=block) from pinned host Γ arrays for "
-                            f"{args.e2e_pi_pieces} blocks of Γ cells + ShardedProducts.to_host (MΠ first, C in {args.e2e_pieces} row pieces); "
-                            "Π, C and MΠ land in pinned host CSR arrays every step, every block downloaded while the next is "
-                            "computed; Ω handle (upload + LBVH) cached"},
+                    "note": ("assemble_blocks_to_host: Π built from pinned host Γ arrays in "
+                             f"{args.e2e_pi_pieces} block(s) of Γ cells + ShardedProducts.to_host (MΠ first, C in {args.e2e_pieces} row piece(s)); "
+                             "Π, C and MΠ land in pinned host CSR arrays every step, every block downloaded while the next is "
+                             "computed; Ω handle (upload + LBVH) cached") if products_on else
+                            "create_interpolation_matrix(V, K, op, host_out=pinned CSR arrays) from pinned host Γ arrays, every step; "
+                            "Ω handle (upload + LBVH) cached"},
             "e2e_cold": {"value": nnz_cold / cold_s if world == 1 else None, "unit": UNIT, "s": cold_s, "mesh_build_s": mesh_build_s,
                          "note": "FIRST call on a fresh mesh: Ω upload + LBVH build + Γ upload + Π build + CSR download (Π only); "
                                  "the reference rebuilds its tree on every call"},
