@@ -915,13 +915,20 @@ static bool lean_enabled() {
   }();
   return on;
 }
-static int lean_load_factor_pct() {
+// Table load factor (percent) of the lean kernel's numeric bins.  FXII_SPGEMM_LF: all bins (default 50);
+// FXII_SPGEMM_LF_HI: the bins of 512 slots and more (default: the same).
+static int lean_load_factor_pct(uint32_t cap) {
   static const int lf = [] {
     const char* e = getenv("FXII_SPGEMM_LF");
     const int v = e ? atoi(e) : 50;  // config 5, after the register caps: 30/40/45/50/60/70/80 % -> 18.3/16.1/15.7/15.5/16.0/16.3/16.5 ms
     return v < 30 ? 30 : (v > 85 ? 85 : v);
   }();
-  return lf;
+  static const int lf_hi = [] {
+    const char* e = getenv("FXII_SPGEMM_LF_HI");
+    const int v = e ? atoi(e) : lf;
+    return v < 30 ? 30 : (v > 85 ? 85 : v);
+  }();
+  return cap >= 512 ? lf_hi : lf;
 }
 static int ilog2(uint32_t v) {
   int l = 0;
@@ -1040,7 +1047,7 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, const double* b_scale, int64_t
     const int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(16, nl / ((int64_t)grid * W * 8)));
     const int shift = 32 - ilog2(cap);
     // register sort: R keys per lane cover 32*R >= the largest row of the bin
-    const int lf = lean_load_factor_pct();
+    const int lf = lean_load_factor_pct(cap);
     const int64_t max_nnz = (int64_t)cap * lf / 100;
     int R = 0;
     if (numeric) R = max_nnz <= 64 ? 2 : (max_nnz <= 128 ? 4 : (max_nnz <= 256 ? 8 : (max_nnz <= 512 ? 16 : 0)));
@@ -1151,9 +1158,8 @@ void spgemm(const fxii_csr* a, const fxii_csr* b, const double* b_scale, int64_t
   // bins 0..7: shared-memory tables of 64..8192 slots; bin 8: exact-size tables in global memory.
   // Lean kernel: bins 0..5 (64..2048 slots, 12 B per slot) hold nnz <= LF*cap; round-1 kernels: nnz <= cap/2.
   BinThresholds num_thr;
-  const int lf = lean_load_factor_pct();
   for (int q = 0; q < kNumBins - 1; ++q)
-    num_thr.v[q] = (lean && q <= 5) ? (int64_t)bin_cap(q) * lf / 100 : (int64_t)bin_cap(q) / 2;
+    num_thr.v[q] = (lean && q <= 5) ? (int64_t)bin_cap(q) * lean_load_factor_pct(bin_cap(q)) / 100 : (int64_t)bin_cap(q) / 2;
   RowBins num;
   bin_rows(row_nnz.p, m, num_thr, s, num);  // synchronises
   out->nnz = nnz;
