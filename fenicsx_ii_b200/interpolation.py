@@ -297,7 +297,7 @@ def device_space(V, tol: float = 1.0e-8) -> DeviceSpace:
     mesh = V.mesh
     if _comm_size(mesh) > 1:
         raise NotImplementedError("distributed 3D meshes are not supported on the device path (no CPU fallback)")
-    # one handle per tol, rebuilt when the coordinates were moved (fingerprint of ~64 samples, see _geometry_token)
+    # one handle per tol, rebuilt when the coordinates were moved (fingerprint of ~32 sampled nodes, see _geometry_token)
     token = _geometry_token(mesh)
     cache = mesh.__dict__.setdefault("_fxii_meshes", {})
     dmesh, seen = cache.get(float(tol), (None, None))
@@ -433,12 +433,13 @@ def clear_interpolation_cache():
 
 
 def _geometry_token(mesh):
-    """A cheap fingerprint of a mesh's coordinates (address, shape and the sum of ~64 strided samples): a cached Π is
+    """A cheap fingerprint of a mesh's coordinates (address, shape and a weighted sum over ~32 sampled nodes): a cached Π is
     not reused after the mesh was moved in place.  Not a hash: changes it cannot see (and changed radius
     functions) need ``clear_interpolation_cache``."""
     x = np.asarray(mesh.geometry.x)
-    flat = x.reshape(-1)
-    return (x.__array_interface__["data"][0], x.shape, float(flat[:: max(1, flat.size // 64)].sum()))
+    rows = x.reshape(x.shape[0], -1)[:: max(1, x.shape[0] // 32)]  # ~32 nodes, every coordinate of each
+    w = 1.0 + 0.25 * np.arange(rows.shape[1])                      # columns weighted apart: a swap of axes is seen too
+    return (x.__array_interface__["data"][0], x.shape, float((rows * w).sum()))
 
 
 def _cache_key(V, K, red_op, tol, cells_K):

@@ -104,3 +104,40 @@ def test_gamma_description_skips_identity_arrays():
     np.testing.assert_array_equal(args[4], Kp.dofmap.list.reshape(-1))
     # generic operators have no device description
     assert device_rows(Kq, fx.MappedRestriction(gamma, lambda x: x), args_only=True) is None
+
+
+def test_geometry_token_follows_in_place_moves():
+    """The Ω handle and the Π cache are keyed on a fingerprint of the coordinates (interpolation._geometry_token)."""
+    from fenicsx_ii_b200.interpolation import _cache_key, _geometry_token
+
+    mesh, V = small_cfg(3, 3, 3)
+    gamma = sy.straight_line(5)
+    K = functionspace(gamma, ("DG", 0))
+    t0, k0 = _geometry_token(mesh), _cache_key(V, K, None, 1e-8, None)
+    assert _geometry_token(mesh) == t0 and _cache_key(V, K, None, 1e-8, None) == k0
+    mesh.geometry.x[:, 1] += 0.25
+    assert _geometry_token(mesh) != t0 and _cache_key(V, K, None, 1e-8, None) != k0
+    mesh.geometry.x[:, 1] -= 0.25
+    assert _geometry_token(mesh) == t0
+    gamma.geometry.x[:, 2] *= 0.5
+    assert _cache_key(V, K, None, 1e-8, None) != k0
+
+
+def test_block_rows_are_refused_where_blocks_of_cells_are_not_blocks_of_rows():
+    """interpolation.device_rows_block returns None — before touching the device — for a K with shared dofs, for a
+    non-contiguous block of cells and for an operator that overrides the plugin contract; assemble_blocks_to_host then
+    builds Π in one general call."""
+    from fenicsx_ii_b200 import Circle, PointwiseTrace
+    from fenicsx_ii_b200.interpolation import device_rows_block
+
+    gamma = sy.straight_line(9)
+    cells = np.arange(2, 6, dtype=np.int32)
+    assert device_rows_block(functionspace(gamma, ("Lagrange", 1)), PointwiseTrace(gamma), cells) is None       # shared dofs
+    assert device_rows_block(functionspace(gamma, ("DG", 1)), PointwiseTrace(gamma), np.array([1, 3, 4], dtype=np.int32)) is None
+
+    class MyCircle(Circle):
+        def compute_quadrature(self, cells, reference_points):  # a generic operator now: host points
+            return super().compute_quadrature(cells, reference_points)
+
+    assert device_rows_block(functionspace(gamma, ("Quadrature", 4)), MyCircle(gamma, 0.1, degree=5), cells) is None
+    assert device_rows_block(functionspace(gamma, ("Quadrature", 4)), Circle(gamma, 0.1, degree=5), np.zeros(0, dtype=np.int32)) is None
