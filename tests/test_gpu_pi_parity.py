@@ -463,3 +463,32 @@ def test_p3_circle_trace_of_polynomials(cuda, family, degree, case):
     expect = np.zeros(K.num_dofs)
     expect[K.dofmap.list.reshape(-1)] = pif(z.reshape(-1))
     np.testing.assert_allclose(b, expect, rtol=1e-12, atol=1e-12)
+
+
+def test_p3_parity_on_an_unstructured_mesh(cuda):
+    """P3 on a Delaunay mesh: the edges of a cell run with and against their reference direction, so the two dofs of an
+    edge appear in both orders in the dofmap — ownership, pattern and values must still match the oracle."""
+    from scipy.spatial import Delaunay
+
+    from fenicsx_ii_b200.mesh import Mesh
+
+    rng = np.random.default_rng(5)
+    g = np.linspace(0.0, 1.0, 5)
+    pts = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(-1, 3)
+    inner = (pts > 0).all(axis=1) & (pts < 1).all(axis=1)
+    pts[inner] += rng.uniform(-0.06, 0.06, size=(int(inner.sum()), 3))
+    tets = Delaunay(pts).simplices.astype(np.int32)
+    vol = np.einsum("ij,ij->i", np.cross(pts[tets[:, 1]] - pts[tets[:, 0]], pts[tets[:, 2]] - pts[tets[:, 0]]), pts[tets[:, 3]] - pts[tets[:, 0]])
+    tets = np.ascontiguousarray(tets[np.abs(vol) > 1e-10])
+    mesh = Mesh(pts, tets, tdim=3)
+    V = functionspace(mesh, ("Lagrange", 3))
+    flipped = (tets[:, 0] > tets[:, 1]).mean()
+    assert 0.05 < flipped < 0.95  # both edge orientations occur
+    gamma = sy.polyline_network(30, 0.2, n_lines=3, lo=0.25, hi=0.75)
+    K = functionspace(gamma, ("DG", 1))
+    op = make_operator("circle", gamma, 0.05, 7)
+    A, _, _ = create_interpolation_matrix(V, K, op)
+    ref = oracle_pi(V, K, gamma, "circle", 0.05, 7)
+    cell, _ = A.rows.diagnostics()
+    np.testing.assert_array_equal(cell, ref["cell"])
+    assert_csr_parity((A.indptr, A.indices, A.data), ref)
